@@ -1,0 +1,268 @@
+"""ctypes binding over libwhisper_b200.so — the only way Python (tests, bench, smoke) reaches the
+product: everything goes through the C ABI of include/whisper_b200.h, exactly as a Rust host
+would.  Fails loudly when the library is missing or has no GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .weights import ModelCfg
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwhisper_b200.so")
+
+WB_PREC_FP32, WB_PREC_BF16 = 0, 1
+N_FRAMES = 3000
+
+
+class WbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libwhisper_b200 error {code}: {msg}")
+        self.code = code
+
+
+class wb_model_cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mels", "d_model", "n_heads", "ffn_dim", "enc_layers", "dec_layers",
+                                         "vocab", "n_audio_ctx", "n_text_ctx", "precision", "max_batch", "max_chunks")]
+    _fields_.append(("seed", C.c_uint64))
+
+
+class wb_timing(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("mel_ms", "encoder_ms", "cross_kv_ms", "decode_ms", "h2d_ms", "d2h_ms")]
+    _fields_ += [(n, C.c_int32) for n in ("mel_launches", "encoder_launches", "decode_launches", "decode_steps")]
+
+
+_lib = None
+i64p, i32p, f32p, f64p = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
+
+
+def lib():
+    """Load the shared library (no GPU needed to load; compute calls need one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WbError(-2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no Python/CPU fallback for the hot path)")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, ci = C.c_void_p, C.c_char_p, C.c_int
+    L.wb_last_error.restype = cp
+    sig = {
+        "wb_default_cfg": [C.POINTER(wb_model_cfg), cp],
+        "wb_create": [C.POINTER(vp), ci, C.POINTER(wb_model_cfg), cp],
+        "wb_get_cfg": [vp, C.POINTER(wb_model_cfg)],
+        "wb_get_timing": [vp, C.POINTER(wb_timing)],
+        "wb_set_debug": [vp, ci],
+        "wb_get_tensor": [vp, cp, f32p, C.c_int64],
+        "wb_log_mel": [vp, f32p, i64p, ci, C.c_int64, C.c_int64, f32p, i64p, C.POINTER(ci)],
+        "wb_upload_pcm": [vp, f32p, i64p, ci, C.c_int64, C.c_int64, C.POINTER(ci)],
+        "wb_run_log_mel": [vp],
+        "wb_get_chunks": [vp, i32p, i64p, ci],
+        "wb_get_chunk_mel": [vp, ci, ci, f32p],
+        "wb_encode": [vp, f32p, ci, ci, f32p],
+        "wb_get_encoder_debug": [vp, cp, f32p, C.c_int64],
+        "wb_greedy_decode": [vp, ci, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, i64p, f32p],
+        "wb_transcribe_batch": [vp, f32p, i64p, ci, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, i32p, ci, C.POINTER(ci)],
+        "wb_transcribe_resident": [vp, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, ci],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = ci
+    L.wb_destroy.argtypes = [vp]
+    L.wb_destroy.restype = None
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise WbError(rc, lib().wb_last_error().decode("utf-8", "replace"))
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(f32p)
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, (a.ctypes.data_as(i64p) if a.size else None)
+
+
+def default_cfg(name: str = "base", precision: int = WB_PREC_FP32, max_batch: int | None = None,
+                max_chunks: int | None = None, seed: int = 0) -> wb_model_cfg:
+    cfg = wb_model_cfg()
+    _chk(lib().wb_default_cfg(C.byref(cfg), name.encode()))
+    cfg.precision = precision
+    if max_batch is not None:
+        cfg.max_batch = max_batch
+        cfg.max_chunks = max(cfg.max_chunks, max_batch)
+    if max_chunks is not None:
+        cfg.max_chunks = max_chunks
+    cfg.seed = seed
+    return cfg
+
+
+def model_cfg_of(cfg: wb_model_cfg) -> ModelCfg:
+    return ModelCfg(cfg.n_mels, cfg.d_model, cfg.n_heads, cfg.ffn_dim, cfg.enc_layers, cfg.dec_layers, cfg.vocab,
+                    cfg.n_audio_ctx, cfg.n_text_ctx)
+
+
+class Whisper:
+    """One context per GPU.  Mirrors the reference's (encoder, decoder, decoder_with_past) session
+    triple built at main.rs:1103-1108."""
+
+    def __init__(self, cfg: wb_model_cfg | None = None, device: int = 0, weights_path: str | None = None):
+        self.L = lib()
+        self.cfg = cfg if cfg is not None else default_cfg()
+        self.h = C.c_void_p()
+        _chk(self.L.wb_create(C.byref(self.h), device, C.byref(self.cfg), weights_path.encode() if weights_path else None))
+
+    def close(self):
+        if self.h:
+            self.L.wb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- group 1 ----
+    @staticmethod
+    def _pack(clips):
+        if isinstance(clips, np.ndarray) and clips.ndim == 2:
+            n, ln = clips.shape
+            return np.ascontiguousarray(clips, np.float32).reshape(-1), np.arange(n + 1, dtype=np.int64) * ln
+        offs = np.zeros(len(clips) + 1, np.int64)
+        offs[1:] = np.cumsum([len(c) for c in clips])
+        flat = np.concatenate([np.asarray(c, np.float32) for c in clips]) if len(clips) else np.zeros(0, np.float32)
+        return flat, offs
+
+    def log_mel(self, clips, chunk_len: int = 0, step: int = 0, want_mel: bool = True):
+        """-> (list of [80, nf_i] arrays or None, n_chunks).  whisper_log_mel_80 per file."""
+        flat, offs = self._pack(clips)
+        n_files = len(offs) - 1
+        nfr = np.zeros(n_files, np.int64)
+        nch = C.c_int(0)
+        # frame count is floor(N/160) (>=1): size the host buffer first
+        lens = np.diff(offs)
+        nf = np.maximum(lens // 160, 1)
+        out = np.empty(int(nf.sum()) * 80, np.float32) if want_mel else None
+        _chk(self.L.wb_log_mel(self.h, flat.ctypes.data_as(f32p), offs.ctypes.data_as(i64p), n_files, chunk_len, step,
+                               out.ctypes.data_as(f32p) if want_mel else None, nfr.ctypes.data_as(i64p), C.byref(nch)))
+        assert np.array_equal(nfr, nf), (nfr, nf)
+        mels = None
+        if want_mel:
+            mels, o = [], 0
+            for k in nf:
+                mels.append(out[o:o + 80 * int(k)].reshape(80, int(k)))
+                o += 80 * int(k)
+        return mels, nch.value
+
+    def upload_pcm(self, clips, chunk_len: int = 0, step: int = 0) -> int:
+        flat, offs = self._pack(clips)
+        nch = C.c_int(0)
+        _chk(self.L.wb_upload_pcm(self.h, flat.ctypes.data_as(f32p), offs.ctypes.data_as(i64p), len(offs) - 1, chunk_len, step, C.byref(nch)))
+        return nch.value
+
+    def run_log_mel(self):
+        _chk(self.L.wb_run_log_mel(self.h))
+
+    def chunks(self, n):
+        fi, sp = np.zeros(n, np.int32), np.zeros(n, np.int64)
+        _chk(self.L.wb_get_chunks(self.h, fi.ctypes.data_as(i32p), sp.ctypes.data_as(i64p), n))
+        return fi, sp
+
+    def chunk_mel(self, begin, n):
+        out = np.empty((n, 80, N_FRAMES), np.float32)
+        _chk(self.L.wb_get_chunk_mel(self.h, begin, n, out.ctypes.data_as(f32p)))
+        return out
+
+    # ---- group 2 ----
+    def encode(self, mel=None, chunk_begin: int = 0, B: int | None = None, want_hidden: bool = True):
+        c = self.cfg
+        if mel is not None:
+            mel, mp = _f32(mel)
+            B = mel.shape[0]
+            assert mel.shape == (B, c.n_mels, N_FRAMES), mel.shape
+        else:
+            mp = None
+        out = np.empty((B, c.n_audio_ctx, c.d_model), np.float32) if want_hidden else None
+        _chk(self.L.wb_encode(self.h, mp, chunk_begin, B, out.ctypes.data_as(f32p) if want_hidden else None))
+        return out
+
+    def set_debug(self, on=True):
+        _chk(self.L.wb_set_debug(self.h, int(on)))
+
+    def encoder_debug(self, what: str, B: int):
+        c = self.cfg
+        out = np.empty((B, c.n_audio_ctx, c.d_model), np.float32)
+        _chk(self.L.wb_get_encoder_debug(self.h, what.encode(), out.ctypes.data_as(f32p), out.size))
+        return out
+
+    # ---- group 3 ----
+    def greedy_decode(self, B, prompt, max_new_tokens, eot, suppress=(), begin_suppress=(), forced=None,
+                      want_logits=False):
+        c = self.cfg
+        prompt, pp = _i64(prompt)
+        sup, sp = _i64(list(suppress))
+        bsup, bp = _i64(list(begin_suppress))
+        mn = max(1, max_new_tokens)
+        toks = np.full((B, len(prompt) + mn), -1, np.int64)
+        lens = np.zeros(B, np.int32)
+        fp = None
+        if forced is not None:
+            forced = np.ascontiguousarray(forced, np.int64)
+            assert forced.shape == (B, mn)
+            fp = forced.ctypes.data_as(i64p)
+        logits = np.empty((B, mn, c.vocab), np.float32) if want_logits else None
+        _chk(self.L.wb_greedy_decode(self.h, B, pp, len(prompt), max_new_tokens, eot, sp, len(sup), bp, len(bsup),
+                                     toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p), fp,
+                                     logits.ctypes.data_as(f32p) if want_logits else None))
+        seqs = [toks[b, :lens[b]].tolist() for b in range(B)]
+        return (seqs, logits) if want_logits else seqs
+
+    # ---- fused ----
+    def transcribe_batch(self, clips, prompt, max_new_tokens, eot, suppress=(), begin_suppress=()):
+        """Host PCM in -> per-chunk token lists + file index per chunk (H2D and D2H inside)."""
+        flat, offs = self._pack(clips)
+        prompt, pp = _i64(prompt)
+        sup, sp = _i64(list(suppress))
+        bsup, bp = _i64(list(begin_suppress))
+        cap = self.cfg.max_chunks
+        stride = len(prompt) + max(1, max_new_tokens)
+        toks = np.full((cap, stride), -1, np.int64)
+        lens, fidx = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        nch = C.c_int(0)
+        _chk(self.L.wb_transcribe_batch(self.h, flat.ctypes.data_as(f32p), offs.ctypes.data_as(i64p), len(offs) - 1,
+                                        pp, len(prompt), max_new_tokens, eot, sp, len(sup), bp, len(bsup),
+                                        toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p), fidx.ctypes.data_as(i32p),
+                                        cap, C.byref(nch)))
+        n = nch.value
+        return [toks[i, :lens[i]].tolist() for i in range(n)], fidx[:n].copy()
+
+    def transcribe_resident(self, n_chunks, prompt, max_new_tokens, eot, suppress=(), begin_suppress=()):
+        prompt, pp = _i64(prompt)
+        sup, sp = _i64(list(suppress))
+        bsup, bp = _i64(list(begin_suppress))
+        stride = len(prompt) + max(1, max_new_tokens)
+        toks = np.full((n_chunks, stride), -1, np.int64)
+        lens = np.zeros(n_chunks, np.int32)
+        _chk(self.L.wb_transcribe_resident(self.h, pp, len(prompt), max_new_tokens, eot, sp, len(sup), bp, len(bsup),
+                                           toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p), n_chunks))
+        return [toks[i, :lens[i]].tolist() for i in range(n_chunks)]
+
+    def timing(self) -> dict:
+        t = wb_timing()
+        _chk(self.L.wb_get_timing(self.h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in wb_timing._fields_}
+
+    def tensor(self, name: str, shape) -> np.ndarray:
+        out = np.empty(shape, np.float32)
+        _chk(self.L.wb_get_tensor(self.h, name.encode(), out.ctypes.data_as(f32p), out.size))
+        return out

@@ -1,0 +1,382 @@
+// api.cpp — the extern "C" surface of include/whisper_b200.h over the CUDA path.
+// No exception crosses the boundary: every entry point converts to a status code + message.
+#include <cstring>
+#include <mutex>
+
+#include "ctx.h"
+
+static thread_local std::string g_err;
+void wb_set_error(const std::string& msg) { g_err = msg; }
+
+#define WB_TRY try {
+#define WB_CATCH                                                             \
+    }                                                                        \
+    catch (const WbError& e) { wb_set_error(e.what()); return e.code; }      \
+    catch (const std::exception& e) { wb_set_error(e.what()); return WB_EINVAL; } \
+    return WB_OK;
+
+namespace {
+
+void require_ctx(const wb_ctx* c) { WB_REQUIRE(c != nullptr, WB_EINVAL, "null wb_ctx"); }
+
+// Stage file list + chunk table on the device (wb_upload_pcm).
+void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files, int64_t chunk_len,
+                int64_t step, int* n_chunks_out) {
+    WB_REQUIRE(pcm && offsets && n_files > 0, WB_EINVAL, "wb_upload_pcm: bad arguments");
+    WB_REQUIRE(ctx->cfg.n_mels == 80, WB_EINVAL, "log-mel kernel implements the reference's 80-bin frontend only");
+    if (chunk_len <= 0) chunk_len = WB_CHUNK_SAMPLES;
+    if (step <= 0) step = 400000;
+    MelState& s = ctx->mel;
+    s.raw_valid = false;
+    s.n_files = n_files;
+    s.h_file_off.assign(offsets, offsets + n_files + 1);
+    s.h_frame_off.assign(n_files + 1, 0);
+    s.h_tile_off.assign(n_files + 1, 0);
+    s.h_chunks.clear();
+    s.h_chunk_pos.clear();
+    for (int i = 0; i < n_files; ++i) {
+        const int64_t n = offsets[i + 1] - offsets[i];
+        WB_REQUIRE(n > 0, WB_EINVAL, "Empty audio (file %d)", i);                      // main.rs:414-416
+        const int64_t nf = mel_n_frames(n);
+        s.h_frame_off[i + 1] = s.h_frame_off[i] + nf;
+        s.h_tile_off[i + 1] = s.h_tile_off[i] + (int)ceil_div64(nf, 32);
+        int64_t pos = 0;                                                               // main.rs:875-882
+        while (pos < n) {
+            const int64_t end = pos + chunk_len < n ? pos + chunk_len : n;
+            s.h_chunks.push_back(MelChunk{i, (int)(pos / 160)});
+            s.h_chunk_pos.push_back(pos);
+            if (end == n) break;
+            pos += step;
+        }
+    }
+    s.n_chunks = (int)s.h_chunks.size();
+    s.total_frames = s.h_frame_off[n_files];
+    s.total_tiles = s.h_tile_off[n_files];
+    WB_REQUIRE(s.n_chunks <= ctx->cfg.max_chunks, WB_ECAP, "%d chunks exceed max_chunks %d", s.n_chunks, ctx->cfg.max_chunks);
+    const int64_t total = offsets[n_files] - offsets[0];
+    WB_REQUIRE(offsets[0] == 0, WB_EINVAL, "offsets[0] must be 0");
+    s.pcm.reserve((size_t)total);
+    s.file_off.reserve(n_files + 1);
+    s.frame_off.reserve(n_files + 1);
+    s.tile_off.reserve(n_files + 1);
+    s.fmax.reserve(n_files);
+    s.raw.reserve((size_t)s.total_frames * 80);
+    s.chunks.reserve(s.n_chunks);
+    cudaStream_t st = ctx->stream;
+    CudaEvent e0, e1;
+    CUDA_CHECK(cudaEventRecord(e0.e, st));
+    CUDA_CHECK(cudaMemcpyAsync(s.pcm.p, pcm, sizeof(float) * (size_t)total, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(s.file_off.p, s.h_file_off.data(), sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(s.frame_off.p, s.h_frame_off.data(), sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(s.tile_off.p, s.h_tile_off.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(s.chunks.p, s.h_chunks.data(), sizeof(MelChunk) * s.n_chunks, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaEventRecord(e1.e, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.h2d_ms, e0.e, e1.e));
+    if (n_chunks_out) *n_chunks_out = s.n_chunks;
+}
+
+void run_log_mel(wb_ctx* ctx, bool sync) {
+    MelState& s = ctx->mel;
+    WB_REQUIRE(s.n_files > 0, WB_ESTATE, "wb_run_log_mel before wb_upload_pcm");
+    ctx->timing.mel_launches = 0;
+    CUDA_CHECK(cudaEventRecord(ctx->ev0.e, ctx->stream));
+    mel_launch_raw(ctx);
+    mel_launch_chunks(ctx, 0, s.n_chunks, ctx->enc.mel_tm.p);
+    CUDA_CHECK(cudaEventRecord(ctx->ev1.e, ctx->stream));
+    s.raw_valid = true;
+    if (sync) {
+        CUDA_CHECK(cudaEventSynchronize(ctx->ev1.e));
+        CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.mel_ms, ctx->ev0.e, ctx->ev1.e));
+    }
+}
+
+DecodeParams make_params(int B, const int64_t* prompt, int prompt_len, int max_new, int64_t eot,
+                         const int64_t* sup, int ns, const int64_t* bsup, int nb, const int64_t* forced,
+                         bool want_logits) {
+    WB_REQUIRE(prompt && prompt_len > 0, WB_EINVAL, "empty prompt");
+    WB_REQUIRE((ns == 0 || sup) && (nb == 0 || bsup), WB_EINVAL, "null suppress list");
+    DecodeParams p{};
+    p.B = B; p.prompt = prompt; p.prompt_len = prompt_len; p.max_new = max_new; p.eot = (int)eot;
+    p.suppress = sup; p.n_suppress = ns; p.begin_suppress = bsup; p.n_begin_suppress = nb;
+    p.forced = forced; p.want_logits = want_logits;
+    return p;
+}
+
+void transcribe_resident(wb_ctx* ctx, const DecodeParams& proto, int64_t* tokens_out, int32_t* lens_out, int cap_chunks) {
+    MelState& s = ctx->mel;
+    WB_REQUIRE(s.n_chunks <= cap_chunks, WB_ECAP, "output capacity %d < %d chunks", cap_chunks, s.n_chunks);
+    run_log_mel(ctx, true);
+    const int stride = proto.prompt_len + (proto.max_new < 1 ? 1 : proto.max_new);
+    const size_t chunk_elems = (size_t)(WB_N_FRAMES + 2) * ctx->cfg.n_mels * ctx->esz();
+    float enc_ms = 0, ckv_ms = 0, dec_ms = 0;
+    int dl = 0, el = 0, ds = 0;
+    for (int c0 = 0; c0 < s.n_chunks; c0 += ctx->cfg.max_batch) {
+        const int B = s.n_chunks - c0 < ctx->cfg.max_batch ? s.n_chunks - c0 : ctx->cfg.max_batch;
+        encoder_forward(ctx, (const char*)ctx->enc.mel_tm.p + (size_t)c0 * chunk_elems, B);
+        DecodeParams p = proto;
+        p.B = B;
+        decoder_run(ctx, p);
+        decoder_fetch(ctx, p, tokens_out + (size_t)c0 * stride, lens_out + c0, nullptr);
+        enc_ms += ctx->timing.encoder_ms; ckv_ms += ctx->timing.cross_kv_ms; dec_ms += ctx->timing.decode_ms;
+        dl += ctx->timing.decode_launches; el += ctx->timing.encoder_launches; ds += ctx->timing.decode_steps;
+    }
+    ctx->timing.encoder_ms = enc_ms; ctx->timing.cross_kv_ms = ckv_ms; ctx->timing.decode_ms = dec_ms;
+    ctx->timing.decode_launches = dl; ctx->timing.encoder_launches = el; ctx->timing.decode_steps = ds;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wb_last_error(void) { return g_err.c_str(); }
+
+int wb_default_cfg(wb_model_cfg* cfg, const char* name) {
+    WB_TRY
+    WB_REQUIRE(cfg && name, WB_EINVAL, "wb_default_cfg: null argument");
+    std::memset(cfg, 0, sizeof(*cfg));
+    const std::string n(name);
+    if (n == "base") *cfg = wb_model_cfg{80, 512, 8, 2048, 6, 6, 51865, 1500, 448, WB_PREC_FP32, 32, 64, 0};
+    else if (n == "large-v3") *cfg = wb_model_cfg{128, 1280, 20, 5120, 32, 32, 51866, 1500, 448, WB_PREC_FP32, 16, 16, 0};
+    else if (n == "toy") *cfg = wb_model_cfg{80, 128, 2, 256, 2, 2, 1031, 1500, 448, WB_PREC_FP32, 4, 8, 0};
+    else WB_THROW(WB_EINVAL, "unknown model name '%s' (base | large-v3 | toy)", name);
+    WB_CATCH
+}
+
+int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* weights_path) {
+    wb_ctx* ctx = nullptr;
+    try {
+        WB_REQUIRE(out && cfg, WB_EINVAL, "wb_create: null argument");
+        *out = nullptr;
+        int n_dev = 0;
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        WB_REQUIRE(e == cudaSuccess && n_dev > 0, WB_ECUDA,
+                   "no CUDA device available (%s): libwhisper_b200 has no CPU fallback", cudaGetErrorString(e));
+        WB_REQUIRE(device >= 0 && device < n_dev, WB_EINVAL, "device %d out of range (%d devices)", device, n_dev);
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop{};
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        WB_REQUIRE(prop.major == 10, WB_ECUDA, "device %s is sm_%d%d; this library is built for sm_100a (B200) only",
+                   prop.name, prop.major, prop.minor);
+        WB_REQUIRE(cfg->precision == WB_PREC_FP32 || cfg->precision == WB_PREC_BF16, WB_EINVAL, "bad precision");
+        WB_REQUIRE(cfg->max_batch >= 1 && cfg->max_chunks >= cfg->max_batch, WB_EINVAL, "need max_chunks >= max_batch >= 1");
+        ctx = new wb_ctx();
+        ctx->cfg = *cfg;
+        ctx->device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        mel_build_tables(ctx->mel_tables);
+        CUDA_CHECK(cudaMalloc(&ctx->mel_tables_dev, sizeof(MelTables)));
+        CUDA_CHECK(cudaMemcpy(ctx->mel_tables_dev, &ctx->mel_tables, sizeof(MelTables), cudaMemcpyHostToDevice));
+        weights_init(ctx, weights_path);
+        encoder_alloc(ctx);
+        decoder_alloc(ctx);
+        const char* dbg = getenv("WB_DEBUG");
+        ctx->debug = dbg && dbg[0] == '1';
+        CUDA_CHECK(cudaDeviceSynchronize());
+        *out = ctx;
+        return WB_OK;
+    } catch (const WbError& e) {
+        wb_set_error(e.what());
+        if (ctx) wb_destroy(ctx);
+        return e.code;
+    } catch (const std::exception& e) {
+        wb_set_error(e.what());
+        if (ctx) wb_destroy(ctx);
+        return WB_EINVAL;
+    }
+}
+
+void wb_destroy(wb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    weights_free(ctx);
+    if (ctx->mel_tables_dev) cudaFree(ctx->mel_tables_dev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int wb_get_cfg(const wb_ctx* ctx, wb_model_cfg* out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(out, WB_EINVAL, "null out");
+    *out = ctx->cfg;
+    WB_CATCH
+}
+
+int wb_get_timing(const wb_ctx* ctx, wb_timing* out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(out, WB_EINVAL, "null out");
+    *out = ctx->timing;
+    WB_CATCH
+}
+
+int wb_set_debug(wb_ctx* ctx, int on) {
+    WB_TRY
+    require_ctx(ctx);
+    ctx->debug = on != 0;
+    WB_CATCH
+}
+
+int wb_get_tensor(wb_ctx* ctx, const char* name, float* out, int64_t n) {
+    WB_TRY
+    require_ctx(ctx);
+    auto it = ctx->w.host.find(name ? name : "");
+    WB_REQUIRE(it != ctx->w.host.end(), WB_EINVAL, "unknown tensor '%s'", name ? name : "");
+    WB_REQUIRE((int64_t)it->second.size() == n, WB_EINVAL, "tensor '%s' has %zu elements, caller asked for %lld",
+               name, it->second.size(), (long long)n);
+    std::memcpy(out, it->second.data(), sizeof(float) * (size_t)n);
+    WB_CATCH
+}
+
+int wb_upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files, int64_t chunk_len,
+                  int64_t step, int* n_chunks_out) {
+    WB_TRY
+    require_ctx(ctx);
+    upload_pcm(ctx, pcm, offsets, n_files, chunk_len, step, n_chunks_out);
+    WB_CATCH
+}
+
+int wb_run_log_mel(wb_ctx* ctx) {
+    WB_TRY
+    require_ctx(ctx);
+    run_log_mel(ctx, true);
+    WB_CATCH
+}
+
+int wb_log_mel(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files, int64_t chunk_len,
+               int64_t step, float* mel_out, int64_t* n_frames_out, int* n_chunks_out) {
+    WB_TRY
+    require_ctx(ctx);
+    upload_pcm(ctx, pcm, offsets, n_files, chunk_len, step, n_chunks_out);
+    run_log_mel(ctx, true);
+    MelState& s = ctx->mel;
+    if (n_frames_out)
+        for (int i = 0; i < n_files; ++i) n_frames_out[i] = s.h_frame_off[i + 1] - s.h_frame_off[i];
+    if (mel_out) {
+        s.export_buf.reserve((size_t)s.total_frames * 80);
+        for (int i = 0; i < n_files; ++i) {
+            const int64_t nf = s.h_frame_off[i + 1] - s.h_frame_off[i];
+            mel_launch_export(ctx, i, 0, nf, s.export_buf.p + s.h_frame_off[i] * 80);
+        }
+        CudaEvent e0, e1;
+        CUDA_CHECK(cudaEventRecord(e0.e, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(mel_out, s.export_buf.p, sizeof(float) * (size_t)s.total_frames * 80, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaEventRecord(e1.e, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.d2h_ms, e0.e, e1.e));
+    }
+    WB_CATCH
+}
+
+int wb_get_chunks(wb_ctx* ctx, int32_t* file_idx, int64_t* sample_pos, int cap) {
+    WB_TRY
+    require_ctx(ctx);
+    MelState& s = ctx->mel;
+    WB_REQUIRE(cap >= s.n_chunks, WB_ECAP, "capacity %d < %d chunks", cap, s.n_chunks);
+    for (int i = 0; i < s.n_chunks; ++i) {
+        if (file_idx) file_idx[i] = s.h_chunks[i].file;
+        if (sample_pos) sample_pos[i] = s.h_chunk_pos[i];
+    }
+    WB_CATCH
+}
+
+int wb_get_chunk_mel(wb_ctx* ctx, int chunk_begin, int n, float* out) {
+    WB_TRY
+    require_ctx(ctx);
+    MelState& s = ctx->mel;
+    WB_REQUIRE(s.raw_valid, WB_ESTATE, "no log-mel resident");
+    WB_REQUIRE(out && chunk_begin >= 0 && n >= 0 && chunk_begin + n <= s.n_chunks, WB_EINVAL, "chunk range out of bounds");
+    s.export_buf.reserve((size_t)n * 80 * WB_N_FRAMES);
+    for (int i = 0; i < n; ++i) {
+        const MelChunk& ch = s.h_chunks[chunk_begin + i];
+        mel_launch_export(ctx, ch.file, ch.frame_start, WB_N_FRAMES, s.export_buf.p + (size_t)i * 80 * WB_N_FRAMES);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, s.export_buf.p, sizeof(float) * (size_t)n * 80 * WB_N_FRAMES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    WB_CATCH
+}
+
+int wb_encode(wb_ctx* ctx, const float* mel, int chunk_begin, int B, float* hidden_out) {
+    WB_TRY
+    require_ctx(ctx);
+    const wb_model_cfg& c = ctx->cfg;
+    WB_REQUIRE(B >= 1 && B <= c.max_batch, WB_ECAP, "batch %d exceeds max_batch %d", B, c.max_batch);
+    const void* in;
+    if (mel) {
+        const size_t n = (size_t)B * c.n_mels * WB_N_FRAMES;
+        CUDA_CHECK(cudaMemcpyAsync(ctx->enc.in_stage.p, mel, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+        mel_launch_transpose_in(ctx, ctx->enc.in_stage.p, ctx->enc.in_tm.p, B);
+        in = ctx->enc.in_tm.p;
+    } else {
+        WB_REQUIRE(ctx->mel.raw_valid, WB_ESTATE, "wb_encode(mel=NULL) needs a prior wb_log_mel");
+        WB_REQUIRE(chunk_begin >= 0 && chunk_begin + B <= ctx->mel.n_chunks, WB_EINVAL, "chunk range out of bounds");
+        in = (const char*)ctx->enc.mel_tm.p + (size_t)chunk_begin * (WB_N_FRAMES + 2) * c.n_mels * ctx->esz();
+    }
+    encoder_forward(ctx, in, B);
+    if (hidden_out) {
+        CUDA_CHECK(cudaMemcpyAsync(hidden_out, ctx->enc.out.p, sizeof(float) * (size_t)B * c.n_audio_ctx * c.d_model,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    WB_CATCH
+}
+
+int wb_get_encoder_debug(wb_ctx* ctx, const char* what, float* out, int64_t n) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(ctx->debug, WB_ESTATE, "debug capture is off (wb_set_debug or WB_DEBUG=1)");
+    const std::string w(what ? what : "");
+    DevBuf<float>* src = w == "stem" ? &ctx->enc.dbg_stem : w == "layer0" ? &ctx->enc.dbg_layer0 : nullptr;
+    WB_REQUIRE(src && src->p, WB_EINVAL, "unknown debug tensor '%s'", w.c_str());
+    WB_REQUIRE(n <= (int64_t)src->cap, WB_EINVAL, "debug tensor smaller than requested");
+    CUDA_CHECK(cudaMemcpyAsync(out, src->p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    WB_CATCH
+}
+
+int wb_greedy_decode(wb_ctx* ctx, int B, const int64_t* prompt, int prompt_len, int max_new_tokens, int64_t eot,
+                     const int64_t* suppress, int n_suppress, const int64_t* begin_suppress, int n_begin_suppress,
+                     int64_t* tokens_out, int32_t* lens_out, const int64_t* forced, float* logits_out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(tokens_out, WB_EINVAL, "null tokens_out");
+    DecodeParams p = make_params(B, prompt, prompt_len, max_new_tokens, eot, suppress, n_suppress, begin_suppress,
+                                 n_begin_suppress, forced, logits_out != nullptr);
+    decoder_run(ctx, p);
+    decoder_fetch(ctx, p, tokens_out, lens_out, logits_out);
+    WB_CATCH
+}
+
+int wb_transcribe_resident(wb_ctx* ctx, const int64_t* prompt, int prompt_len, int max_new_tokens, int64_t eot,
+                           const int64_t* suppress, int n_suppress, const int64_t* begin_suppress, int n_begin_suppress,
+                           int64_t* tokens_out, int32_t* lens_out, int cap_chunks) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(tokens_out && lens_out, WB_EINVAL, "null output");
+    DecodeParams p = make_params(1, prompt, prompt_len, max_new_tokens, eot, suppress, n_suppress, begin_suppress,
+                                 n_begin_suppress, nullptr, false);
+    transcribe_resident(ctx, p, tokens_out, lens_out, cap_chunks);
+    WB_CATCH
+}
+
+int wb_transcribe_batch(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files, const int64_t* prompt,
+                        int prompt_len, int max_new_tokens, int64_t eot, const int64_t* suppress, int n_suppress,
+                        const int64_t* begin_suppress, int n_begin_suppress, int64_t* tokens_out, int32_t* lens_out,
+                        int32_t* file_idx_out, int cap_chunks, int* n_chunks_out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(tokens_out && lens_out, WB_EINVAL, "null output");
+    int n_chunks = 0;
+    upload_pcm(ctx, pcm, offsets, n_files, 0, 0, &n_chunks);
+    DecodeParams p = make_params(1, prompt, prompt_len, max_new_tokens, eot, suppress, n_suppress, begin_suppress,
+                                 n_begin_suppress, nullptr, false);
+    transcribe_resident(ctx, p, tokens_out, lens_out, cap_chunks);
+    if (file_idx_out)
+        for (int i = 0; i < n_chunks; ++i) file_idx_out[i] = ctx->mel.h_chunks[i].file;
+    if (n_chunks_out) *n_chunks_out = n_chunks;
+    WB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// ctx.h — the per-GPU context behind the opaque `wb_ctx` of include/whisper_b200.h, and the
+// internal interfaces between the translation units (mel / gemm / encoder / decoder / weights).
+#pragma once
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+// ---------------- log-mel ----------------
+struct MelTables {                 // POD, copied to the device once
+    float window[400];             // periodic Hann, main.rs:323-330
+    float tw_re[400], tw_im[400];  // W_400^k
+    float fb_w[400];               // non-zero filterbank weights, mel-major runs
+    int fb_idx[240];               // start[80], len[80], offset-into-fb_w[80]
+};
+struct MelChunk {
+    int file;
+    int frame_start;               // chunk_pos / 160 (main.rs:895)
+};
+struct MelState {
+    DevBuf<float> pcm;
+    DevBuf<int64_t> file_off, frame_off;
+    DevBuf<int> tile_off, fmax;
+    DevBuf<float> raw;             // [total_frames][80] log10 mel, time-major
+    DevBuf<MelChunk> chunks;
+    DevBuf<float> export_buf;
+    std::vector<int64_t> h_file_off, h_frame_off, h_chunk_pos;
+    std::vector<int> h_tile_off;
+    std::vector<MelChunk> h_chunks;
+    int n_files = 0, n_chunks = 0, total_tiles = 0;
+    int64_t total_frames = 0;
+    bool raw_valid = false;
+};
+
+// ---------------- weights ----------------
+struct LinearW {
+    void* w = nullptr;             // [out][in] in the compute dtype (f32 or bf16)
+    float* b = nullptr;            // [out] f32 or nullptr
+    int out = 0, in = 0;
+};
+struct LNW {
+    float* w = nullptr;
+    float* b = nullptr;
+};
+struct EncLayerW {
+    LNW ln1, ln2;
+    LinearW qkv, o, fc1, fc2;
+};
+struct DecLayerW {
+    LNW ln1, ln2, ln3;
+    LinearW qkv, o, cq, ckv, co, fc1, fc2;
+};
+struct ModelW {
+    LinearW conv1, conv2;          // packed [d][3*C_in], k-major then channel
+    float* enc_pos = nullptr;      // [n_audio_ctx][d] f32
+    std::vector<EncLayerW> enc;
+    LNW enc_ln;
+    void* embed = nullptr;         // [vocab][d] compute dtype (tied input embedding / output proj)
+    float* dec_pos = nullptr;      // [n_text_ctx][d] f32
+    std::vector<DecLayerW> dec;
+    LNW dec_ln;
+    std::vector<void*> allocs;
+    std::map<std::string, std::vector<float>> host;   // f32 originals by HF name
+};
+
+// ---------------- activations ----------------
+struct EncBufs {
+    DevBuf<unsigned char> mel_tm;      // [max_chunks][3002][n_mels] compute dtype (resident chunks)
+    DevBuf<unsigned char> in_tm;       // [max_batch][3002][n_mels]   (host-provided mel path)
+    DevBuf<float> in_stage;            // [max_batch][n_mels][3000] f32 staging of host mel
+    DevBuf<unsigned char> h1p;         // [B][3001][d] compute dtype, row 0 zero
+    DevBuf<float> x;                   // [B][1500][d] residual stream
+    DevBuf<unsigned char> h;           // [B][1500][d] LN output
+    DevBuf<unsigned char> qkv;         // [B][1500][3d]
+    DevBuf<unsigned char> att;         // [B][1500][d]
+    DevBuf<unsigned char> ffn;         // [B][1500][ffn]
+    DevBuf<float> scores;              // [G*H][1500][1500] (SIMT attention path)
+    DevBuf<float> out;                 // [B][1500][d] f32 encoder output (ONNX output 0)
+    DevBuf<unsigned char> out_c;       // compute-dtype copy (bf16 mode)
+    DevBuf<unsigned char> ckv;         // [dec_layers][B][1500][2d] compute dtype
+    DevBuf<float> dbg_stem, dbg_layer0;
+    int attn_group = 4;
+    int B_valid = 0;                   // sequences encoded by the last wb_encode
+};
+struct DecBufs {
+    DevBuf<float> x, qkv, att, q, ffn, logits;
+    DevBuf<unsigned char> self_kv;     // [dec_layers][B][T_max][2d] compute dtype
+    DevBuf<float> logits_all;          // optional [B][steps][V]
+    DevBuf<int> tokens;                // [B][T_total] generated+prompt ids (device)
+    DevBuf<int> forced;                // [B][max_new] teacher forcing (optional)
+    DevBuf<int> lens, finished, state; // state: [0]=position t, [1]=#unfinished
+    DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
+    int T_max = 0;
+};
+
+struct wb_ctx {
+    wb_model_cfg cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ModelW w;
+    MelTables mel_tables{};
+    MelTables* mel_tables_dev = nullptr;
+    MelState mel;
+    EncBufs enc;
+    DecBufs dec;
+    wb_timing timing{};
+    bool debug = false;
+    CudaEvent ev0, ev1;
+    size_t esz() const { return cfg.precision == WB_PREC_BF16 ? 2 : 4; }
+};
+
+// mel.cu
+void mel_build_tables(MelTables& t);
+int64_t mel_n_frames(int64_t n);
+void mel_launch_raw(wb_ctx* ctx);
+void mel_launch_chunks(wb_ctx* ctx, int chunk0, int n, void* out);
+void mel_launch_export(wb_ctx* ctx, int file, int64_t frame0, int64_t n_out, float* out_dev);
+void mel_launch_transpose_in(wb_ctx* ctx, const float* in_dev, void* out, int B);
+
+// weights.cpp
+void weights_init(wb_ctx* ctx, const char* path);
+void weights_free(wb_ctx* ctx);
+
+// gemm_simt.cu — C = epilogue(alpha * A[M,K] * B^T) ; B is [N][K] (K contiguous) or, if b_kn,
+// [K][N] (N contiguous).  Batched over z with a two-level (outer, inner) stride decomposition.
+enum { WB_F32 = 0, WB_BF16 = 1 };
+struct GemmArgs {
+    const void* A = nullptr; const void* B = nullptr; void* C = nullptr;
+    int ta = WB_F32, tb = WB_F32, tc = WB_F32;
+    int M = 0, N = 0, K = 0, lda = 0, ldb = 0, ldc = 0;
+    int batch = 1, inner = 1;
+    long long sAo = 0, sAi = 0, sBo = 0, sBi = 0, sCo = 0, sCi = 0;
+    bool b_kn = false;
+    float alpha = 1.0f;
+    const float* bias = nullptr;        // [N]
+    int act = 0;                        // 1 = exact-erf GELU
+    const float* rowadd = nullptr;      // [M][N] f32 added after activation (positional table)
+    int ld_rowadd = 0;
+    const float* residual = nullptr;    // f32, same indexing as C (may alias C)
+};
+void gemm_simt(wb_ctx* ctx, const GemmArgs& a);
+// dispatcher: tensor-core kernel when eligible (bf16, aligned), else SIMT
+void gemm(wb_ctx* ctx, const GemmArgs& a);
+
+// encoder.cu
+void encoder_alloc(wb_ctx* ctx);
+void encoder_forward(wb_ctx* ctx, const void* mel_tm, int B);   // mel_tm: [B][3002][n_mels] compute dtype
+// decoder.cu
+void decoder_alloc(wb_ctx* ctx);
+struct DecodeParams {
+    int B, prompt_len, max_new;
+    int eot;
+    const int64_t* prompt;
+    const int64_t* suppress; int n_suppress;
+    const int64_t* begin_suppress; int n_begin_suppress;
+    const int64_t* forced;
+    bool want_logits;
+};
+void decoder_run(wb_ctx* ctx, const DecodeParams& p);           // async on ctx->stream
+void decoder_fetch(wb_ctx* ctx, const DecodeParams& p, int64_t* tokens_out, int32_t* lens_out, float* logits_out);

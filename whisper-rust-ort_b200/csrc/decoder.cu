@@ -1,0 +1,518 @@
+// decoder.cu — kernel group 3: KV-cache greedy decode held on the device (replaces
+// greedy_decode_with_past + argmax_last_dim_raw + insert_present_as_past,
+// /root/reference/src/main.rs:753-829, 709-735, 737-751; decoder.run at :773, binding.run at :814).
+//
+// One "step" feeds one token per sequence at absolute position s (read from device state, so the
+// step is a replayable CUDA graph): positions 0..prompt_len-1 are the forced prompt (the
+// reference's step 0 runs them as one T=4 causal pass — same math, one row at a time), from
+// s = prompt_len-1 on the step ends with vocab projection + masked argmax whose result is the
+// next step's input.  No host round trip per token: the host only enqueues.
+//
+// HBM-bound: per step the weights (48.6 M params) and, per sequence, the cached
+// cross-attention K/V (2*1500*d per layer) are streamed once.  Activations stay f32; weights and
+// K/V caches are in the compute dtype (f32 validation build / bf16 fast build).
+#include <cstdlib>
+
+#include "ctx.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void load4(const float* p, float (&f)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&f)[4]) {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(bf16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ float load1(const float* p) { return *p; }
+__device__ __forceinline__ float load1(const bf16* p) { return __bfloat162float(*p); }
+
+// state[0] = s (position of the token fed this step), state[1] = prompt_len
+// ---- token + position embedding:  x[b] = E[tok] + P[s] ----
+template <typename WT>
+__global__ void embed_kernel(const int* __restrict__ state, const int* __restrict__ prompt,
+                             const int* __restrict__ cur_tok, const WT* __restrict__ E,
+                             const float* __restrict__ P, float* __restrict__ x, int d) {
+    const int b = blockIdx.x, s = state[0];
+    const int tok = s < state[1] ? prompt[s] : cur_tok[b];
+    for (int c = threadIdx.x; c < d; c += blockDim.x)
+        x[(size_t)b * d + c] = load1(E + (size_t)tok * d + c) + P[(size_t)s * d + c];
+}
+
+// ---- skinny GEMM: Y[B][N] = epi( LN?(X[B][K]) . W[N][K]^T ) ----
+// 4 warps per CTA, R weight rows per warp, lanes along K, batch tile of 32 sequences held as
+// 32*R accumulators per lane, transposing butterfly reduction so lane b ends with sequence b.
+constexpr int SK_THREADS = 128, SK_BT = 32, SK_KC = 512;
+
+template <typename WT, int R>
+__global__ void __launch_bounds__(SK_THREADS)
+skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restrict__ W, int N,
+                   const float* __restrict__ bias, const float* __restrict__ ln_w,
+                   const float* __restrict__ ln_b, int act, const float* residual, float* Y) {
+    extern __shared__ float xs[];                  // [SK_BT][kc]
+    __shared__ float s_mean[SK_BT], s_rstd[SK_BT];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = (blockIdx.x * (SK_THREADS / 32) + warp) * R;
+
+    for (int bt0 = 0; bt0 < B; bt0 += SK_BT) {
+        const int nb = min(SK_BT, B - bt0);
+        if (ln_w) {       // LayerNorm statistics of this batch tile (two-pass, like the oracle)
+            for (int bb = warp; bb < SK_BT; bb += SK_THREADS / 32) {
+                float mean = 0.f, sd = 1.f;
+                if (bb < nb) {
+                    const float* xr = X + (size_t)(bt0 + bb) * K;
+                    float s = 0.f;
+                    for (int c = lane; c < K; c += 32) s += xr[c];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    mean = s / (float)K;
+                    float q = 0.f;
+                    for (int c = lane; c < K; c += 32) { float t = xr[c] - mean; q += t * t; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                    sd = sqrtf(q / (float)K + 1e-5f);
+                }
+                if (lane == 0) { s_mean[bb] = mean; s_rstd[bb] = sd; }
+            }
+        }
+        float acc[R * SK_BT];
+#pragma unroll
+        for (int i = 0; i < R * SK_BT; ++i) acc[i] = 0.f;
+
+        for (int k0 = 0; k0 < K; k0 += SK_KC) {
+            const int kc = min(SK_KC, K - k0);
+            __syncthreads();                       // previous chunk consumed, LN stats visible
+            for (int i = tid; i < SK_BT * kc; i += SK_THREADS) {
+                int bb = i / kc, c = i - bb * kc;
+                float v = 0.f;
+                if (bb < nb) {
+                    v = X[(size_t)(bt0 + bb) * K + k0 + c];
+                    if (ln_w) v = (v - s_mean[bb]) / s_rstd[bb] * ln_w[k0 + c] + ln_b[k0 + c];
+                }
+                xs[bb * kc + c] = v;
+            }
+            __syncthreads();
+            for (int c = lane * 4; c < kc; c += 128) {
+                float w[R][4];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (n0 + r < N) load4(W + (size_t)(n0 + r) * K + k0 + c, w[r]);
+                    else { w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0.f; }
+                }
+#pragma unroll
+                for (int bb = 0; bb < SK_BT; ++bb) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + bb * kc + c);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float a = acc[bb * R + r];
+                        a = fmaf(w[r][0], xv.x, a); a = fmaf(w[r][1], xv.y, a);
+                        a = fmaf(w[r][2], xv.z, a); a = fmaf(w[r][3], xv.w, a);
+                        acc[bb * R + r] = a;
+                    }
+                }
+            }
+        }
+        // transposing butterfly: after 5 rounds lane l holds acc index l*R .. l*R+R-1 (sequence l)
+#pragma unroll
+        for (int off = 16, n = R * SK_BT; off >= 1; off >>= 1, n >>= 1) {
+            const int half = n >> 1;
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                float send = up ? acc[i] : acc[i + half];
+                float keep = up ? acc[i + half] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        if (lane < nb) {
+            const int b = bt0 + lane;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = n0 + r;
+                if (n < N) {
+                    float v = acc[r];
+                    if (bias) v += bias[n];
+                    if (act == 1) v = gelu_erf(v);
+                    if (residual) v += residual[(size_t)b * N + n];
+                    Y[(size_t)b * N + n] = v;
+                }
+            }
+        }
+    }
+}
+
+// ---- decoder self-attention for the new token (causal = all cached keys 0..s) ----
+// grid (H, B), 128 threads.  Appends this step's k,v to the cache first.
+template <typename KT>
+__global__ void __launch_bounds__(128)
+self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, KT* __restrict__ cache,
+                 float* __restrict__ out, int d, int T_max) {
+    __shared__ float s_q[64], s_p[512], s_red[4], s_acc[2][64];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = state[0];
+    const float* row = qkv + (size_t)b * 3 * d;
+    KT* kv = cache + (size_t)b * T_max * 2 * d;
+    if (tid < 64) {
+        s_q[tid] = row[h * 64 + tid] * 0.125f;
+        store1(kv + (size_t)s * 2 * d + h * 64 + tid, row[d + h * 64 + tid]);
+    } else {
+        store1(kv + (size_t)s * 2 * d + d + h * 64 + (tid - 64), row[2 * d + h * 64 + (tid - 64)]);
+    }
+    __syncthreads();
+    const int nk = s + 1;
+    for (int j = warp; j < nk; j += 4) {
+        const KT* kr = kv + (size_t)j * 2 * d + h * 64;
+        float p = s_q[lane] * load1(kr + lane) + s_q[lane + 32] * load1(kr + lane + 32);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) s_p[j] = p;
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int j = tid; j < nk; j += 128) m = fmaxf(m, s_p[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < nk; j += 128) { float e = expf(s_p[j] - m); s_p[j] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    const int dim = tid & 63, part = tid >> 6;
+    float a = 0.f;
+    for (int j = part; j < nk; j += 2) a = fmaf(s_p[j] / sum, load1(kv + (size_t)j * 2 * d + d + h * 64 + dim), a);
+    s_acc[part][dim] = a;
+    __syncthreads();
+    if (tid < 64) out[(size_t)b * d + h * 64 + tid] = s_acc[0][tid] + s_acc[1][tid];
+}
+
+// ---- cross-attention over the cached encoder K/V: the dominant HBM stream of a step ----
+// grid (H, B), 256 threads.  8 lanes cover one 64-wide K or V row with 16/32-byte loads.
+template <typename KT>
+__global__ void __launch_bounds__(256)
+cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out,
+                  int d, int Tk) {
+    extern __shared__ float sm[];                 // scores [Tk] + reduce scratch
+    float* s_p = sm;
+    __shared__ float s_red[8];
+    __shared__ float s_acc[8][64];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 3, li = tid & 7;       // 32 groups of 8 lanes
+    const KT* base = ckv + (size_t)b * Tk * 2 * d + h * 64 + li * 8;
+    float qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * 8 + i] * 0.125f;
+
+    float lmax = -INFINITY;
+    for (int j = grp; j < Tk; j += 32) {
+        float kf[8];
+        load8(base + (size_t)j * 2 * d, kf);
+        float p = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p = fmaf(qv[i], kf[i], p);
+        p += __shfl_xor_sync(0xffffffffu, p, 4);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        if (li == 0) s_p[j] = p;
+        lmax = fmaxf(lmax, p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if (lane == 0) s_red[warp] = lmax;
+    __syncthreads();
+    float m = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < Tk; j += 256) { float e = expf(s_p[j] - m); s_p[j] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += s_red[i];
+    const float inv = 1.0f / sum;
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const KT* vbase = base + d;
+    for (int j = grp; j < Tk; j += 32) {
+        float vf[8];
+        load8(vbase + (size_t)j * 2 * d, vf);
+        const float p = s_p[j] * inv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+    }
+    // reduce the 4 groups of a warp, then the 8 warps
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_acc[warp][lane * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += s_acc[w][tid];
+        out[(size_t)b * d + h * 64 + tid] = a;
+    }
+}
+
+// ---- masked argmax + token bookkeeping (argmax_last_dim_raw, main.rs:709-735) ----
+// One CTA per sequence.  strict '>' in increasing index order => lowest index wins ties, NaN never
+// wins, everything masked => 0.  Also advances the per-sequence output/finished state.
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const int* __restrict__ state, const float* __restrict__ logits, int V,
+              const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
+              const int* __restrict__ forced, int max_new, int eot, int T_total,
+              int* __restrict__ tokens, int* __restrict__ lens, int* __restrict__ finished,
+              int* __restrict__ cur_tok) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = state[0], prompt_len = state[1];
+    const int gi = s - (prompt_len - 1);
+    const unsigned* sup = gi == 0 ? sup_first : sup_base;
+    const float* row = logits + (size_t)b * V;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += 1024) {
+        if ((sup[i >> 5] >> (i & 31)) & 1u) continue;
+        float v = row[i];
+        if (v > bv) { bv = v; bi = i; }
+    }
+    auto better = [](float v1, int i1, float v2, int i2) { return v1 > v2 || (v1 == v2 && i1 < i2); };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bv = s_v[lane]; bi = s_i[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            int tok = (bi == 0x7fffffff) ? 0 : bi;        // nothing beat -inf -> index 0
+            if (!finished[b]) {
+                tokens[(size_t)b * T_total + prompt_len + gi] = tok;
+                lens[b] = prompt_len + gi + 1;
+                if (tok == eot) finished[b] = 1;           // main.rs:781-783, 820-822
+            }
+            cur_tok[b] = forced ? forced[(size_t)b * max_new + gi] : tok;
+        }
+    }
+}
+
+__global__ void advance_kernel(int* state) { state[0] += 1; }
+
+template <typename WT>
+void skinny(wb_ctx* ctx, const float* X, int B, int K, const LinearW& L, const LNW* ln, int act,
+            const float* residual, float* Y, int N_override = 0, const void* W_override = nullptr) {
+    const int N = N_override ? N_override : L.out;
+    const WT* W = reinterpret_cast<const WT*>(W_override ? W_override : L.w);
+    WB_REQUIRE(K % 128 == 0, WB_EINVAL, "skinny gemm needs K %% 128 == 0 (K=%d)", K);
+    const int kc = K < SK_KC ? K : SK_KC;
+    const size_t smem = sizeof(float) * SK_BT * kc;
+    const float* lw = ln ? ln->w : nullptr;
+    const float* lb = ln ? ln->b : nullptr;
+    if (N >= 1536) {
+        constexpr int R = 4;
+        static bool done = false;
+        if (!done) { CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<WT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SK_BT * SK_KC))); done = true; }
+        skinny_gemm_kernel<WT, R><<<ceil_div(N, 4 * R), SK_THREADS, smem, ctx->stream>>>(X, B, K, W, N, L.b && !W_override ? L.b : nullptr, lw, lb, act, residual, Y);
+    } else {
+        constexpr int R = 1;
+        static bool done = false;
+        if (!done) { CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<WT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SK_BT * SK_KC))); done = true; }
+        skinny_gemm_kernel<WT, R><<<ceil_div(N, 4 * R), SK_THREADS, smem, ctx->stream>>>(X, B, K, W, N, L.b && !W_override ? L.b : nullptr, lw, lb, act, residual, Y);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// Enqueue one decode step.  with_logits: final LN + tied vocab projection + argmax.
+template <typename WT>
+int enqueue_step(wb_ctx* ctx, int B, bool with_logits, const int* prompt_dev, const int* cur_tok,
+                 const int* forced_dev, int max_new, int eot, int T_total) {
+    const wb_model_cfg& c = ctx->cfg;
+    const int d = c.d_model, H = c.n_heads, Tk = c.n_audio_ctx;
+    DecBufs& D = ctx->dec;
+    ModelW& w = ctx->w;
+    int* state = D.state.p;
+    int n = 0;
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(cross_attn_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
+        attr = true;
+    }
+    embed_kernel<WT><<<B, 128, 0, ctx->stream>>>(state, prompt_dev, cur_tok, (const WT*)w.embed, w.dec_pos, D.x.p, d); ++n;
+    for (int l = 0; l < c.dec_layers; ++l) {
+        const DecLayerW& L = w.dec[l];
+        WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + (size_t)l * c.max_batch * D.T_max * 2 * d;
+        const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + (size_t)l * c.max_batch * Tk * 2 * d;
+        skinny<WT>(ctx, D.x.p, B, d, L.qkv, &L.ln1, 0, nullptr, D.qkv.p); ++n;                 // K3c
+        self_attn_kernel<WT><<<dim3(H, B), 128, 0, ctx->stream>>>(state, D.qkv.p, skv, D.att.p, d, D.T_max); ++n;   // K3d
+        skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, D.x.p, D.x.p); ++n;                     // K3f
+        skinny<WT>(ctx, D.x.p, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
+        cross_attn_kernel<WT><<<dim3(H, B), 256, sizeof(float) * Tk, ctx->stream>>>(D.q.p, ckv, D.att.p, d, Tk); ++n;  // K3e
+        skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, D.x.p, D.x.p); ++n;
+        skinny<WT>(ctx, D.x.p, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                  // K3g
+        skinny<WT>(ctx, D.ffn.p, B, c.ffn_dim, L.fc2, nullptr, 0, D.x.p, D.x.p); ++n;
+    }
+    if (with_logits) {                                                                           // K3h
+        LinearW dummy;
+        skinny<WT>(ctx, D.x.p, B, d, dummy, &w.dec_ln, 0, nullptr, D.logits.p, c.vocab, w.embed); ++n;
+        argmax_kernel<<<B, 1024, 0, ctx->stream>>>(state, D.logits.p, c.vocab, D.sup_base.p, D.sup_first.p, forced_dev,
+                                                   max_new, eot, T_total, D.tokens.p, D.lens.p, D.finished.p, D.tokens.p + (size_t)c.max_batch * T_total); ++n;
+    }
+    advance_kernel<<<1, 1, 0, ctx->stream>>>(state); ++n;
+    CUDA_CHECK(cudaGetLastError());
+    (void)cur_tok;
+    return n;
+}
+
+}  // namespace
+
+void decoder_alloc(wb_ctx* ctx) {
+    const wb_model_cfg& c = ctx->cfg;
+    const size_t B = c.max_batch, d = c.d_model;
+    DecBufs& D = ctx->dec;
+    D.T_max = c.n_text_ctx;
+    D.x.reserve(B * d);
+    D.qkv.reserve(B * 3 * d);
+    D.att.reserve(B * d);
+    D.q.reserve(B * d);
+    D.ffn.reserve(B * c.ffn_dim);
+    D.logits.reserve(B * c.vocab);
+    D.self_kv.reserve((size_t)c.dec_layers * B * D.T_max * 2 * d * ctx->esz());
+    D.tokens.reserve(B * (size_t)c.n_text_ctx + B + (size_t)c.n_text_ctx);   // ids | cur_tok | prompt
+    D.forced.reserve(B * (size_t)c.n_text_ctx);
+    D.lens.reserve(B);
+    D.finished.reserve(B);
+    D.state.reserve(4);
+    const size_t words = ((size_t)c.vocab + 31) / 32;
+    D.sup_base.reserve(words);
+    D.sup_first.reserve(words);
+}
+
+void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
+    const wb_model_cfg& c = ctx->cfg;
+    DecBufs& D = ctx->dec;
+    const int B = p.B, P = p.prompt_len, max_new = p.max_new < 1 ? 1 : p.max_new;   // main.rs:779,793
+    const int T_total = P + max_new;
+    WB_REQUIRE(B >= 1 && B <= c.max_batch, WB_ECAP, "decode batch %d exceeds max_batch %d", B, c.max_batch);
+    WB_REQUIRE(B <= ctx->enc.B_valid, WB_ESTATE, "decode batch %d but only %d sequences encoded", B, ctx->enc.B_valid);
+    WB_REQUIRE(P >= 1 && T_total <= D.T_max, WB_ECAP, "prompt_len + max_new_tokens = %d exceeds n_text_ctx %d", T_total, D.T_max);
+    for (int i = 0; i < P; ++i) WB_REQUIRE(p.prompt[i] >= 0 && p.prompt[i] < c.vocab, WB_EINVAL, "prompt id out of range");
+
+    // host -> device control state (small)
+    const size_t words = ((size_t)c.vocab + 31) / 32;
+    std::vector<unsigned> base(words, 0u), first;
+    for (int i = 0; i < p.n_suppress; ++i)
+        if (p.suppress[i] >= 0 && p.suppress[i] < c.vocab) base[(size_t)p.suppress[i] >> 5] |= 1u << (p.suppress[i] & 31);
+    first = base;
+    for (int i = 0; i < p.n_begin_suppress; ++i)
+        if (p.begin_suppress[i] >= 0 && p.begin_suppress[i] < c.vocab) first[(size_t)p.begin_suppress[i] >> 5] |= 1u << (p.begin_suppress[i] & 31);
+    std::vector<int> tok((size_t)c.max_batch * T_total + c.max_batch + P, -1);
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < P; ++i) tok[(size_t)b * T_total + i] = (int)p.prompt[i];
+    int* cur_tok = D.tokens.p + (size_t)c.max_batch * T_total;
+    int* prompt_dev = cur_tok + c.max_batch;
+    for (int i = 0; i < P; ++i) tok[(size_t)c.max_batch * T_total + c.max_batch + i] = (int)p.prompt[i];
+    cudaStream_t st = ctx->stream;
+    CUDA_CHECK(cudaMemcpyAsync(D.tokens.p, tok.data(), sizeof(int) * tok.size(), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.sup_base.p, base.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.sup_first.p, first.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
+    std::vector<int> lens(B, P), st4 = {0, P, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(D.lens.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemsetAsync(D.finished.p, 0, sizeof(int) * B, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.state.p, st4.data(), sizeof(int) * 4, cudaMemcpyHostToDevice, st));
+    int* forced_dev = nullptr;
+    std::vector<int> forced;
+    if (p.forced) {
+        forced.resize((size_t)B * max_new);
+        for (size_t i = 0; i < forced.size(); ++i) {
+            WB_REQUIRE(p.forced[i] >= 0 && p.forced[i] < c.vocab, WB_EINVAL, "forced id out of range");
+            forced[i] = (int)p.forced[i];
+        }
+        CUDA_CHECK(cudaMemcpyAsync(D.forced.p, forced.data(), sizeof(int) * forced.size(), cudaMemcpyHostToDevice, st));
+        forced_dev = D.forced.p;
+    }
+    if (p.want_logits) D.logits_all.reserve((size_t)B * max_new * c.vocab);
+    CUDA_CHECK(cudaStreamSynchronize(st));      // host staging vectors go out of scope below
+
+    CudaEvent e0, e1;
+    CUDA_CHECK(cudaEventRecord(e0.e, st));
+    const int steps = P + max_new - 1;
+    int launches = 0;
+    const bool bf = c.precision == WB_PREC_BF16;
+    for (int s = 0; s < steps; ++s) {
+        const bool with_logits = s >= P - 1;
+        launches += bf ? enqueue_step<bf16>(ctx, B, with_logits, prompt_dev, cur_tok, forced_dev, max_new, p.eot, T_total)
+                       : enqueue_step<float>(ctx, B, with_logits, prompt_dev, cur_tok, forced_dev, max_new, p.eot, T_total);
+        if (with_logits && p.want_logits) {
+            const int gi = s - (P - 1);
+            CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
+                                         D.logits.p, sizeof(float) * c.vocab, sizeof(float) * c.vocab, B,
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    CUDA_CHECK(cudaEventRecord(e1.e, st));
+    CUDA_CHECK(cudaEventSynchronize(e1.e));
+    CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.decode_ms, e0.e, e1.e));
+    ctx->timing.decode_launches = launches;
+    ctx->timing.decode_steps = steps;
+}
+
+void decoder_fetch(wb_ctx* ctx, const DecodeParams& p, int64_t* tokens_out, int32_t* lens_out, float* logits_out) {
+    const wb_model_cfg& c = ctx->cfg;
+    DecBufs& D = ctx->dec;
+    const int B = p.B, max_new = p.max_new < 1 ? 1 : p.max_new, T_total = p.prompt_len + max_new;
+    std::vector<int> tok((size_t)B * T_total), lens(B);
+    CUDA_CHECK(cudaMemcpyAsync(tok.data(), D.tokens.p, sizeof(int) * tok.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(lens.data(), D.lens.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logits_out)
+        CUDA_CHECK(cudaMemcpyAsync(logits_out, D.logits_all.p, sizeof(float) * (size_t)B * max_new * c.vocab, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < B; ++b) {
+        if (lens_out) lens_out[b] = lens[b];
+        for (int i = 0; i < T_total; ++i)
+            tokens_out[(size_t)b * T_total + i] = i < lens[b] ? (int64_t)tok[(size_t)b * T_total + i] : -1;
+    }
+}

@@ -1,0 +1,255 @@
+// encoder.cu — kernel group 2: the Whisper encoder forward (replaces run_encoder,
+// /root/reference/src/main.rs:698-707, i.e. encoder.run at :703 on encoder_model.onnx) plus the
+// cross-attention K/V projection that decoder_model.onnx emits as present.*.encoder.* (:786-787).
+//
+// Layout: activations are token-major [clip][frame][channel]; the conv stem is expressed as two
+// GEMMs over overlapping row windows of a zero-padded time-major buffer (row t of conv1's A
+// operand = frames t..t+2 of [3002][n_mels]; row t of conv2's = frames 2t..2t+2 of [3001][d]), so
+// no im2col buffer ever touches HBM.  Residual stream f32; GEMM operands in the compute dtype.
+#include "ctx.h"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ void put(T* p, float v);
+template <> __device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+constexpr int LN_MAX_PER_LANE = 40;   // d_model <= 1280
+
+// One warp per row.  out = (x-mean)/sqrt(var+eps)*w+b (two-pass, f32), optional second f32 copy.
+template <typename TO>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ b, TO* __restrict__ out,
+                                 float* __restrict__ out_f32, int rows, int d) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * d;
+    float v[LN_MAX_PER_LANE];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+        int c = lane + i * 32;
+        v[i] = c < d ? xr[c] : 0.0f;
+        s += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+        int c = lane + i * 32;
+        float t = c < d ? v[i] - mean : 0.0f;
+        v[i] = t;
+        q += t * t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float sd = sqrtf(q / (float)d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+        int c = lane + i * 32;
+        if (c < d) {
+            float y = v[i] / sd * w[c] + b[c];
+            put<TO>(out + (size_t)row * d + c, y);
+            if (out_f32) out_f32[(size_t)row * d + c] = y;
+        }
+    }
+}
+
+// Row softmax in place over f32 scores (SIMT attention path).  One warp per row, n <= 1536.
+__global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int n) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* r = s + (size_t)row * n;
+    float v[48];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+        int c = lane + i * 32;
+        v[i] = c < n ? r[c] : -INFINITY;
+        m = fmaxf(m, v[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+        int c = lane + i * 32;
+        v[i] = c < n ? expf(v[i] - m) : 0.0f;
+        sum += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int i = 0; i < 48; ++i) {
+        int c = lane + i * 32;
+        if (c < n) r[c] = v[i] / sum;
+    }
+}
+
+void layernorm(wb_ctx* ctx, const float* x, const LNW& ln, void* out, float* out_f32, int rows) {
+    const int d = ctx->cfg.d_model;
+    const int wpb = 8;
+    dim3 grid(ceil_div(rows, wpb));
+    if (ctx->cfg.precision == WB_PREC_BF16)
+        layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, (__nv_bfloat16*)out, out_f32, rows, d);
+    else
+        layernorm_kernel<float><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, (float*)out, out_f32, rows, d);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void encoder_alloc(wb_ctx* ctx) {
+    const wb_model_cfg& c = ctx->cfg;
+    const size_t B = c.max_batch, T = WB_N_FRAMES, Tc = c.n_audio_ctx, d = c.d_model, e = ctx->esz();
+    WB_REQUIRE(c.n_audio_ctx * 2 == WB_N_FRAMES, WB_EINVAL, "n_audio_ctx must be 1500");
+    WB_REQUIRE(d <= 32 * LN_MAX_PER_LANE && d % 128 == 0 && c.ffn_dim % 128 == 0, WB_EINVAL, "unsupported d_model/ffn_dim");
+    WB_REQUIRE(d / c.n_heads == 64 && d % c.n_heads == 0, WB_EINVAL, "head_dim must be 64");
+    EncBufs& b = ctx->enc;
+    b.mel_tm.reserve_zero((size_t)c.max_chunks * (T + 2) * c.n_mels * e);
+    b.in_tm.reserve_zero(B * (T + 2) * c.n_mels * e);
+    b.in_stage.reserve(B * c.n_mels * T);
+    b.h1p.reserve_zero(B * (T + 1) * d * e);
+    b.x.reserve(B * Tc * d);
+    b.h.reserve(B * Tc * d * e);
+    b.qkv.reserve(B * Tc * 3 * d * e);
+    b.att.reserve(B * Tc * d * e);
+    b.ffn.reserve(B * Tc * c.ffn_dim * e);
+    b.attn_group = (int)(B < 4 ? B : 4);
+    b.scores.reserve((size_t)b.attn_group * c.n_heads * Tc * Tc);
+    b.out.reserve(B * Tc * d);
+    if (c.precision == WB_PREC_BF16) b.out_c.reserve(B * Tc * d * e);
+    b.ckv.reserve((size_t)c.dec_layers * B * Tc * 2 * d * e);
+}
+
+void encoder_forward(wb_ctx* ctx, const void* mel_tm, int B) {
+    const wb_model_cfg& c = ctx->cfg;
+    const int T = WB_N_FRAMES, Tc = c.n_audio_ctx, d = c.d_model, H = c.n_heads, C = c.n_mels;
+    const int ct = c.precision == WB_PREC_BF16 ? WB_BF16 : WB_F32;
+    EncBufs& b = ctx->enc;
+    ModelW& w = ctx->w;
+    CUDA_CHECK(cudaEventRecord(ctx->ev0.e, ctx->stream));
+    int launches = 0;
+
+    {   // conv1 + GELU -> h1p rows 1..3000           (K2a)
+        GemmArgs g;
+        g.A = mel_tm; g.B = w.conv1.w; g.C = (char*)b.h1p.p + (size_t)d * ctx->esz();
+        g.ta = g.tb = g.tc = ct;
+        g.M = T; g.N = d; g.K = 3 * C; g.lda = C; g.ldb = 3 * C; g.ldc = d;
+        g.batch = B; g.inner = 1; g.sAo = (long long)(T + 2) * C; g.sCo = (long long)(T + 1) * d;
+        g.bias = w.conv1.b; g.act = 1;
+        gemm(ctx, g); ++launches;
+    }
+    {   // conv2 (stride 2) + GELU + positions -> x
+        GemmArgs g;
+        g.A = b.h1p.p; g.B = w.conv2.w; g.C = b.x.p;
+        g.ta = g.tb = ct; g.tc = WB_F32;
+        g.M = Tc; g.N = d; g.K = 3 * d; g.lda = 2 * d; g.ldb = 3 * d; g.ldc = d;
+        g.batch = B; g.inner = 1; g.sAo = (long long)(T + 1) * d; g.sCo = (long long)Tc * d;
+        g.bias = w.conv2.b; g.act = 1; g.rowadd = w.enc_pos; g.ld_rowadd = d;
+        gemm(ctx, g); ++launches;
+    }
+    if (ctx->debug) {
+        b.dbg_stem.reserve((size_t)c.max_batch * Tc * d);
+        CUDA_CHECK(cudaMemcpyAsync(b.dbg_stem.p, b.x.p, sizeof(float) * (size_t)B * Tc * d, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+
+    const int rows = B * Tc;
+    for (int l = 0; l < c.enc_layers; ++l) {
+        const EncLayerW& L = w.enc[l];
+        layernorm(ctx, b.x.p, L.ln1, b.h.p, nullptr, rows); ++launches;                  // K2b
+        {   // fused QKV projection, N = 3d                                             (K2c)
+            GemmArgs g;
+            g.A = b.h.p; g.B = L.qkv.w; g.C = b.qkv.p; g.ta = g.tb = g.tc = ct;
+            g.M = rows; g.N = 3 * d; g.K = d; g.lda = d; g.ldb = d; g.ldc = 3 * d; g.bias = L.qkv.b;
+            gemm(ctx, g); ++launches;
+        }
+        // self-attention, non-causal, T = 1500, head_dim 64                            (K2d)
+        for (int g0 = 0; g0 < B; g0 += b.attn_group) {
+            const int G = (B - g0 < b.attn_group) ? B - g0 : b.attn_group;
+            const char* qkv = (const char*)b.qkv.p + (size_t)g0 * Tc * 3 * d * ctx->esz();
+            {   // S = (q * hd^-0.5) k^T   (0.125 is a power of two: exact in either order)
+                GemmArgs g;
+                g.A = qkv; g.B = qkv + (size_t)d * ctx->esz(); g.C = b.scores.p;
+                g.ta = g.tb = ct; g.tc = WB_F32;
+                g.M = Tc; g.N = Tc; g.K = 64; g.lda = 3 * d; g.ldb = 3 * d; g.ldc = Tc;
+                g.batch = G * H; g.inner = H;
+                g.sAo = (long long)Tc * 3 * d; g.sAi = 64; g.sBo = g.sAo; g.sBi = 64;
+                g.sCo = (long long)H * Tc * Tc; g.sCi = (long long)Tc * Tc;
+                g.alpha = 0.125f;
+                gemm_simt(ctx, g); ++launches;
+            }
+            softmax_rows_kernel<<<ceil_div(G * H * Tc, 8), 256, 0, ctx->stream>>>(b.scores.p, G * H * Tc, Tc);
+            CUDA_CHECK(cudaGetLastError()); ++launches;
+            {   // O = P v
+                GemmArgs g;
+                g.A = b.scores.p; g.B = qkv + (size_t)2 * d * ctx->esz();
+                g.C = (char*)b.att.p + (size_t)g0 * Tc * d * ctx->esz();
+                g.ta = WB_F32; g.tb = ct; g.tc = ct; g.b_kn = true;
+                g.M = Tc; g.N = 64; g.K = Tc; g.lda = Tc; g.ldb = 3 * d; g.ldc = d;
+                g.batch = G * H; g.inner = H;
+                g.sAo = (long long)H * Tc * Tc; g.sAi = (long long)Tc * Tc;
+                g.sBo = (long long)Tc * 3 * d; g.sBi = 64;
+                g.sCo = (long long)Tc * d; g.sCi = 64;
+                gemm_simt(ctx, g); ++launches;
+            }
+        }
+        {   // out-proj + bias + residual (in place on x)
+            GemmArgs g;
+            g.A = b.att.p; g.B = L.o.w; g.C = b.x.p; g.ta = g.tb = ct; g.tc = WB_F32;
+            g.M = rows; g.N = d; g.K = d; g.lda = d; g.ldb = d; g.ldc = d; g.bias = L.o.b; g.residual = b.x.p;
+            gemm(ctx, g); ++launches;
+        }
+        layernorm(ctx, b.x.p, L.ln2, b.h.p, nullptr, rows); ++launches;
+        {   // fc1 + GELU
+            GemmArgs g;
+            g.A = b.h.p; g.B = L.fc1.w; g.C = b.ffn.p; g.ta = g.tb = g.tc = ct;
+            g.M = rows; g.N = c.ffn_dim; g.K = d; g.lda = d; g.ldb = d; g.ldc = c.ffn_dim; g.bias = L.fc1.b; g.act = 1;
+            gemm(ctx, g); ++launches;
+        }
+        {   // fc2 + bias + residual
+            GemmArgs g;
+            g.A = b.ffn.p; g.B = L.fc2.w; g.C = b.x.p; g.ta = g.tb = ct; g.tc = WB_F32;
+            g.M = rows; g.N = d; g.K = c.ffn_dim; g.lda = c.ffn_dim; g.ldb = c.ffn_dim; g.ldc = d; g.bias = L.fc2.b; g.residual = b.x.p;
+            gemm(ctx, g); ++launches;
+        }
+        if (ctx->debug && l == 0) {
+            b.dbg_layer0.reserve((size_t)c.max_batch * Tc * d);
+            CUDA_CHECK(cudaMemcpyAsync(b.dbg_layer0.p, b.x.p, sizeof(float) * (size_t)B * Tc * d, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    // final LayerNorm -> f32 output (ONNX output 0) + compute-dtype copy for the cross-K/V GEMMs
+    const void* enc_c;
+    if (ct == WB_BF16) {
+        layernorm(ctx, b.x.p, w.enc_ln, b.out_c.p, b.out.p, rows);
+        enc_c = b.out_c.p;
+    } else {
+        layernorm(ctx, b.x.p, w.enc_ln, b.out.p, nullptr, rows);
+        enc_c = b.out.p;
+    }
+    ++launches;
+    CUDA_CHECK(cudaEventRecord(ctx->ev1.e, ctx->stream));
+
+    // cross-attention K/V for every decoder layer: [layer][B][1500][2d] (k | v)       (K3a)
+    CudaEvent e2;
+    for (int l = 0; l < c.dec_layers; ++l) {
+        GemmArgs g;
+        g.A = enc_c; g.B = w.dec[l].ckv.w;
+        g.C = (char*)b.ckv.p + (size_t)l * c.max_batch * Tc * 2 * d * ctx->esz();
+        g.ta = g.tb = g.tc = ct;
+        g.M = rows; g.N = 2 * d; g.K = d; g.lda = d; g.ldb = d; g.ldc = 2 * d; g.bias = w.dec[l].ckv.b;
+        gemm(ctx, g); ++launches;
+    }
+    CUDA_CHECK(cudaEventRecord(e2.e, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(e2.e));
+    CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.encoder_ms, ctx->ev0.e, ctx->ev1.e));
+    CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.cross_kv_ms, ctx->ev1.e, e2.e));
+    ctx->timing.encoder_launches = launches;
+    b.B_valid = B;
+}
+
+void gemm(wb_ctx* ctx, const GemmArgs& a) { gemm_simt(ctx, a); }

@@ -1,0 +1,205 @@
+// json.h — minimal JSON reader/writer (replaces serde_json uses in /root/reference/src/main.rs:
+// discovery json :124-167, generation_config.json :650-657, tokenizer.json, output files :1232-1259).
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace wbjson {
+
+struct Value {
+    enum Type { Null, Bool, Num, Str, Arr, Obj } type = Null;
+    bool b = false;
+    double n = 0.0;
+    bool is_int = false;
+    std::string s;
+    std::vector<Value> a;
+    std::vector<std::pair<std::string, Value>> o;   // insertion order
+
+    bool is_null() const { return type == Null; }
+    double num() const { return n; }
+    const std::string& str() const { return s; }
+    const std::vector<Value>& arr() const { return a; }
+    const Value* find(const std::string& k) const {
+        for (const auto& kv : o) if (kv.first == k) return &kv.second;
+        return nullptr;
+    }
+    const Value& operator[](const std::string& k) const {
+        static const Value null_v;
+        const Value* v = find(k);
+        return v ? *v : null_v;
+    }
+};
+
+struct Parser {
+    const std::string& t;
+    size_t i = 0;
+    explicit Parser(const std::string& text) : t(text) {}
+    [[noreturn]] void fail(const char* m) const {
+        throw std::runtime_error(std::string("JSON parse error at byte ") + std::to_string(i) + ": " + m);
+    }
+    void ws() { while (i < t.size() && (t[i] == ' ' || t[i] == '\n' || t[i] == '\t' || t[i] == '\r')) ++i; }
+    static void utf8(std::string& out, unsigned cp) {
+        if (cp < 0x80) out += (char)cp;
+        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+        else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+        else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+    }
+    unsigned hex4() {
+        if (i + 4 > t.size()) fail("bad \\u escape");
+        unsigned v = 0;
+        for (int k = 0; k < 4; ++k) {
+            char c = t[i++];
+            v <<= 4;
+            if (c >= '0' && c <= '9') v |= (unsigned)(c - '0');
+            else if (c >= 'a' && c <= 'f') v |= (unsigned)(c - 'a' + 10);
+            else if (c >= 'A' && c <= 'F') v |= (unsigned)(c - 'A' + 10);
+            else fail("bad hex digit");
+        }
+        return v;
+    }
+    std::string string() {
+        if (t[i] != '"') fail("expected string");
+        ++i;
+        std::string out;
+        while (true) {
+            if (i >= t.size()) fail("unterminated string");
+            char c = t[i++];
+            if (c == '"') break;
+            if (c != '\\') { out += c; continue; }
+            if (i >= t.size()) fail("bad escape");
+            char e = t[i++];
+            switch (e) {
+                case '"': out += '"'; break;
+                case '\\': out += '\\'; break;
+                case '/': out += '/'; break;
+                case 'b': out += '\b'; break;
+                case 'f': out += '\f'; break;
+                case 'n': out += '\n'; break;
+                case 'r': out += '\r'; break;
+                case 't': out += '\t'; break;
+                case 'u': {
+                    unsigned cp = hex4();
+                    if (cp >= 0xD800 && cp < 0xDC00 && i + 1 < t.size() && t[i] == '\\' && t[i + 1] == 'u') {
+                        i += 2;
+                        unsigned lo = hex4();
+                        cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                    }
+                    utf8(out, cp);
+                    break;
+                }
+                default: fail("unknown escape");
+            }
+        }
+        return out;
+    }
+    Value value() {
+        ws();
+        if (i >= t.size()) fail("unexpected end");
+        Value v;
+        char c = t[i];
+        if (c == '{') {
+            v.type = Value::Obj;
+            ++i; ws();
+            if (i < t.size() && t[i] == '}') { ++i; return v; }
+            while (true) {
+                ws();
+                std::string k = string();
+                ws();
+                if (i >= t.size() || t[i] != ':') fail("expected ':'");
+                ++i;
+                v.o.emplace_back(std::move(k), value());
+                ws();
+                if (i < t.size() && t[i] == ',') { ++i; continue; }
+                if (i < t.size() && t[i] == '}') { ++i; break; }
+                fail("expected ',' or '}'");
+            }
+        } else if (c == '[') {
+            v.type = Value::Arr;
+            ++i; ws();
+            if (i < t.size() && t[i] == ']') { ++i; return v; }
+            while (true) {
+                v.a.push_back(value());
+                ws();
+                if (i < t.size() && t[i] == ',') { ++i; continue; }
+                if (i < t.size() && t[i] == ']') { ++i; break; }
+                fail("expected ',' or ']'");
+            }
+        } else if (c == '"') {
+            v.type = Value::Str;
+            v.s = string();
+        } else if (t.compare(i, 4, "true") == 0) { v.type = Value::Bool; v.b = true; i += 4; }
+        else if (t.compare(i, 5, "false") == 0) { v.type = Value::Bool; v.b = false; i += 5; }
+        else if (t.compare(i, 4, "null") == 0) { i += 4; }
+        else {
+            size_t s0 = i;
+            bool isint = true;
+            if (t[i] == '-') ++i;
+            while (i < t.size() && ((t[i] >= '0' && t[i] <= '9') || t[i] == '.' || t[i] == 'e' || t[i] == 'E' || t[i] == '+' || t[i] == '-')) {
+                if (t[i] == '.' || t[i] == 'e' || t[i] == 'E') isint = false;
+                ++i;
+            }
+            if (s0 == i) fail("unexpected character");
+            v.type = Value::Num;
+            v.n = std::strtod(t.substr(s0, i - s0).c_str(), nullptr);
+            v.is_int = isint;
+        }
+        return v;
+    }
+};
+
+inline Value parse(const std::string& text) {
+    Parser p(text);
+    Value v = p.value();
+    p.ws();
+    if (p.i != text.size()) p.fail("trailing characters");
+    return v;
+}
+
+// ---- writer: serde_json-compatible escaping and pretty printing (2-space indent) ----
+inline std::string escape(const std::string& s) {
+    std::string o = "\"";
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            case '\b': o += "\\b"; break;
+            case '\f': o += "\\f"; break;
+            default:
+                if (c < 0x20) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); o += b; }
+                else o += (char)c;
+        }
+    }
+    return o + "\"";
+}
+
+// Shortest round-trip f64 formatting in serde_json/ryu style ("14.884440201999999", "1.0", "1e-9").
+inline std::string fmt_f64(double v) {
+    if (std::isnan(v) || std::isinf(v)) return "null";       // serde_json writes null
+    char buf[40];
+    for (int prec = 1; prec <= 17; ++prec) {
+        snprintf(buf, sizeof(buf), "%.*g", prec, v);
+        if (std::strtod(buf, nullptr) == v) break;
+    }
+    std::string s(buf);
+    size_t epos = s.find('e');
+    if (epos == std::string::npos) {
+        if (s.find('.') == std::string::npos) s += ".0";
+        return s;
+    }
+    // ryu prints exponents without '+' or leading zeros, mantissa keeps ".0" dropped: 1e-9, 1.5e-7
+    std::string mant = s.substr(0, epos), ex = s.substr(epos + 1);
+    int e = std::atoi(ex.c_str());
+    // serde_json (ryu) uses plain decimals for 1e-5 <= |v| < 1e16; %g switches at 1e-5 too.
+    return mant + "e" + std::to_string(e);
+}
+
+}  // namespace wbjson

@@ -1,0 +1,374 @@
+// mel.cu — kernel group 1: batched Whisper log-mel (replaces whisper_log_mel_80,
+// /root/reference/src/main.rs:407-509, and the chunk slicing of :895-905).
+//
+// K1a logmel_raw_kernel : PCM -> log10(max(mel,1e-10)) time-major [frame][80] + per-FILE max
+//                         (the reference clamps against the max of the whole file, quirk Q1).
+// K1b mel_chunks_kernel : clamp(max-8), (x+4)/4, cut 3000-frame windows, zero-pad in mel space
+//                         (Q2) -> [chunk][1+3000+1][n_mels] time-major in the encoder's compute
+//                         dtype, the layout the conv-stem GEMM consumes without im2col.
+// K1c mel_export_kernel : same normalisation, reference layout [80][frames] f32 (API/test only).
+//
+// HBM-bound by design (1.92 MB in + 0.96 MB out per 30 s clip); the FFT is a
+// register-resident 20x20 four-step (mel_math.h) so the only global traffic is PCM in, mel out.
+#include "ctx.h"
+#include "mel_math.h"
+
+namespace {
+
+constexpr int FPT = 32;                       // frames per tile (one CTA)
+constexpr int MEL_THREADS = 160;              // 8 FFT groups x 20 threads
+constexpr int FFTS = 8;                       // complex FFTs per pass = 16 frames
+constexpr int SPAN = (FPT - 1) * 160 + 400;   // padded samples a tile touches
+constexpr int SCR = 420;                      // 20 x 21 (padded) complex per FFT
+constexpr int POW_LD = 204;
+
+__device__ __forceinline__ float padded_sample(const float* __restrict__ x, int64_t N, int64_t p) {
+    // main.rs:419-435: reflect-pad 200 each side (N >= 2), else audio then zeros.
+    if (N >= 2) {
+        int64_t n = p - 200;
+        if (n < 0) {
+            int64_t idx = 200 - p;
+            return x[idx < N - 1 ? idx : N - 1];
+        }
+        if (n < N) return x[n];
+        int64_t i = n - N;
+        if (i >= 200) return 0.0f;                       // main.rs:468 (never hit for valid frames)
+        int64_t idx = N - 2 - i;
+        return x[idx > 0 ? idx : 0];
+    }
+    return p < N ? x[p] : 0.0f;
+}
+
+__device__ __forceinline__ void atomic_max_float(int* addr, float v) {
+    if (v >= 0.0f) atomicMax(addr, __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(MEL_THREADS)
+logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ file_off,
+                  const int64_t* __restrict__ frame_off, const int* __restrict__ tile_off,
+                  int n_files, const MelTables* __restrict__ tab, float* __restrict__ raw,
+                  int* __restrict__ fmax) {
+    extern __shared__ float smem[];
+    float* s_pcm = smem;                                       // SPAN
+    float* s_win = s_pcm + SPAN;                               // 400
+    float2* s_tw = reinterpret_cast<float2*>(s_win + 400);     // 400
+    float2* s_scr = s_tw + 400;                                // FFTS * SCR
+    float* s_pow = reinterpret_cast<float*>(s_scr + FFTS * SCR);  // 16 * POW_LD
+    float* s_fbw = s_pow + 16 * POW_LD;                        // 400
+    int* s_fbi = reinterpret_cast<int*>(s_fbw + 400);          // start[80], len[80], off[80]
+    __shared__ float s_red[8];
+
+    const int tid = threadIdx.x;
+    // tile -> file (binary search over the tile prefix sums)
+    int lo = 0, hi = n_files - 1;
+    const int tile = blockIdx.x;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
+    }
+    const int file = lo;
+    const int64_t N = file_off[file + 1] - file_off[file];
+    const float* x = pcm + file_off[file];
+    const int64_t nf = frame_off[file + 1] - frame_off[file];
+    const int64_t f0 = (int64_t)(tile - tile_off[file]) * FPT;
+
+    for (int i = tid; i < 400; i += MEL_THREADS) {
+        s_win[i] = tab->window[i];
+        s_tw[i] = make_float2(tab->tw_re[i], tab->tw_im[i]);
+        s_fbw[i] = tab->fb_w[i];
+    }
+    for (int i = tid; i < 240; i += MEL_THREADS) s_fbi[i] = tab->fb_idx[i];
+    for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j] = padded_sample(x, N, f0 * 160 + j);
+    __syncthreads();
+
+    const int g = tid / 20, r = tid % 20;      // FFT group, row/col index
+    float tmax = -INFINITY;
+
+    for (int pass = 0; pass < FPT / 16; ++pass) {
+        // ---- step 1: 20-pt DFT over n1 for column n2 = r, twiddle, scatter ----
+        {
+            const int fa = pass * 16 + 2 * g;             // tile-local frame A (B = A + 1)
+            const float* pa = s_pcm + fa * 160;
+            c32 v[20];
+#pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) {
+                int i = 20 * n1 + r;
+                float w = s_win[i];
+                v[n1] = {pa[i] * w, pa[160 + i] * w};
+            }
+            dft20(v);
+            float2* scr = s_scr + g * SCR;
+#pragma unroll
+            for (int k1 = 0; k1 < 20; ++k1) {
+                float2 t = s_tw[r * k1];
+                c32 z = cmul(v[k1], c32{t.x, t.y});
+                scr[k1 * 21 + r] = make_float2(z.x, z.y);
+            }
+        }
+        __syncthreads();
+        // ---- step 2: 20-pt DFT over n2 for row k1 = r ----
+        {
+            float2* scr = s_scr + g * SCR;
+            c32 v[20];
+#pragma unroll
+            for (int n2 = 0; n2 < 20; ++n2) {
+                float2 t = scr[r * 21 + n2];
+                v[n2] = {t.x, t.y};
+            }
+            dft20(v);
+            __syncthreads();                               // everyone has read its row
+#pragma unroll
+            for (int k2 = 0; k2 < 20; ++k2) scr[r + 20 * k2] = make_float2(v[k2].x, v[k2].y);
+        }
+        __syncthreads();
+        // ---- power spectra of both packed frames, k = 0..200 ----
+        for (int it = tid; it < FFTS * 201; it += MEL_THREADS) {
+            int gg = it / 201, k = it - gg * 201;
+            const float2* scr = s_scr + gg * SCR;
+            float2 z = scr[k];
+            float2 c = scr[k == 0 ? 0 : 400 - k];
+            float ar = z.x + c.x, ai = z.y - c.y;          // 2*A[k]
+            float br = z.x - c.x, bi = z.y + c.y;          // 2i*B[k]
+            s_pow[(2 * gg) * POW_LD + k] = 0.25f * (ar * ar + ai * ai);
+            s_pow[(2 * gg + 1) * POW_LD + k] = 0.25f * (br * br + bi * bi);
+        }
+        __syncthreads();
+        // ---- mel filterbank (sequential f32 sum in k order, main.rs:484-490), log10 ----
+        const int64_t fbase = f0 + pass * 16;
+        for (int it = tid; it < 16 * 80; it += MEL_THREADS) {
+            int fl = it / 80, m = it - fl * 80;
+            if (fbase + fl < nf) {
+                const float* p = s_pow + fl * POW_LD + s_fbi[m];
+                const float* w = s_fbw + s_fbi[160 + m];
+                int len = s_fbi[80 + m];
+                float e = 0.0f;
+                for (int j = 0; j < len; ++j) e = __fadd_rn(e, __fmul_rn(w[j], p[j]));
+                float lv = log10f(fmaxf(e, 1e-10f));
+                raw[(frame_off[file] + fbase) * 80 + it] = lv;
+                tmax = fmaxf(tmax, lv);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- block max -> one atomic per tile ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = tmax;
+    __syncthreads();
+    if (tid == 0) {
+        float m = s_red[0];
+        for (int w = 1; w < MEL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+        if (m > -INFINITY) atomic_max_float(fmax + file, m);
+    }
+}
+
+template <typename T> __device__ __forceinline__ T to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+// K1b: one CTA row-block per chunk; out [chunk][3002][n_mels], rows 0 and 3001 stay zero.
+template <typename T>
+__global__ void mel_chunks_kernel(const float* __restrict__ raw, const int64_t* __restrict__ frame_off,
+                                  const int* __restrict__ fmax, const MelChunk* __restrict__ chunks,
+                                  T* __restrict__ out, int chunk0) {
+    const int c = blockIdx.y;
+    const MelChunk ch = chunks[chunk0 + c];
+    const int64_t nf = frame_off[ch.file + 1] - frame_off[ch.file];
+    const float floor_v = __int_as_float(fmax[ch.file]) - 8.0f;
+    const float* src = raw + (frame_off[ch.file] + ch.frame_start) * 80;
+    T* dst = out + (size_t)c * (WB_N_FRAMES + 2) * 80;
+    const int total = (WB_N_FRAMES + 2) * 80;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int row = i / 80;
+        int t = row - 1;
+        float v = 0.0f;                                           // literal 0.0 padding (Q2)
+        if (t >= 0 && t < WB_N_FRAMES && ch.frame_start + t < nf) {
+            float lv = src[i - 80];
+            v = (fmaxf(lv, floor_v) + 4.0f) / 4.0f;               // main.rs:502-506
+        }
+        dst[i] = to_out<T>(v);
+    }
+}
+
+// K1c: reference layout out[m][f] for f in [0,n_out), source frames frame0+f (valid if < nf).
+__global__ void mel_export_kernel(const float* __restrict__ raw, int64_t frame_base, int64_t frame0,
+                                  int64_t nf, const int* __restrict__ fmax, int file,
+                                  float* __restrict__ out, int64_t n_out) {
+    __shared__ float tile[32][81];
+    const float floor_v = __int_as_float(fmax[file]) - 8.0f;
+    const int64_t fb = (int64_t)blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * 80; i += blockDim.x) {
+        int fl = i / 80, m = i - fl * 80;
+        int64_t f = frame0 + fb + fl;
+        float v = 0.0f;
+        if (fb + fl < n_out && f < nf) v = (fmaxf(raw[(frame_base + f) * 80 + m], floor_v) + 4.0f) / 4.0f;
+        tile[fl][m] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 80; i += blockDim.x) {
+        int m = i / 32, fl = i - m * 32;
+        if (fb + fl < n_out) out[(int64_t)m * n_out + fb + fl] = tile[fl][m];
+    }
+}
+
+// host mel [B][n_mels][3000] (reference layout) -> time-major padded compute-dtype buffer
+template <typename T>
+__global__ void mel_transpose_in_kernel(const float* __restrict__ in, T* __restrict__ out, int n_mels) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const float* src = in + (size_t)b * n_mels * WB_N_FRAMES;
+    T* dst = out + (size_t)b * (WB_N_FRAMES + 2) * n_mels;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int m = m0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (m < n_mels && t < WB_N_FRAMES) ? src[(size_t)m * WB_N_FRAMES + t] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int t = t0 + i, m = m0 + threadIdx.x;
+        if (t < WB_N_FRAMES && m < n_mels) dst[(size_t)(t + 1) * n_mels + m] = to_out<T>(tile[threadIdx.x][i]);
+    }
+}
+
+constexpr size_t MEL_SMEM = sizeof(float) * (SPAN + 400 + 800 + 2 * FFTS * SCR + 16 * POW_LD + 400 + 240);
+
+}  // namespace
+
+// ---------------- host side ----------------
+void mel_build_tables(MelTables& t) {
+    // main.rs:323-330
+    for (int i = 0; i < 400; ++i) {
+        float x = (3.14159265358979323846f * 2.0f * (float)i) / 400.0f;
+        t.window[i] = 0.5f - 0.5f * cosf(x);
+    }
+    for (int k = 0; k < 400; ++k) {
+        double a = -2.0 * 3.14159265358979323846 * (double)k / 400.0;
+        t.tw_re[k] = (float)cos(a);
+        t.tw_im[k] = (float)sin(a);
+    }
+    // main.rs:332-405 (Slaney mel scale + area normalisation), f32 throughout
+    auto hz_to_mel = [](float hz) {
+        const float logstep = 27.0f / logf(6.4f);
+        float mel = 3.0f * hz / 200.0f;
+        if (hz >= 1000.0f) mel = 15.0f + logf(hz / 1000.0f) * logstep;
+        return mel;
+    };
+    auto mel_to_hz = [](float mel) {
+        const float logstep = logf(6.4f) / 27.0f;
+        float hz = 200.0f * mel / 3.0f;
+        if (mel >= 15.0f) hz = 1000.0f * expf(logstep * (mel - 15.0f));
+        return hz;
+    };
+    const int n_mels = 80, n_freq = 201;
+    float fmax_hz = fminf(8000.0f, 16000.0f / 2.0f);
+    float mel_min = hz_to_mel(0.0f), mel_max = hz_to_mel(fmax_hz);
+    float fp[82], ff[201];
+    for (int i = 0; i < n_mels + 2; ++i) {
+        float m = mel_min + (mel_max - mel_min) * (float)i / (float)(n_mels + 1);
+        fp[i] = mel_to_hz(m);
+    }
+    for (int k = 0; k < n_freq; ++k) ff[k] = (float)k * 8000.0f / (float)(n_freq - 1);
+    std::vector<float> fb((size_t)n_mels * n_freq);
+    for (int m = 0; m < n_mels; ++m) {
+        float dl = fmaxf(fp[m + 1] - fp[m], 1e-6f), dr = fmaxf(fp[m + 2] - fp[m + 1], 1e-6f);
+        float enorm = 2.0f / fmaxf(fp[m + 2] - fp[m], 1e-6f);
+        for (int k = 0; k < n_freq; ++k) {
+            float lower = (ff[k] - fp[m]) / dl, upper = (fp[m + 2] - ff[k]) / dr;
+            float w = fmaxf(fminf(lower, upper), 0.0f);
+            fb[(size_t)m * n_freq + k] = w * enorm;
+        }
+    }
+    // compact: contiguous non-zero run per mel (zeros contribute exactly 0 to the f32 sum)
+    int off = 0;
+    for (int i = 0; i < 400; ++i) t.fb_w[i] = 0.0f;
+    for (int m = 0; m < n_mels; ++m) {
+        int s = 0, e = 0;
+        bool any = false;
+        for (int k = 0; k < n_freq; ++k)
+            if (fb[(size_t)m * n_freq + k] != 0.0f) {
+                if (!any) s = k;
+                any = true;
+                e = k + 1;
+            }
+        if (!any) { s = 0; e = 0; }
+        WB_REQUIRE(off + (e - s) <= 400, WB_EINVAL, "mel filterbank has too many non-zeros");
+        t.fb_idx[m] = s;
+        t.fb_idx[80 + m] = e - s;
+        t.fb_idx[160 + m] = off;
+        for (int k = s; k < e; ++k) t.fb_w[off++] = fb[(size_t)m * n_freq + k];
+    }
+}
+
+int64_t mel_n_frames(int64_t n) {
+    int64_t nf = 1 + n / 160;          // 1 + (n + 400 - 400)/160, main.rs:444-448
+    if (nf > 1) nf -= 1;               // dropped last frame, :450-452
+    return nf;
+}
+
+void mel_launch_raw(wb_ctx* ctx) {
+    MelState& s = ctx->mel;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MEL_SMEM));
+        attr_done = true;
+    }
+    // -inf as int bits
+    std::vector<int> init(s.n_files, (int)0xff800000u);
+    CUDA_CHECK(cudaMemcpyAsync(s.fmax.p, init.data(), sizeof(int) * s.n_files, cudaMemcpyHostToDevice, ctx->stream));
+    logmel_raw_kernel<<<s.total_tiles, MEL_THREADS, MEL_SMEM, ctx->stream>>>(
+        s.pcm.p, s.file_off.p, s.frame_off.p, s.tile_off.p, s.n_files, ctx->mel_tables_dev, s.raw.p, s.fmax.p);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->timing.mel_launches += 1;
+}
+
+void mel_launch_chunks(wb_ctx* ctx, int chunk0, int n, void* out) {
+    MelState& s = ctx->mel;
+    dim3 grid(60, n);
+    if (ctx->cfg.precision == WB_PREC_BF16)
+        mel_chunks_kernel<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(s.raw.p, s.frame_off.p, s.fmax.p, s.chunks.p, (__nv_bfloat16*)out, chunk0);
+    else
+        mel_chunks_kernel<float><<<grid, 256, 0, ctx->stream>>>(s.raw.p, s.frame_off.p, s.fmax.p, s.chunks.p, (float*)out, chunk0);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->timing.mel_launches += 1;
+}
+
+void mel_launch_export(wb_ctx* ctx, int file, int64_t frame0, int64_t n_out, float* out_dev) {
+    MelState& s = ctx->mel;
+    int64_t nf = s.h_frame_off[file + 1] - s.h_frame_off[file];
+    int blocks = (int)ceil_div64(n_out, 32);
+    mel_export_kernel<<<blocks, 256, 0, ctx->stream>>>(s.raw.p, s.h_frame_off[file], frame0, nf, s.fmax.p, file, out_dev, n_out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void mel_launch_transpose_in(wb_ctx* ctx, const float* in_dev, void* out, int B) {
+    int n_mels = ctx->cfg.n_mels;
+    dim3 grid(ceil_div(WB_N_FRAMES, 32), ceil_div(n_mels, 32), B), block(32, 8);
+    if (ctx->cfg.precision == WB_PREC_BF16)
+        mel_transpose_in_kernel<__nv_bfloat16><<<grid, block, 0, ctx->stream>>>(in_dev, (__nv_bfloat16*)out, n_mels);
+    else
+        mel_transpose_in_kernel<float><<<grid, block, 0, ctx->stream>>>(in_dev, (float*)out, n_mels);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// CPU emulation of the kernel's FFT data flow (same mel_math.h code) for the no-GPU unit test.
+extern "C" int wb_selftest_fft400(const float* re, const float* im, float* out_re, float* out_im) {
+    std::vector<c32> scr(SCR), X(400);
+    for (int n2 = 0; n2 < 20; ++n2) {
+        c32 v[20];
+        for (int n1 = 0; n1 < 20; ++n1) v[n1] = {re[20 * n1 + n2], im[20 * n1 + n2]};
+        dft20(v);
+        for (int k1 = 0; k1 < 20; ++k1) {
+            double a = -2.0 * 3.14159265358979323846 * (double)(n2 * k1) / 400.0;
+            scr[k1 * 21 + n2] = cmul(v[k1], c32{(float)cos(a), (float)sin(a)});
+        }
+    }
+    for (int k1 = 0; k1 < 20; ++k1) {
+        c32 v[20];
+        for (int n2 = 0; n2 < 20; ++n2) v[n2] = scr[k1 * 21 + n2];
+        dft20(v);
+        for (int k2 = 0; k2 < 20; ++k2) X[k1 + 20 * k2] = v[k2];
+    }
+    for (int k = 0; k < 400; ++k) { out_re[k] = X[k].x; out_im[k] = X[k].y; }
+    return 0;
+}
