@@ -128,6 +128,15 @@ int wb_transcribe_resident(wb_ctx* ctx, const int64_t* prompt, int prompt_len, i
                            const int64_t* begin_suppress, int n_begin_suppress,
                            int64_t* tokens_out, int32_t* lens_out, int cap_chunks);
 
+/* ---- measurement hooks (bench.py): CUDA events on the library's own stream ---- */
+int wb_mark(wb_ctx* ctx, int slot /* 0..7 */);
+int wb_elapsed_ms(wb_ctx* ctx, int slot_a, int slot_b, float* ms_out);   /* syncs on slot_b */
+/* Replays one hot kernel `iters` times on the buffers of the last encode/decode (rotating over
+ * decoder layers so no launch re-reads what the previous one left in L2) and returns the mean
+ * launch duration from CUDA events plus the algorithmic bytes one launch moves.
+ * kernel: "cross_attn" | "vocab_proj" | "logmel". */
+int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg_ms_out, double* bytes_per_launch_out);
+
 /* ---- host-side pieces of the path (C++ in csrc/host/, exported for the CLI and tests) ---- */
 /* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8/s16/s24/s32/f32, channel
  * mean downmix, linear resample to 16 kHz.  *pcm_out is malloc'd; release with wb_host_free. */

@@ -1,0 +1,89 @@
+"""CPU: the oracles against the committed golden vectors (how the oracle is pinned)."""
+import numpy as np
+import pytest
+
+import mel_oracle as mo
+import whisper_ref as wr
+
+
+def test_mel_oracle_matches_hf_feature_extractor_golden(wb, golden_dir):
+    g = np.load(f"{golden_dir}/mel_hf_seed0.npz")
+    x = wb.synth.batch(3, seed=0)
+    for i in range(3):
+        m = mo.log_mel(x[i])
+        assert m.shape == (80, 3000)
+        assert np.abs(m[:, g["frames"]] - g["mel"][i]).max() <= 1e-4
+        assert np.abs(m[:, -4:] - g["edge"][i]).max() <= 1e-4
+
+
+def test_mel_oracle_f32_fft_vs_f64_dft(wb):
+    x = wb.synth.clip(1, seed=2, seconds=4.0)
+    assert np.abs(mo.log_mel(x) - mo.log_mel(x, dft64=True)).max() <= 5e-5
+    re = np.random.default_rng(0).normal(size=400).astype(np.float32)
+    ro, io = mo.fft400(re)
+    ref = np.fft.fft(re.astype(np.float64))
+    assert np.abs(ro - ref.real).max() < 2e-5 and np.abs(io - ref.imag).max() < 2e-5
+
+
+@pytest.mark.parametrize("n,frames", [(1, 1), (159, 1), (160, 1), (161, 1), (320, 1), (399, 2), (480000, 3000), (480159, 3000)])
+def test_mel_frame_count_quirk(n, frames):
+    # main.rs:444-452: 1 + N/160 frames, last dropped when more than one
+    assert mo.n_frames(n) == max(n // 160, 1)
+    assert mo.log_mel(np.full(n, 0.25, np.float32)).shape == (80, max(n // 160, 1))
+
+
+def test_mel_empty_audio_is_an_error():
+    with pytest.raises(ValueError, match="Empty audio"):
+        mo.log_mel(np.zeros(0, np.float32))
+
+
+def test_chunk_slicing_zero_pads_in_mel_space():
+    n = 16000 * 62
+    assert mo.chunk_starts(n) == [0, 400000, 800000]
+    assert mo.chunk_starts(480000) == [0] and mo.chunk_starts(480001) == [0, 400000]
+    mel = np.ones((80, n // 160), np.float32)
+    ch = mo.chunk_mels(mel, n)
+    assert ch.shape == (3, 80, 3000)
+    assert ch[2][:, : 6200 - 5000].min() == 1.0 and np.all(ch[2][:, 1200:] == 0.0)
+
+
+def test_argmax_semantics():
+    row = np.array([1.0, 3.0, 3.0, np.nan, 2.0], np.float32)
+    assert wr.argmax_last_dim_raw(row, None) == 1               # strict '>' keeps the lowest index
+    assert wr.argmax_last_dim_raw(row, {1}) == 2
+    assert wr.argmax_last_dim_raw(row, {0, 1, 2, 3, 4}) == 0    # everything masked
+    assert wr.argmax_last_dim_raw(np.full(4, np.nan, np.float32), None) == 0
+    assert wr.argmax_last_dim_raw(np.full(4, -np.inf, np.float32), None) == 0
+
+
+@pytest.mark.parametrize("tag", ["toy", "base"])
+def test_whisper_oracle_matches_hf_golden(wb, golden_dir, tag):
+    cfg = wb.weights.WHISPER_TOY if tag == "toy" else wb.weights.WHISPER_BASE
+    g = np.load(f"{golden_dir}/hf_whisper_{tag}_seed0.npz")
+    m = wr.WhisperRef(cfg, wb.weights.generate(cfg, 0))
+    x = wb.synth.batch(2, seed=0)
+    mel = np.stack([mo.log_mel(c) for c in x])
+    enc, layers = m.encode(mel, return_layers=True)
+    assert np.abs(layers[0][:, g["rows"]] - g["stem"]).max() <= 2e-5
+    assert np.abs(layers[1][:, g["rows"]] - g["layer0"]).max() <= 2e-5
+    assert np.abs(enc[:, g["rows"]] - g["enc"]).max() <= 2e-5
+    steps = g["tokens"].shape[1] - len(g["prompt"])
+    toks, lg = m.greedy(enc, g["prompt"], steps, 50257, g["suppress"], g["begin_suppress"], return_logits=True)
+    assert np.array_equal(np.array(toks), g["tokens"])
+    assert np.abs(np.stack(lg, 1)[:, :, g["logit_cols"]] - g["logits"]).max() <= 2e-5
+
+
+def test_greedy_loop_control_matches_reference_quirks(wb):
+    cfg = wb.weights.WHISPER_TOY
+    m = wr.WhisperRef(cfg, wb.weights.generate(cfg, 0))
+    enc = m.encode(np.zeros((1, 80, 3000), np.float32))
+    free = m.greedy(enc, [1, 2, 3, 4], 5, eot=10**6)[0]
+    assert len(free) == 9
+    assert len(m.greedy(enc, [1, 2, 3, 4], 0, eot=10**6)[0]) == 5       # step 0 always emits one token
+    stop = free[5]
+    cut = m.greedy(enc, [1, 2, 3, 4], 5, eot=stop)[0]
+    assert cut[-1] == stop and cut == free[: len(cut)]                  # eot kept, then stop
+    # begin_suppress applies to the first generated token only
+    first = free[4]
+    alt = m.greedy(enc, [1, 2, 3, 4], 3, eot=10**6, begin_suppress=[first])[0]
+    assert alt[4] != first

@@ -55,6 +55,9 @@ def lib():
         "wb_get_cfg": [vp, C.POINTER(wb_model_cfg)],
         "wb_get_timing": [vp, C.POINTER(wb_timing)],
         "wb_set_debug": [vp, ci],
+        "wb_mark": [vp, ci],
+        "wb_elapsed_ms": [vp, ci, ci, f32p],
+        "wb_bench_kernel": [vp, cp, ci, ci, f32p, f64p],
         "wb_get_tensor": [vp, cp, f32p, C.c_int64],
         "wb_log_mel": [vp, f32p, i64p, ci, C.c_int64, C.c_int64, f32p, i64p, C.POINTER(ci)],
         "wb_upload_pcm": [vp, f32p, i64p, ci, C.c_int64, C.c_int64, C.POINTER(ci)],
@@ -256,6 +259,39 @@ class Whisper:
         _chk(self.L.wb_transcribe_resident(self.h, pp, len(prompt), max_new_tokens, eot, sp, len(sup), bp, len(bsup),
                                            toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p), n_chunks))
         return [toks[i, :lens[i]].tolist() for i in range(n_chunks)]
+
+    def transcribe_batch_ptr(self, pcm_ptr: int, n_clips: int, clip_len: int, prompt, max_new_tokens, eot,
+                             suppress=(), begin_suppress=(), out=None):
+        """Same as transcribe_batch for equal-length clips living in caller memory (e.g. a pinned
+        host buffer): no Python-side copy of the PCM.  Returns (tokens [n, stride], lens)."""
+        offs = np.arange(n_clips + 1, dtype=np.int64) * clip_len
+        prompt, pp = _i64(prompt)
+        sup, sp = _i64(list(suppress))
+        bsup, bp = _i64(list(begin_suppress))
+        cap = self.cfg.max_chunks
+        stride = len(prompt) + max(1, max_new_tokens)
+        toks = np.full((cap, stride), -1, np.int64) if out is None else out
+        lens, fidx = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        nch = C.c_int(0)
+        _chk(self.L.wb_transcribe_batch(self.h, C.cast(pcm_ptr, f32p), offs.ctypes.data_as(i64p), n_clips,
+                                        pp, len(prompt), max_new_tokens, eot, sp, len(sup), bp, len(bsup),
+                                        toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p), fidx.ctypes.data_as(i32p),
+                                        cap, C.byref(nch)))
+        return toks[:nch.value], lens[:nch.value]
+
+    def mark(self, slot: int):
+        _chk(self.L.wb_mark(self.h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        _chk(self.L.wb_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def bench_kernel(self, kernel: str, B: int, iters: int = 20):
+        """-> (mean launch ms from CUDA events, algorithmic bytes per launch)."""
+        ms, by = C.c_float(0), C.c_double(0)
+        _chk(self.L.wb_bench_kernel(self.h, kernel.encode(), B, iters, C.byref(ms), C.byref(by)))
+        return float(ms.value), float(by.value)
 
     def timing(self) -> dict:
         t = wb_timing()

@@ -212,6 +212,45 @@ int wb_get_timing(const wb_ctx* ctx, wb_timing* out) {
     WB_CATCH
 }
 
+int wb_mark(wb_ctx* ctx, int slot) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(slot >= 0 && slot < 8, WB_EINVAL, "slot out of range");
+    CUDA_CHECK(cudaEventRecord(ctx->marks[slot].e, ctx->stream));
+    WB_CATCH
+}
+
+int wb_elapsed_ms(wb_ctx* ctx, int a, int b, float* ms_out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(a >= 0 && a < 8 && b >= 0 && b < 8 && ms_out, WB_EINVAL, "bad argument");
+    CUDA_CHECK(cudaEventSynchronize(ctx->marks[b].e));
+    CUDA_CHECK(cudaEventElapsedTime(ms_out, ctx->marks[a].e, ctx->marks[b].e));
+    WB_CATCH
+}
+
+int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg_ms_out, double* bytes_out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(kernel && avg_ms_out && bytes_out && iters > 0, WB_EINVAL, "bad argument");
+    if (std::string(kernel) == "logmel") {
+        WB_REQUIRE(ctx->mel.n_files > 0, WB_ESTATE, "no PCM resident");
+        CudaEvent e0, e1;
+        mel_launch_raw(ctx);
+        CUDA_CHECK(cudaEventRecord(e0.e, ctx->stream));
+        for (int i = 0; i < iters; ++i) mel_launch_raw(ctx);
+        CUDA_CHECK(cudaEventRecord(e1.e, ctx->stream));
+        CUDA_CHECK(cudaEventSynchronize(e1.e));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0.e, e1.e));
+        *avg_ms_out = ms / iters;
+        *bytes_out = 4.0 * (double)(ctx->mel.h_file_off[ctx->mel.n_files]) + 4.0 * 80.0 * (double)ctx->mel.total_frames;
+    } else {
+        decoder_bench(ctx, kernel, B, iters, avg_ms_out, bytes_out);
+    }
+    WB_CATCH
+}
+
 int wb_set_debug(wb_ctx* ctx, int on) {
     WB_TRY
     require_ctx(ctx);

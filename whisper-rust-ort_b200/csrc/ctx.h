@@ -108,6 +108,7 @@ struct wb_ctx {
     wb_timing timing{};
     bool debug = false;
     CudaEvent ev0, ev1;
+    CudaEvent marks[8];
     size_t esz() const { return cfg.precision == WB_PREC_BF16 ? 2 : 4; }
 };
 
@@ -159,4 +160,5 @@ struct DecodeParams {
     bool want_logits;
 };
 void decoder_run(wb_ctx* ctx, const DecodeParams& p);           // async on ctx->stream
+void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg_ms, double* bytes);
 void decoder_fetch(wb_ctx* ctx, const DecodeParams& p, int64_t* tokens_out, int32_t* lens_out, float* logits_out);

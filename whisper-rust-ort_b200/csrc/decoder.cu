@@ -500,6 +500,42 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     ctx->timing.decode_steps = steps;
 }
 
+// Microbenchmark hook for bench.py's roofline block: replays one kernel on live buffers.
+void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg_ms, double* bytes) {
+    const wb_model_cfg& c = ctx->cfg;
+    DecBufs& D = ctx->dec;
+    const int d = c.d_model, H = c.n_heads, Tk = c.n_audio_ctx;
+    WB_REQUIRE(B >= 1 && B <= ctx->enc.B_valid, WB_ESTATE, "bench needs %d encoded sequences", B);
+    const bool bf = c.precision == WB_PREC_BF16;
+    const std::string k(kernel);
+    CudaEvent e0, e1;
+    auto launch = [&](int i) {
+        const int l = i % c.dec_layers;
+        if (k == "cross_attn") {
+            const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * Tk * 2 * d * ctx->esz();
+            if (bf) cross_attn_kernel<bf16><<<dim3(H, B), 256, sizeof(float) * Tk, ctx->stream>>>(D.q.p, (const bf16*)ckv, D.att.p, d, Tk);
+            else cross_attn_kernel<float><<<dim3(H, B), 256, sizeof(float) * Tk, ctx->stream>>>(D.q.p, (const float*)ckv, D.att.p, d, Tk);
+        } else if (k == "vocab_proj") {
+            LinearW dummy;
+            if (bf) skinny<bf16>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
+            else skinny<float>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
+        } else {
+            WB_THROW(WB_EINVAL, "unknown bench kernel '%s'", kernel);
+        }
+    };
+    launch(0);
+    CUDA_CHECK(cudaEventRecord(e0.e, ctx->stream));
+    for (int i = 0; i < iters; ++i) launch(i + 1);
+    CUDA_CHECK(cudaEventRecord(e1.e, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(e1.e));
+    CUDA_CHECK(cudaGetLastError());
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0.e, e1.e));
+    *avg_ms = ms / iters;
+    if (k == "cross_attn") *bytes = (double)B * 2.0 * Tk * d * ctx->esz() + (double)B * d * 8.0;      // K+V stream, q in, out
+    else *bytes = (double)c.vocab * d * ctx->esz() + (double)B * c.vocab * 4.0 + (double)B * d * 4.0;  // weights, logits out
+}
+
 void decoder_fetch(wb_ctx* ctx, const DecodeParams& p, int64_t* tokens_out, int32_t* lens_out, float* logits_out) {
     const wb_model_cfg& c = ctx->cfg;
     DecBufs& D = ctx->dec;

@@ -181,25 +181,41 @@ inline std::string escape(const std::string& s) {
     return o + "\"";
 }
 
-// Shortest round-trip f64 formatting in serde_json/ryu style ("14.884440201999999", "1.0", "1e-9").
+// Shortest round-trip f64 formatting with ryu's "pretty" layout, which is what serde_json emits
+// ("14.884440201999999", "1.0", "0.0000482", "4.82e-6", "1e16").
 inline std::string fmt_f64(double v) {
     if (std::isnan(v) || std::isinf(v)) return "null";       // serde_json writes null
-    char buf[40];
-    for (int prec = 1; prec <= 17; ++prec) {
-        snprintf(buf, sizeof(buf), "%.*g", prec, v);
+    if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[48];
+    int prec = 0;
+    for (; prec <= 16; ++prec) {
+        snprintf(buf, sizeof(buf), "%.*e", prec, v);
         if (std::strtod(buf, nullptr) == v) break;
     }
-    std::string s(buf);
-    size_t epos = s.find('e');
-    if (epos == std::string::npos) {
-        if (s.find('.') == std::string::npos) s += ".0";
-        return s;
+    std::string t(buf);
+    const bool neg = t[0] == '-';
+    if (neg) t.erase(0, 1);
+    const size_t epos = t.find('e');
+    std::string digits;
+    for (size_t i = 0; i < epos; ++i) if (t[i] != '.') digits += t[i];
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int e10 = std::atoi(t.c_str() + epos + 1);
+    const int len = (int)digits.size();
+    const int k = e10 - (len - 1);          // value = digits * 10^k
+    const int kk = len + k;                 // position of the decimal point
+    std::string out;
+    if (k >= 0 && kk <= 16) {
+        out = digits + std::string((size_t)k, '0') + ".0";
+    } else if (kk > 0 && kk <= 16) {
+        out = digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+    } else if (kk > -5 && kk <= 0) {
+        out = "0." + std::string((size_t)(-kk), '0') + digits;
+    } else if (len == 1) {
+        out = digits + "e" + std::to_string(kk - 1);
+    } else {
+        out = digits.substr(0, 1) + "." + digits.substr(1) + "e" + std::to_string(kk - 1);
     }
-    // ryu prints exponents without '+' or leading zeros, mantissa keeps ".0" dropped: 1e-9, 1.5e-7
-    std::string mant = s.substr(0, epos), ex = s.substr(epos + 1);
-    int e = std::atoi(ex.c_str());
-    // serde_json (ryu) uses plain decimals for 1e-5 <= |v| < 1e16; %g switches at 1e-5 too.
-    return mant + "e" + std::to_string(e);
+    return neg ? "-" + out : out;
 }
 
 }  // namespace wbjson

@@ -1,0 +1,62 @@
+// utf8.h — the few Unicode operations the reference's Rust std calls imply (char iteration,
+// White_Space, simple lowercase) without ICU.  Lowercasing covers ASCII, Latin-1, Latin Extended-A,
+// Greek and Cyrillic — the scripts Whisper emits with case; other code points map to themselves.
+#pragma once
+#include <cstdint>
+#include <string>
+
+namespace wbutf8 {
+
+// Decode one code point at s[i], advance i. Invalid bytes decode as U+FFFD and advance by one.
+inline uint32_t decode(const std::string& s, size_t& i) {
+    const unsigned char c = (unsigned char)s[i];
+    auto cont = [&](size_t k) { return i + k < s.size() && ((unsigned char)s[i + k] & 0xC0) == 0x80; };
+    if (c < 0x80) { i += 1; return c; }
+    if ((c & 0xE0) == 0xC0 && cont(1)) {
+        uint32_t cp = ((c & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu);
+        i += 2;
+        return cp;
+    }
+    if ((c & 0xF0) == 0xE0 && cont(1) && cont(2)) {
+        uint32_t cp = ((c & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) | ((unsigned char)s[i + 2] & 0x3Fu);
+        i += 3;
+        return cp;
+    }
+    if ((c & 0xF8) == 0xF0 && cont(1) && cont(2) && cont(3)) {
+        uint32_t cp = ((c & 0x07u) << 18) | (((unsigned char)s[i + 1] & 0x3Fu) << 12) |
+                      (((unsigned char)s[i + 2] & 0x3Fu) << 6) | ((unsigned char)s[i + 3] & 0x3Fu);
+        i += 4;
+        return cp;
+    }
+    i += 1;
+    return 0xFFFD;
+}
+
+inline void encode(std::string& out, uint32_t cp) {
+    if (cp < 0x80) out += (char)cp;
+    else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+    else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+    else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+}
+
+inline bool is_whitespace(uint32_t c) {      // Unicode White_Space (what Rust's char::is_whitespace tests)
+    return (c >= 0x09 && c <= 0x0D) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 ||
+           (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+
+inline uint32_t to_lower(uint32_t c) {
+    if (c >= 'A' && c <= 'Z') return c + 32;
+    if (c < 0x80) return c;
+    if ((c >= 0xC0 && c <= 0xDE) && c != 0xD7) return c + 32;                 // Latin-1
+    if (c >= 0x100 && c <= 0x137) return (c & 1) ? c : c + 1;                   // Latin Extended-A pairs
+    if (c >= 0x139 && c <= 0x148) return (c & 1) ? c + 1 : c;
+    if (c >= 0x14A && c <= 0x177) return (c & 1) ? c : c + 1;
+    if (c == 0x178) return 0xFF;
+    if (c >= 0x179 && c <= 0x17E) return (c & 1) ? c + 1 : c;
+    if (c >= 0x391 && c <= 0x3A9 && c != 0x3A2) return c + 32;                  // Greek
+    if (c >= 0x410 && c <= 0x42F) return c + 32;                                // Cyrillic
+    if (c >= 0x400 && c <= 0x40F) return c + 80;
+    return c;
+}
+
+}  // namespace wbutf8
