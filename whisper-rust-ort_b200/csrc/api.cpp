@@ -163,6 +163,7 @@ int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* wei
         ctx = new wb_ctx();
         ctx->cfg = *cfg;
         ctx->device = device;
+        ctx->sm_count = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         mel_build_tables(ctx->mel_tables);
         CUDA_CHECK(cudaMalloc(&ctx->mel_tables_dev, sizeof(MelTables)));
@@ -191,6 +192,7 @@ void wb_destroy(wb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     weights_free(ctx);
+    if (ctx->dec.graph_exec) cudaGraphExecDestroy(ctx->dec.graph_exec);
     if (ctx->mel_tables_dev) cudaFree(ctx->mel_tables_dev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -93,6 +93,10 @@ struct DecBufs {
     DevBuf<int> lens, finished, state; // state: [0]=position t, [1]=#unfinished
     DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
     int T_max = 0;
+    // whole-decode CUDA graph (all steps), rebuilt when the key changes
+    cudaGraphExec_t graph_exec = nullptr;
+    int g_key[6] = {-1, -1, -1, -1, -1, -1};
+    int g_launches = 0;
 };
 
 struct wb_ctx {
@@ -107,6 +111,7 @@ struct wb_ctx {
     DecBufs dec;
     wb_timing timing{};
     bool debug = false;
+    int sm_count = 148;
     CudaEvent ev0, ev1;
     CudaEvent marks[8];
     size_t esz() const { return cfg.precision == WB_PREC_BF16 ? 2 : 4; }
