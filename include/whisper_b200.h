@@ -137,6 +137,11 @@ int wb_elapsed_ms(wb_ctx* ctx, int slot_a, int slot_b, float* ms_out);   /* sync
  * kernel: "cross_attn" | "vocab_proj" | "logmel". */
 int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg_ms_out, double* bytes_per_launch_out);
 
+/* Test hook: runs one bf16 GEMM (A[M,K] row stride lda, W[N,K]) with bias+GELU+f32 residual through the
+ * tcgen05 kernel and through the SIMT kernel on the same seeded operands; returns the largest
+ * |difference| and the largest |SIMT value| (flags bit0: f32 output instead of bf16). */
+int wb_selftest_gemm(wb_ctx* ctx, int M, int N, int K, int lda, int batch, int flags, float* max_diff_out, float* max_abs_out);
+
 /* ---- host-side pieces of the path (C++ in csrc/host/, exported for the CLI and tests) ---- */
 /* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8/s16/s24/s32/f32, channel
  * mean downmix, linear resample to 16 kHz.  *pcm_out is malloc'd; release with wb_host_free. */

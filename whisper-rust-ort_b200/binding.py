@@ -55,6 +55,7 @@ def lib():
         "wb_get_cfg": [vp, C.POINTER(wb_model_cfg)],
         "wb_get_timing": [vp, C.POINTER(wb_timing)],
         "wb_set_debug": [vp, ci],
+        "wb_selftest_gemm": [vp, ci, ci, ci, ci, ci, ci, f32p, f32p],
         "wb_mark": [vp, ci],
         "wb_elapsed_ms": [vp, ci, ci, f32p],
         "wb_bench_kernel": [vp, cp, ci, ci, f32p, f64p],
@@ -278,6 +279,12 @@ class Whisper:
                                         toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p), fidx.ctypes.data_as(i32p),
                                         cap, C.byref(nch)))
         return toks[:nch.value], lens[:nch.value]
+
+    def selftest_gemm(self, M, N, K, lda=None, batch=1, f32_out=False):
+        """tcgen05 kernel vs SIMT kernel on seeded bf16 operands -> (max |diff|, max |value|)."""
+        d, a = C.c_float(0), C.c_float(0)
+        _chk(self.L.wb_selftest_gemm(self.h, M, N, K, lda if lda else K, batch, int(f32_out), C.byref(d), C.byref(a)))
+        return float(d.value), float(a.value)
 
     def mark(self, slot: int):
         _chk(self.L.wb_mark(self.h, slot))

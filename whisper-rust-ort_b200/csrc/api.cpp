@@ -1,5 +1,6 @@
 // api.cpp — the extern "C" surface of include/whisper_b200.h over the CUDA path.
 // No exception crosses the boundary: every entry point converts to a status code + message.
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -250,6 +251,58 @@ int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* av
     } else {
         decoder_bench(ctx, kernel, B, iters, avg_ms_out, bytes_out);
     }
+    WB_CATCH
+}
+
+int wb_selftest_gemm(wb_ctx* ctx, int M, int N, int K, int lda, int batch, int flags, float* max_diff_out, float* max_abs_out) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(M > 0 && N > 0 && K > 0 && lda > 0 && batch > 0 && max_diff_out && max_abs_out, WB_EINVAL, "bad argument");
+    const bool f32out = flags & 1;
+    // A rows may overlap (lda < K), as in the conv stem: allocate what the last row touches
+    const size_t a_batch = (size_t)(M - 1) * lda + K + 8, a_elems = a_batch * batch;
+    std::vector<__nv_bfloat16> hA(a_elems), hW((size_t)N * K);
+    std::vector<float> hb(N), hres((size_t)batch * M * N);
+    uint32_t st = 12345u;
+    auto rnd = [&]() { st = st * 1664525u + 1013904223u; return ((st >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+    for (auto& v : hA) v = __float2bfloat16(rnd());
+    for (auto& v : hW) v = __float2bfloat16(rnd() * 0.25f);
+    for (auto& v : hb) v = rnd();
+    for (auto& v : hres) v = rnd();
+    DevBuf<__nv_bfloat16> dA, dW;
+    DevBuf<float> db, dres0, dres1;
+    DevBuf<unsigned char> c0, c1;
+    const size_t out_elems = (size_t)batch * M * N, esz = f32out ? 4 : 2;
+    dA.reserve(a_elems); dW.reserve(hW.size()); db.reserve(N); dres0.reserve(out_elems); dres1.reserve(out_elems);
+    c0.reserve(out_elems * esz); c1.reserve(out_elems * esz);
+    CUDA_CHECK(cudaMemcpy(dA.p, hA.data(), a_elems * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dW.p, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(db.p, hb.data(), N * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dres0.p, hres.data(), out_elems * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dres1.p, hres.data(), out_elems * 4, cudaMemcpyHostToDevice));
+    GemmArgs g;
+    g.A = dA.p; g.B = dW.p; g.ta = g.tb = WB_BF16; g.tc = f32out ? WB_F32 : WB_BF16;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = K; g.ldc = N; g.batch = batch; g.inner = 1;
+    g.sAo = (long long)a_batch; g.sCo = (long long)M * N; g.bias = db.p; g.act = 1;
+    WB_REQUIRE(gemm_tc_eligible(g), WB_EINVAL, "shape not eligible for the tcgen05 kernel");
+    g.C = c0.p; g.residual = dres0.p;
+    gemm_tc(ctx, g);
+    g.C = c1.p; g.residual = dres1.p;
+    gemm_simt(ctx, g);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::vector<unsigned char> h0(out_elems * esz), h1(out_elems * esz);
+    CUDA_CHECK(cudaMemcpy(h0.data(), c0.p, h0.size(), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(h1.data(), c1.p, h1.size(), cudaMemcpyDeviceToHost));
+    float md = 0.f, ma = 0.f;
+    for (size_t i = 0; i < out_elems; ++i) {
+        float x0, x1;
+        if (f32out) { x0 = reinterpret_cast<float*>(h0.data())[i]; x1 = reinterpret_cast<float*>(h1.data())[i]; }
+        else { x0 = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(h0.data())[i]); x1 = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(h1.data())[i]); }
+        float d = std::fabs(x0 - x1);
+        if (!(d <= md)) md = d;            // NaN-propagating max
+        if (std::fabs(x1) > ma) ma = std::fabs(x1);
+    }
+    *max_diff_out = md; *max_abs_out = ma;
     WB_CATCH
 }
 

@@ -147,7 +147,10 @@ struct GemmArgs {
     const float* residual = nullptr;    // f32, same indexing as C (may alias C)
 };
 void gemm_simt(wb_ctx* ctx, const GemmArgs& a);
-// dispatcher: tensor-core kernel when eligible (bf16, aligned), else SIMT
+// gemm_tc.cu — tcgen05/TMEM/TMA kernel (bf16 operands, K-major, N % 128 == 0)
+bool gemm_tc_eligible(const GemmArgs& a);
+void gemm_tc(wb_ctx* ctx, const GemmArgs& a);
+// dispatcher: tensor-core kernel when eligible, else SIMT
 void gemm(wb_ctx* ctx, const GemmArgs& a);
 
 // encoder.cu

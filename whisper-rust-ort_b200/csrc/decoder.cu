@@ -63,6 +63,22 @@ __global__ void embed_kernel(const int* __restrict__ state, const int* __restric
 // X (and its LayerNorm) is staged once per CTA in shared memory with 128-bit loads, then the CTA
 // walks row groups (grid-stride) so the staging is amortised over many weight rows.
 constexpr int SK_WARPS = 8, SK_THREADS = SK_WARPS * 32, SK_BT = 32, SK_KC = 512;
+#define SK_PRE (R == 1 || sizeof(WT) == 2)      // prefetch depth that still fits the register file
+
+template <int R>
+__device__ __forceinline__ void fma_tile(float (&acc)[R * 32], const float (&w)[R][4], const float* xcol, int kc) {
+#pragma unroll
+    for (int bb = 0; bb < 32; ++bb) {
+        const float4 xv = *reinterpret_cast<const float4*>(xcol + bb * kc);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float a = acc[bb * R + r];
+            a = fmaf(w[r][0], xv.x, a); a = fmaf(w[r][1], xv.y, a);
+            a = fmaf(w[r][2], xv.z, a); a = fmaf(w[r][3], xv.w, a);
+            acc[bb * R + r] = a;
+        }
+    }
+}
 
 template <typename WT, int R>
 __global__ void __launch_bounds__(SK_THREADS)
@@ -103,6 +119,20 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
             float acc[R * SK_BT];
 #pragma unroll
             for (int i = 0; i < R * SK_BT; ++i) acc[i] = 0.f;
+            // single-chunk rows: issue every weight load of this row group BEFORE the activations
+            // are staged/normalised, so the HBM/L2 latency hides behind that work
+            float wpre[SK_KC / 128][R][4];
+            if (single_chunk && SK_PRE) {
+#pragma unroll
+                for (int ci = 0; ci < SK_KC / 128; ++ci) {
+                    const int c = ci * 128 + lane * 4;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (c < K && n0 + r < N) load4(W + (size_t)(n0 + r) * K + c, wpre[ci][r]);
+                        else { wpre[ci][r][0] = wpre[ci][r][1] = wpre[ci][r][2] = wpre[ci][r][3] = 0.f; }
+                    }
+                }
+            }
 
             for (int k0 = 0; k0 < K; k0 += SK_KC) {
                 const int kc = min(SK_KC, K - k0);
@@ -149,23 +179,23 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
                         __syncthreads();
                     }
                 }
-                for (int c = lane * 4; c < kc; c += 128) {
-                    float w[R][4];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if (n0 + r < N) load4(W + (size_t)(n0 + r) * K + k0 + c, w[r]);
-                        else { w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0.f; }
-                    }
-#pragma unroll
-                    for (int bb = 0; bb < SK_BT; ++bb) {
-                        const float4 xv = *reinterpret_cast<const float4*>(xs + bb * kc + c);
+                // weights of this chunk (prefetched below, before the staging, when single_chunk)
+                if (!(single_chunk && SK_PRE)) {
+#pragma unroll 1
+                    for (int c = lane * 4; c < kc; c += 128) {
+                        float w[R][4];
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            float a = acc[bb * R + r];
-                            a = fmaf(w[r][0], xv.x, a); a = fmaf(w[r][1], xv.y, a);
-                            a = fmaf(w[r][2], xv.z, a); a = fmaf(w[r][3], xv.w, a);
-                            acc[bb * R + r] = a;
+                            if (n0 + r < N) load4(W + (size_t)(n0 + r) * K + k0 + c, w[r]);
+                            else { w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0.f; }
                         }
+                        fma_tile<R>(acc, w, xs + c, kc);
+                    }
+                } else {
+#pragma unroll
+                    for (int ci = 0; ci < SK_KC / 128; ++ci) {
+                        const int c = ci * 128 + lane * 4;
+                        if (c < kc) fma_tile<R>(acc, wpre[ci], xs + c, kc);
                     }
                 }
             }

@@ -252,4 +252,7 @@ void encoder_forward(wb_ctx* ctx, const void* mel_tm, int B) {
     b.B_valid = B;
 }
 
-void gemm(wb_ctx* ctx, const GemmArgs& a) { gemm_simt(ctx, a); }
+void gemm(wb_ctx* ctx, const GemmArgs& a) {
+    if (gemm_tc_eligible(a)) gemm_tc(ctx, a);
+    else gemm_simt(ctx, a);
+}
