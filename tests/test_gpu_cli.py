@@ -1,0 +1,81 @@
+"""GPU: the drop-in CLI end to end on synthetic WAV files — flags, the three output files, their
+schema (key order, rounding) and the transcripts, against the reference's committed outputs and
+the library called directly."""
+import csv
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import host_ref as hr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "whisper-rust-ort_b200", "whisper_b200_cli")
+
+SUMMARY_KEYS = ["breakdown_s", "config_used", "language", "latency_end_to_end_s", "max_new_tokens", "model_id", "n_files",
+                "notes", "onnx_dir", "rtf_end_to_end", "task", "timestamps", "tokenizer_json"]
+STAT_KEYS = ["max", "mean", "median", "min", "p90", "p95"]
+
+
+def test_cli_end_to_end(wb, tmp_path):
+    audio, onnx, out = tmp_path / "audio", tmp_path / "onnx", tmp_path / "out"
+    audio.mkdir(); onnx.mkdir()
+    clips = {"b_long.wav": wb.synth.clip(1, 3, 41.0), "a_short.WAV": wb.synth.clip(2, 3, 7.3), "c.txt": None}
+    for name, x in clips.items():
+        if x is None:
+            (audio / name).write_text("not audio")
+        else:
+            wb.synth.write_wav(str(audio / name), x, fmt="f32")
+    (onnx / "generation_config.json").write_text(json.dumps({"suppress_tokens": [1, 2, 7], "begin_suppress_tokens": [220, 50257]}))
+    cmd = [EXE, "--audio-dir", str(audio), "--onnx-dir", str(onnx), "--max-new-tokens", "6", "--warmup", "1", "--write-txt",
+           "--precision", "fp32", "--batch", "4", "--intra-op", "3", "--chunk-parallelism", "4",
+           "--out-csv", str(out / "per_file.csv"), "--out-json", str(out / "per_file.json"), "--out-summary-json", str(out / "summary.json")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "DONE" and lines[1] == "Config used:" and any(l.startswith("End-to-end p95(s): ") for l in lines)
+
+    summary = json.loads((out / "summary.json").read_text())
+    assert list(summary.keys()) == SUMMARY_KEYS                               # alphabetical, like serde_json
+    assert list(summary["breakdown_s"].keys()) == ["decode_s", "load_s", "model_only_s", "preprocess_s"]
+    assert list(summary["latency_end_to_end_s"].keys()) == STAT_KEYS
+    assert summary["n_files"] == 2 and summary["max_new_tokens"] == 6 and summary["config_used"]["intra_op"] == 3
+    assert summary["tokenizer_json"] == "" and summary["notes"]["token_decode"].startswith("Prints token IDs")
+    ref_p = "/root/reference/results.old/benchmarks/container_4c4g/epyc-9654/without_hf_pipeline_rust/inference_summary.json"
+    if os.path.exists(ref_p):
+        ref = json.loads(open(ref_p).read())
+        assert list(ref.keys()) == SUMMARY_KEYS and list(ref["config_used"].keys()) == list(summary["config_used"].keys())
+
+    rows = json.loads((out / "per_file.json").read_text())
+    assert [r_["file"] for r_ in rows] == ["a_short.WAV", "b_long.wav"]             # sorted, extension case-insensitive
+    assert list(rows[0].keys()) == ["file", "duration_s", "end_to_end_s", "rtf", "text"]
+    assert rows[0]["duration_s"] == 7.3 and rows[1]["duration_s"] == 41.0
+    with open(out / "per_file.csv", newline="") as f:
+        table = list(csv.reader(f))
+    assert table[0] == ["file", "duration_s", "end_to_end_s", "rtf", "text"]
+    assert table[1][1] == "7.300" and table[2][0] == "b_long.wav" and table[2][4] == rows[1]["text"]
+
+    # transcripts: no tokenizer -> "[TOKENS:...]" per chunk, stitched with a space (main.rs:644-647, 659-684)
+    m = wb.Whisper(wb.default_cfg("base", max_batch=4, max_chunks=8))
+    prompt = [50258, 50259, 50359, 50363]
+    for row, name in zip(rows, ["a_short.WAV", "b_long.wav"]):
+        toks, fidx = m.transcribe_batch([clips[name]], prompt, 6, 50257, [1, 2, 7], [220, 50257])
+        texts = [hr.decode_tokens_fallback(t[4:]) for t in toks]
+        assert row["text"] == hr.stitch_texts(texts)
+        stem = name.rsplit(".", 1)[0]
+        assert (out / f"{stem}.transcript.txt").read_text() == row["text"].strip() + "\n"
+    assert len(m.transcribe_batch([clips["b_long.wav"]], prompt, 6, 50257)[0]) == 2    # 41 s -> 2 chunks
+    m.close()
+
+
+def test_cli_unsupported_container_aborts_like_anyhow(wb, tmp_path):
+    audio, onnx = tmp_path / "audio", tmp_path / "onnx"
+    audio.mkdir(); onnx.mkdir()
+    (audio / "x.mp3").write_bytes(b"ID3" + b"\0" * 100)
+    r = subprocess.run([EXE, "--audio-dir", str(audio), "--onnx-dir", str(onnx), "--arch", "toy", "--out-csv", str(tmp_path / "o.csv"),
+                        "--out-json", str(tmp_path / "o.json"), "--out-summary-json", str(tmp_path / "s.json")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "unsupported audio container" in r.stderr
