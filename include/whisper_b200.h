@@ -142,6 +142,10 @@ int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* av
  * |difference| and the largest |SIMT value| (flags bit0: f32 output instead of bf16). */
 int wb_selftest_gemm(wb_ctx* ctx, int M, int N, int K, int lda, int batch, int flags, float* max_diff_out, float* max_abs_out);
 
+/* Test hook (bf16 build): seeded q|k|v for B clips through the tcgen05 attention kernel and the
+ * SIMT attention path; returns the largest |difference| and the largest |SIMT value|. */
+int wb_selftest_attn(wb_ctx* ctx, int B, float* max_diff_out, float* max_abs_out);
+
 /* ---- host-side pieces of the path (C++ in csrc/host/, exported for the CLI and tests) ---- */
 /* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8/s16/s24/s32/f32, channel
  * mean downmix, linear resample to 16 kHz.  *pcm_out is malloc'd; release with wb_host_free. */

@@ -42,6 +42,13 @@ def test_tcgen05_gemm_matches_simt_kernel(fast, M, N, K, lda, batch, f32):
     assert diff <= tol, (diff, mx)
 
 
+@pytest.mark.parametrize("B", [1, 3])
+def test_tcgen05_flash_attention_matches_simt_attention(fast, B):
+    # T = 1500 is not a multiple of the 128-wide tiles: exercises key masking and query-row masking
+    diff, mx = fast.selftest_attn(B)
+    assert diff <= mx * 2.0 ** -6, (diff, mx)          # bf16 outputs, P rounded to bf16 before PV
+
+
 def test_bf16_encoder_within_2e_2_of_fp32_oracle(wb, fast, oracle):
     x = wb.synth.batch(2, seed=0)
     mel = np.stack([mo.log_mel(c) for c in x])

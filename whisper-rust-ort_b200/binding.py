@@ -56,6 +56,7 @@ def lib():
         "wb_get_timing": [vp, C.POINTER(wb_timing)],
         "wb_set_debug": [vp, ci],
         "wb_selftest_gemm": [vp, ci, ci, ci, ci, ci, ci, f32p, f32p],
+        "wb_selftest_attn": [vp, ci, f32p, f32p],
         "wb_mark": [vp, ci],
         "wb_elapsed_ms": [vp, ci, ci, f32p],
         "wb_bench_kernel": [vp, cp, ci, ci, f32p, f64p],
@@ -284,6 +285,12 @@ class Whisper:
         """tcgen05 kernel vs SIMT kernel on seeded bf16 operands -> (max |diff|, max |value|)."""
         d, a = C.c_float(0), C.c_float(0)
         _chk(self.L.wb_selftest_gemm(self.h, M, N, K, lda if lda else K, batch, int(f32_out), C.byref(d), C.byref(a)))
+        return float(d.value), float(a.value)
+
+    def selftest_attn(self, B=1):
+        """tcgen05 flash attention vs SIMT attention on seeded bf16 q|k|v -> (max |diff|, max |value|)."""
+        d, a = C.c_float(0), C.c_float(0)
+        _chk(self.L.wb_selftest_attn(self.h, B, C.byref(d), C.byref(a)))
         return float(d.value), float(a.value)
 
     def mark(self, slot: int):

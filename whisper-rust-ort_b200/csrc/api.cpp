@@ -306,6 +306,38 @@ int wb_selftest_gemm(wb_ctx* ctx, int M, int N, int K, int lda, int batch, int f
     WB_CATCH
 }
 
+int wb_selftest_attn(wb_ctx* ctx, int B, float* max_diff_out, float* max_abs_out) {
+    WB_TRY
+    require_ctx(ctx);
+    const wb_model_cfg& c = ctx->cfg;
+    WB_REQUIRE(c.precision == WB_PREC_BF16, WB_EINVAL, "wb_selftest_attn needs the bf16 build");
+    WB_REQUIRE(B >= 1 && B <= c.max_batch && max_diff_out && max_abs_out, WB_EINVAL, "bad argument");
+    const int T = c.n_audio_ctx, d = c.d_model;
+    const size_t n_in = (size_t)B * T * 3 * d, n_out = (size_t)B * T * d;
+    std::vector<__nv_bfloat16> h(n_in);
+    uint32_t st = 777u;
+    for (auto& v : h) { st = st * 1664525u + 1013904223u; v = __float2bfloat16((((st >> 8) & 0xFFFF) / 65536.0f - 0.5f) * 4.0f); }
+    CUDA_CHECK(cudaMemcpy(ctx->enc.qkv.p, h.data(), n_in * 2, cudaMemcpyHostToDevice));
+    DevBuf<__nv_bfloat16> o0, o1;
+    o0.reserve(n_out); o1.reserve(n_out);
+    CUDA_CHECK(cudaMemset(o0.p, 0xFF, n_out * 2));
+    attn_tc(ctx, ctx->enc.qkv.p, o0.p, B, T, d, c.n_heads);
+    attention_simt(ctx, ctx->enc.qkv.p, o1.p, B);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::vector<__nv_bfloat16> h0(n_out), h1(n_out);
+    CUDA_CHECK(cudaMemcpy(h0.data(), o0.p, n_out * 2, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(h1.data(), o1.p, n_out * 2, cudaMemcpyDeviceToHost));
+    float md = 0.f, ma = 0.f;
+    for (size_t i = 0; i < n_out; ++i) {
+        float x0 = __bfloat162float(h0[i]), x1 = __bfloat162float(h1[i]);
+        float dd = std::fabs(x0 - x1);
+        if (!(dd <= md)) md = dd;
+        if (std::fabs(x1) > ma) ma = std::fabs(x1);
+    }
+    *max_diff_out = md; *max_abs_out = ma;
+    WB_CATCH
+}
+
 int wb_set_debug(wb_ctx* ctx, int on) {
     WB_TRY
     require_ctx(ctx);

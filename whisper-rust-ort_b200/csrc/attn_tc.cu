@@ -1,0 +1,313 @@
+// attn_tc.cu — encoder self-attention of the bf16 build on tcgen05 (kernel K2d): non-causal,
+// T = 1500, head_dim 64.  One CTA per (clip, head, 128-query block); per 128-key block:
+//   S = Q.K^T        tcgen05.mma 128x128x64 (both operands K-major, TMA 128B swizzle) -> TMEM
+//   softmax          4 warps, one query row per thread: tcgen05.ld S, online max/sum in registers,
+//                    P -> bf16 -> shared memory in the UMMA K-major swizzled layout
+//   O_j = P.V        tcgen05.mma 128x64x128 (V consumed MN-major straight from the TMA tile) -> TMEM
+//   O += O_j         in registers (tcgen05.ld), rescaled by exp(m_old - m_new)
+// K/V tiles are double buffered by TMA; the PV MMA of block j overlaps the softmax of block j+1.
+// Replaces the Softmax(QK^T)V sub-graphs ONNX Runtime executes inside encoder.run
+// (/root/reference/src/main.rs:703); same math as oracle/whisper_ref.py::_attend.
+#include <cuda.h>
+
+#include "ctx.h"
+
+namespace {
+
+constexpr int AQ = 128, AK = 128, HD = 64;
+constexpr int ATT_THREADS = 160;                       // warp 0: TMA + MMA issue; warps 1-4: softmax / epilogue
+constexpr uint32_t TILE_BYTES = 128 * 64 * 2;          // one [128 x 64] bf16 tile, 128-byte rows
+constexpr uint32_t ATT_TMEM_COLS = 256;                // S: [0,128)  O_j: [128,192)
+constexpr size_t ATT_SMEM = 7 * TILE_BYTES + 1024 + 128;   // Q, K[2], V[2], P[2 halves]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// SWIZZLE_128B descriptor over [rows][64 bf16] tiles (128-byte rows, 8-row groups 1024 B apart).
+// Valid both for a K-major operand (rows = M/N index) and for an MN-major operand whose MN extent
+// is one 64-element swizzle atom (rows = K index): in both cases the 8-row group stride is SBO.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 16;                  // LBO (only used across MN atoms; single atom here)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // SBO
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// idesc: D f32, A/B bf16, M = 128; N and B-major per use
+__device__ __forceinline__ constexpr uint32_t idesc_of(int n, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int d, int H, int n_qb) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + TILE_BYTES;                   // 2 buffers
+    uint8_t* sV = smem + 3 * TILE_BYTES;               // 2 buffers
+    uint8_t* sP = smem + 5 * TILE_BYTES;               // 2 halves of 64 keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE_BYTES);
+    uint64_t* bar_q = bars;            // 1
+    uint64_t* bar_kv = bars + 1;       // 2
+    uint64_t* bar_kvfree = bars + 3;   // 2
+    uint64_t* bar_s = bars + 5;
+    uint64_t* bar_p = bars + 6;
+    uint64_t* bar_o = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x % n_qb, h = (blockIdx.x / n_qb) % H, b = blockIdx.x / (n_qb * H);
+    const int n_kb = (T + AK - 1) / AK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQKV)) : "memory");
+            mbar_init(bar_q, 1);
+            mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
+            mbar_init(&bar_kvfree[0], 1); mbar_init(&bar_kvfree[1], 1);
+            mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ATT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA + MMA control thread =====
+            const uint32_t idesc_s = idesc_of(128, 0), idesc_o = idesc_of(64, 1);
+            mbar_expect_tx(bar_q, TILE_BYTES);
+            tma_load_3d(&tmQKV, bar_q, sQ, h * HD, qb * AQ, b);
+            mbar_expect_tx(&bar_kv[0], 2 * TILE_BYTES);
+            tma_load_3d(&tmQKV, &bar_kv[0], sK, d + h * HD, 0, b);
+            tma_load_3d(&tmQKV, &bar_kv[0], sV, 2 * d + h * HD, 0, b);
+            mbar_wait(bar_q, 0);
+            const uint64_t dq = make_desc_sw128(smem_u32(sQ));
+            for (int j = 0; j < n_kb; ++j) {
+                const int s = j & 1;
+                mbar_wait(&bar_kv[s], (uint32_t)((j >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t dk = make_desc_sw128(smem_u32(sK + s * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)                        // S = Q K^T, K dim = head_dim
+                    umma(tS, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+                umma_commit(bar_s);
+                if (j + 1 < n_kb) {                                      // prefetch K/V block j+1
+                    const int s1 = (j + 1) & 1;
+                    if (j >= 1) mbar_wait(&bar_kvfree[s1], (uint32_t)(((j - 1) >> 1) & 1));
+                    mbar_expect_tx(&bar_kv[s1], 2 * TILE_BYTES);
+                    tma_load_3d(&tmQKV, &bar_kv[s1], sK + s1 * TILE_BYTES, d + h * HD, (j + 1) * AK, b);
+                    tma_load_3d(&tmQKV, &bar_kv[s1], sV + s1 * TILE_BYTES, 2 * d + h * HD, (j + 1) * AK, b);
+                }
+                mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, O_{j-1} consumed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t dv = make_desc_sw128(smem_u32(sV + s * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < AK / 16; ++k) {                      // O_j = P_j V_j, K dim = keys
+                    const uint64_t dp = make_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES)) + (uint64_t)((k & 3) * 2);
+                    umma(tO, dp, dv + (uint64_t)(k * 128), idesc_o, (uint32_t)(k != 0));   // 16 keys = 16 rows x 128 B
+                }
+                umma_commit(bar_o);
+                umma_commit(&bar_kvfree[s]);
+            }
+        }
+    } else {
+        // ===== softmax + output: thread <-> query row =====
+        const int q = warp & 3;                                          // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;                   // head_dim^-0.5 * log2(e)
+        float m = -INFINITY, l = 0.f;
+        float o[HD];
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        uint8_t* prow = sP + row * 128;
+        const int sw = row & 7;
+
+        for (int j = 0; j < n_kb; ++j) {
+            mbar_wait(bar_s, (uint32_t)(j & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int valid = T - j * AK;                                // keys of this block that exist
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(tS + lane_off + ch * 32, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (ch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+            const float m_new = fmaxf(m, mx * sc);
+            const float alpha = ex2(m - m_new);                          // 0 on the first block (m = -inf)
+            // pass 2: p = exp2(s*sc - m_new) -> bf16 -> swizzled smem; row sum of the rounded values
+            float sum = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(tS + lane_off + ch * 32, r);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = (ch * 32 + 2 * i < valid) ? ex2(fmaf(__uint_as_float(r[2 * i]), sc, -m_new)) : 0.f;
+                    float p1 = (ch * 32 + 2 * i + 1 < valid) ? ex2(fmaf(__uint_as_float(r[2 * i + 1]), sc, -m_new)) : 0.f;
+                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    sum += __low2float(pb) + __high2float(pb);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&pb);
+                }
+                // 32 keys = 4 chunks of 16 bytes inside half (ch >> 1), chunk index (ch & 1) * 4 + c
+                uint8_t* half = prow + (ch >> 1) * TILE_BYTES;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = (ch & 1) * 4 + c;
+                    *reinterpret_cast<uint4*>(half + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
+            }
+            l = l * alpha + sum;
+            m = m_new;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor core
+            if (j > 0) {                                                   // fold in O_{j-1}, then rescale
+                mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tO + lane_off + ch * 32, r);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[ch * 32 + i] = (o[ch * 32 + i] + __uint_as_float(r[i])) * alpha;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_p);
+        }
+        mbar_wait(bar_o, (uint32_t)((n_kb - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float inv = 1.0f / l;
+        const int gq = qb * AQ + row;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tO + lane_off + ch * 32, r);
+            if (gq < T) {
+                uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * T + gq) * d + h * HD + ch * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = c * 8 + 2 * i;
+                        __nv_bfloat162 v = __floats2bfloat162_rn((o[ch * 32 + e] + __uint_as_float(r[e])) * inv,
+                                                                 (o[ch * 32 + e + 1] + __uint_as_float(r[e + 1])) * inv);
+                        w[i] = *reinterpret_cast<uint32_t*>(&v);
+                    }
+                    dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ATT_TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+bool attn_tc_enabled() {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("WB_TC_ATTN"); enabled = !(e && e[0] == '0'); }
+    return enabled != 0;
+}
+
+// qkv: [B][T][3d] bf16 (q | k | v), out: [B][T][d] bf16.
+void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        WB_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, WB_ECUDA, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    }
+    WB_REQUIRE(d == H * HD, WB_EINVAL, "attention kernel needs head_dim 64");
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)(3 * d), (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)(3 * d) * 2, (cuuint64_t)T * 3 * d * 2};
+    cuuint32_t box[3] = {HD, 128, 1}, estr[3] = {1, 1, 1};
+    CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    WB_REQUIRE(r == CUDA_SUCCESS, WB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    const int n_qb = ceil_div(T, AQ);
+    attn_tc_kernel<<<B * H * n_qb, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, (__nv_bfloat16*)out, T, d, H, n_qb);
+    CUDA_CHECK(cudaGetLastError());
+}

@@ -153,7 +153,11 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& a);
 // dispatcher: tensor-core kernel when eligible, else SIMT
 void gemm(wb_ctx* ctx, const GemmArgs& a);
 
+// attn_tc.cu — tcgen05 flash attention (bf16 build)
+bool attn_tc_enabled();
+void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H);
 // encoder.cu
+int attention_simt(wb_ctx* ctx, const void* qkv, void* att, int B);
 void encoder_alloc(wb_ctx* ctx);
 void encoder_forward(wb_ctx* ctx, const void* mel_tm, int B);   // mel_tm: [B][3002][n_mels] compute dtype
 // decoder.cu

@@ -103,6 +103,46 @@ void layernorm(wb_ctx* ctx, const float* x, const LNW& ln, void* out, float* out
 
 }  // namespace
 
+// SIMT attention (fp32 build, and bring-up reference for attn_tc.cu): S = QK^T, row softmax, PV
+// through an f32 score scratch, in groups of attn_group clips.
+int attention_simt(wb_ctx* ctx, const void* qkv_all, void* att_all, int B) {
+    const wb_model_cfg& c = ctx->cfg;
+    const int Tc = c.n_audio_ctx, d = c.d_model, H = c.n_heads;
+    const int ct = c.precision == WB_PREC_BF16 ? WB_BF16 : WB_F32;
+    EncBufs& b = ctx->enc;
+    int launches = 0;
+        for (int g0 = 0; g0 < B; g0 += b.attn_group) {
+            const int G = (B - g0 < b.attn_group) ? B - g0 : b.attn_group;
+            const char* qkv = (const char*)qkv_all + (size_t)g0 * Tc * 3 * d * ctx->esz();
+            {   // S = (q * hd^-0.5) k^T   (0.125 is a power of two: exact in either order)
+                GemmArgs g;
+                g.A = qkv; g.B = qkv + (size_t)d * ctx->esz(); g.C = b.scores.p;
+                g.ta = g.tb = ct; g.tc = WB_F32;
+                g.M = Tc; g.N = Tc; g.K = 64; g.lda = 3 * d; g.ldb = 3 * d; g.ldc = Tc;
+                g.batch = G * H; g.inner = H;
+                g.sAo = (long long)Tc * 3 * d; g.sAi = 64; g.sBo = g.sAo; g.sBi = 64;
+                g.sCo = (long long)H * Tc * Tc; g.sCi = (long long)Tc * Tc;
+                g.alpha = 0.125f;
+                gemm_simt(ctx, g); ++launches;
+            }
+            softmax_rows_kernel<<<ceil_div(G * H * Tc, 8), 256, 0, ctx->stream>>>(b.scores.p, G * H * Tc, Tc);
+            CUDA_CHECK(cudaGetLastError()); ++launches;
+            {   // O = P v
+                GemmArgs g;
+                g.A = b.scores.p; g.B = qkv + (size_t)2 * d * ctx->esz();
+                g.C = (char*)att_all + (size_t)g0 * Tc * d * ctx->esz();
+                g.ta = WB_F32; g.tb = ct; g.tc = ct; g.b_kn = true;
+                g.M = Tc; g.N = 64; g.K = Tc; g.lda = Tc; g.ldb = 3 * d; g.ldc = d;
+                g.batch = G * H; g.inner = H;
+                g.sAo = (long long)H * Tc * Tc; g.sAi = (long long)Tc * Tc;
+                g.sBo = (long long)Tc * 3 * d; g.sBi = 64;
+                g.sCo = (long long)Tc * d; g.sCi = 64;
+                gemm_simt(ctx, g); ++launches;
+            }
+        }
+    return launches;
+}
+
 void encoder_alloc(wb_ctx* ctx) {
     const wb_model_cfg& c = ctx->cfg;
     const size_t B = c.max_batch, T = WB_N_FRAMES, Tc = c.n_audio_ctx, d = c.d_model, e = ctx->esz();
@@ -169,35 +209,8 @@ void encoder_forward(wb_ctx* ctx, const void* mel_tm, int B) {
             gemm(ctx, g); ++launches;
         }
         // self-attention, non-causal, T = 1500, head_dim 64                            (K2d)
-        for (int g0 = 0; g0 < B; g0 += b.attn_group) {
-            const int G = (B - g0 < b.attn_group) ? B - g0 : b.attn_group;
-            const char* qkv = (const char*)b.qkv.p + (size_t)g0 * Tc * 3 * d * ctx->esz();
-            {   // S = (q * hd^-0.5) k^T   (0.125 is a power of two: exact in either order)
-                GemmArgs g;
-                g.A = qkv; g.B = qkv + (size_t)d * ctx->esz(); g.C = b.scores.p;
-                g.ta = g.tb = ct; g.tc = WB_F32;
-                g.M = Tc; g.N = Tc; g.K = 64; g.lda = 3 * d; g.ldb = 3 * d; g.ldc = Tc;
-                g.batch = G * H; g.inner = H;
-                g.sAo = (long long)Tc * 3 * d; g.sAi = 64; g.sBo = g.sAo; g.sBi = 64;
-                g.sCo = (long long)H * Tc * Tc; g.sCi = (long long)Tc * Tc;
-                g.alpha = 0.125f;
-                gemm_simt(ctx, g); ++launches;
-            }
-            softmax_rows_kernel<<<ceil_div(G * H * Tc, 8), 256, 0, ctx->stream>>>(b.scores.p, G * H * Tc, Tc);
-            CUDA_CHECK(cudaGetLastError()); ++launches;
-            {   // O = P v
-                GemmArgs g;
-                g.A = b.scores.p; g.B = qkv + (size_t)2 * d * ctx->esz();
-                g.C = (char*)b.att.p + (size_t)g0 * Tc * d * ctx->esz();
-                g.ta = WB_F32; g.tb = ct; g.tc = ct; g.b_kn = true;
-                g.M = Tc; g.N = 64; g.K = Tc; g.lda = Tc; g.ldb = 3 * d; g.ldc = d;
-                g.batch = G * H; g.inner = H;
-                g.sAo = (long long)H * Tc * Tc; g.sAi = (long long)Tc * Tc;
-                g.sBo = (long long)Tc * 3 * d; g.sBi = 64;
-                g.sCo = (long long)Tc * d; g.sCi = 64;
-                gemm_simt(ctx, g); ++launches;
-            }
-        }
+        if (ct == WB_BF16 && attn_tc_enabled()) { attn_tc(ctx, b.qkv.p, b.att.p, B, Tc, d, H); ++launches; }
+        else launches += attention_simt(ctx, b.qkv.p, b.att.p, B);
         {   // out-proj + bias + residual (in place on x)
             GemmArgs g;
             g.A = b.att.p; g.B = L.o.w; g.C = b.x.p; g.ta = g.tb = ct; g.tc = WB_F32;
