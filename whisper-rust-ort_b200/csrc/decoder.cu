@@ -63,7 +63,7 @@ __global__ void embed_kernel(const int* __restrict__ state, const int* __restric
 // X (and its LayerNorm) is staged once per CTA in shared memory with 128-bit loads, then the CTA
 // walks row groups (grid-stride) so the staging is amortised over many weight rows.
 constexpr int SK_WARPS = 8, SK_THREADS = SK_WARPS * 32, SK_BT = 32, SK_KC = 512;
-#define SK_PRE (R == 1 || sizeof(WT) == 2)      // prefetch depth that still fits the register file
+#define SK_PRE (R == 1)                          // prefetch only where it fits the register file
 
 template <int R>
 __device__ __forceinline__ void fma_tile(float (&acc)[R * 32], const float (&w)[R][4], const float* xcol, int kc) {
@@ -138,46 +138,85 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
                 const int kc = min(SK_KC, K - k0);
                 if (!(single_chunk && g != (int)blockIdx.x)) {      // (re)stage X unless still resident
                     __syncthreads();
-                    const int kc4 = kc >> 2, nvec = SK_BT * kc4;
-                    for (int i0 = tid; i0 < nvec; i0 += SK_THREADS * 4) {
-                        float4 v[4];
+                    // Each warp stages (and LayerNorms) its own rows: global -> registers -> smem, every
+                    // load of the 4 rows in flight at once, statistics by warp shuffles, one CTA barrier.
+                    constexpr int RPW = SK_BT / SK_WARPS;               // rows per warp
+                    constexpr int VPL = SK_KC / 128;                    // float4 per lane per row
+                    float4 xv[RPW][VPL];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u * SK_THREADS;
-                            const int bb = i / kc4, c4 = i - bb * kc4;
-                            v[u] = (i < nvec && bb < nb) ? *reinterpret_cast<const float4*>(X + (size_t)(bt0 + bb) * K + k0 + c4 * 4)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int rr = 0; rr < RPW; ++rr) {
+                        const int bb = warp + rr * SK_WARPS;
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) {
+                            const int c = i * 128 + lane * 4;
+                            xv[rr][i] = (bb < nb && c < kc) ? *reinterpret_cast<const float4*>(X + (size_t)(bt0 + bb) * K + k0 + c)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    if (ln_w) {
+                        float4 gw[VPL], gb[VPL];
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) {
+                            const int c = i * 128 + lane * 4;
+                            gw[i] = c < kc ? *reinterpret_cast<const float4*>(ln_w + k0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            gb[i] = c < kc ? *reinterpret_cast<const float4*>(ln_b + k0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        float mean[RPW], sd[RPW];
+                        if (single_chunk) {                              // two-pass statistics like the oracle
+                            float s1[RPW];
+#pragma unroll
+                            for (int rr = 0; rr < RPW; ++rr) {
+                                s1[rr] = 0.f;
+#pragma unroll
+                                for (int i = 0; i < VPL; ++i) s1[rr] += (xv[rr][i].x + xv[rr][i].y) + (xv[rr][i].z + xv[rr][i].w);
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                                for (int rr = 0; rr < RPW; ++rr) s1[rr] += __shfl_xor_sync(0xffffffffu, s1[rr], o);
+#pragma unroll
+                            for (int rr = 0; rr < RPW; ++rr) {
+                                mean[rr] = s1[rr] / (float)K;
+                                float q = 0.f;
+#pragma unroll
+                                for (int i = 0; i < VPL; ++i) {
+                                    if (i * 128 + lane * 4 < kc) {
+                                        float t0 = xv[rr][i].x - mean[rr], t1 = xv[rr][i].y - mean[rr], t2 = xv[rr][i].z - mean[rr], t3 = xv[rr][i].w - mean[rr];
+                                        q += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                                    }
+                                }
+                                s1[rr] = q;
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                                for (int rr = 0; rr < RPW; ++rr) s1[rr] += __shfl_xor_sync(0xffffffffu, s1[rr], o);
+#pragma unroll
+                            for (int rr = 0; rr < RPW; ++rr) sd[rr] = sqrtf(s1[rr] / (float)K + 1e-5f);
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < RPW; ++rr) { mean[rr] = s_mean[warp + rr * SK_WARPS]; sd[rr] = s_rstd[warp + rr * SK_WARPS]; }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u * SK_THREADS;
-                            if (i < nvec) *reinterpret_cast<float4*>(xs + (size_t)i * 4) = v[u];
+                        for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+                            for (int i = 0; i < VPL; ++i) {
+                                xv[rr][i].x = (xv[rr][i].x - mean[rr]) / sd[rr] * gw[i].x + gb[i].x;
+                                xv[rr][i].y = (xv[rr][i].y - mean[rr]) / sd[rr] * gw[i].y + gb[i].y;
+                                xv[rr][i].z = (xv[rr][i].z - mean[rr]) / sd[rr] * gw[i].z + gb[i].z;
+                                xv[rr][i].w = (xv[rr][i].w - mean[rr]) / sd[rr] * gw[i].w + gb[i].w;
+                            }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < RPW; ++rr) {
+                        const int bb = warp + rr * SK_WARPS;
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) {
+                            const int c = i * 128 + lane * 4;
+                            if (c < kc) *reinterpret_cast<float4*>(xs + bb * kc + c) = (bb < nb) ? xv[rr][i] : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
                     __syncthreads();
-                    if (ln_w) {
-                        // LayerNorm in place (two-pass statistics like the oracle); each warp its rows
-                        for (int bb = warp; bb < nb; bb += SK_WARPS) {
-                            float* xr = xs + bb * kc;
-                            float mean, sd;
-                            if (single_chunk) {
-                                float s = 0.f;
-                                for (int c = lane; c < kc; c += 32) s += xr[c];
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                                mean = s / (float)K;
-                                float q = 0.f;
-                                for (int c = lane; c < kc; c += 32) { float t = xr[c] - mean; q += t * t; }
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-                                sd = sqrtf(q / (float)K + 1e-5f);
-                            } else {
-                                mean = s_mean[bb]; sd = s_rstd[bb];
-                            }
-                            for (int c = lane; c < kc; c += 32) xr[c] = (xr[c] - mean) / sd * ln_w[k0 + c] + ln_b[k0 + c];
-                        }
-                        __syncthreads();
-                    }
                 }
                 // weights of this chunk (prefetched below, before the staging, when single_chunk)
                 if (!(single_chunk && SK_PRE)) {
@@ -281,34 +320,61 @@ self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, K
 }
 
 // ---- cross-attention over the cached encoder K/V: the dominant HBM stream of a step ----
-// grid (H, B), 256 threads.  8 lanes cover one 64-wide K or V row with 16/32-byte loads.
+// grid (H, B), 256 threads.  Every lane moves 32 bytes per row visit (two 128-bit loads), so a
+// 64-wide K or V row takes 8 lanes in f32 and 4 lanes in bf16 and a warp instruction always
+// covers 1 KB; UN rows per lane group are in flight before any of them is consumed.
+template <typename KT> struct RowLoad;
+template <> struct RowLoad<float> {
+    static constexpr int DPL = 8;                         // dims per lane
+    static __device__ __forceinline__ void load(const float* p, float (&f)[8]) { load8(p, f); }
+};
+template <> struct RowLoad<bf16> {
+    static constexpr int DPL = 16;
+    static __device__ __forceinline__ void load(const bf16* p, float (&f)[16]) {
+        float a[8], b[8];
+        load8(p, a); load8(p + 8, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { f[i] = a[i]; f[8 + i] = b[i]; }
+    }
+};
+
 template <typename KT>
 __global__ void __launch_bounds__(256)
 cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out,
                   int d, int Tk) {
-    extern __shared__ float sm[];                 // scores [Tk] + reduce scratch
+    constexpr int DPL = RowLoad<KT>::DPL, LPR = 64 / DPL, NG = 256 / LPR, UN = 4;
+    extern __shared__ float sm[];                 // scores [Tk]
     float* s_p = sm;
     __shared__ float s_red[8];
     __shared__ float s_acc[8][64];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = tid >> 3, li = tid & 7;       // 32 groups of 8 lanes
-    const KT* base = ckv + (size_t)b * Tk * 2 * d + h * 64 + li * 8;
-    float qv[8];
+    const int grp = tid / LPR, li = tid % LPR;
+    const KT* base = ckv + (size_t)b * Tk * 2 * d + h * 64 + li * DPL;
+    float qv[DPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * 8 + i] * 0.125f;
+    for (int i = 0; i < DPL; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * DPL + i] * 0.125f;
 
     float lmax = -INFINITY;
-    for (int j = grp; j < Tk; j += 32) {
-        float kf[8];
-        load8(base + (size_t)j * 2 * d, kf);
-        float p = 0.f;
+    for (int j0 = grp; j0 < Tk; j0 += NG * UN) {
+        float kf[UN][DPL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) p = fmaf(qv[i], kf[i], p);
-        p += __shfl_xor_sync(0xffffffffu, p, 4);
-        p += __shfl_xor_sync(0xffffffffu, p, 2);
-        p += __shfl_xor_sync(0xffffffffu, p, 1);
-        if (li == 0) s_p[j] = p;
-        lmax = fmaxf(lmax, p);
+        for (int u = 0; u < UN; ++u) {
+            const int j = min(j0 + u * NG, Tk - 1);           // clamp: uniform control flow, result discarded
+            RowLoad<KT>::load(base + (size_t)j * 2 * d, kf[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int j = j0 + u * NG;
+            float p = 0.f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) p = fmaf(qv[i], kf[u][i], p);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            if (j < Tk) {
+                if (li == 0) s_p[j] = p;
+                lmax = fmaxf(lmax, p);
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -329,26 +395,34 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
     for (int i = 0; i < 8; ++i) sum += s_red[i];
     const float inv = 1.0f / sum;
 
-    float acc[8];
+    float acc[DPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
     const KT* vbase = base + d;
-    for (int j = grp; j < Tk; j += 32) {
-        float vf[8];
-        load8(vbase + (size_t)j * 2 * d, vf);
-        const float p = s_p[j] * inv;
+    for (int j0 = grp; j0 < Tk; j0 += NG * UN) {
+        float vf[UN][DPL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+        for (int u = 0; u < UN; ++u) {
+            const int j = min(j0 + u * NG, Tk - 1);
+            RowLoad<KT>::load(vbase + (size_t)j * 2 * d, vf[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int j = j0 + u * NG;
+            const float p = j < Tk ? s_p[j] * inv : 0.f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) acc[i] = fmaf(p, vf[u][i], acc[i]);
+        }
     }
-    // reduce the 4 groups of a warp, then the 8 warps
+    // reduce the lane groups of a warp, then the 8 warps
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    for (int i = 0; i < DPL; ++i) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     }
-    if (lane < 8) {
+    if (lane < LPR) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_acc[warp][lane * 8 + i] = acc[i];
+        for (int i = 0; i < DPL; ++i) s_acc[warp][lane * DPL + i] = acc[i];
     }
     __syncthreads();
     if (tid < 64) {
@@ -420,7 +494,7 @@ void skinny_launch(wb_ctx* ctx, const float* X, int B, int K, const WT* W, int N
     const size_t smem = sizeof(float) * SK_BT * kc;
     const int groups = ceil_div(N, SK_WARPS * R);
     // single-chunk: persistent-style grid (<= 2 CTAs per SM) walking row groups; else one group per CTA
-    const int cap = (R == 1 ? 2 : 1) * ctx->sm_count;          // resident CTAs (register-limited for R = 4)
+    const int cap = ctx->sm_count;                               // one resident CTA per SM (register-limited)
     const int grid = K <= SK_KC ? (groups < cap ? groups : cap) : groups;
     skinny_gemm_kernel<WT, R><<<grid, SK_THREADS, smem, ctx->stream>>>(X, B, K, W, N, bias, lw, lb, act, residual, Y);
 }
