@@ -194,6 +194,11 @@ void wb_destroy(wb_ctx* ctx) {
     cudaDeviceSynchronize();
     weights_free(ctx);
     if (ctx->dec.graph_exec) cudaGraphExecDestroy(ctx->dec.graph_exec);
+    for (int k = 0; k < 3; ++k) {
+        if (ctx->dec.side[k]) cudaStreamDestroy(ctx->dec.side[k]);
+        if (ctx->dec.ev_join[k]) cudaEventDestroy(ctx->dec.ev_join[k]);
+    }
+    if (ctx->dec.ev_fork) cudaEventDestroy(ctx->dec.ev_fork);
     if (ctx->mel_tables_dev) cudaFree(ctx->mel_tables_dev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

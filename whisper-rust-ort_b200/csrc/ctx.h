@@ -97,6 +97,8 @@ struct DecBufs {
     cudaGraphExec_t graph_exec = nullptr;
     int g_key[6] = {-1, -1, -1, -1, -1, -1};
     int g_launches = 0;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // parallel sub-batch chains
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 struct wb_ctx {

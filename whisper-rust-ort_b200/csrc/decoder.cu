@@ -63,7 +63,7 @@ __global__ void embed_kernel(const int* __restrict__ state, const int* __restric
 // X (and its LayerNorm) is staged once per CTA in shared memory with 128-bit loads, then the CTA
 // walks row groups (grid-stride) so the staging is amortised over many weight rows.
 constexpr int SK_WARPS = 8, SK_THREADS = SK_WARPS * 32, SK_BT = 32, SK_KC = 512;
-#define SK_PRE (R == 1)                          // prefetch only where it fits the register file
+#define SK_PRE (R <= 2)                          // prefetch only where it fits the register file
 
 template <int R>
 __device__ __forceinline__ void fma_tile(float (&acc)[R * 32], const float (&w)[R][4], const float* xcol, int kc) {
@@ -508,7 +508,9 @@ void skinny(wb_ctx* ctx, const float* X, int B, int K, const LinearW& L, const L
     const float* lw = ln ? ln->w : nullptr;
     const float* lb = ln ? ln->b : nullptr;
     const float* bias = (L.b && !W_override) ? L.b : nullptr;
-    if (N >= 1536) skinny_launch<WT, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
+    // rows per warp: enough CTAs to cover the chip for the per-layer GEMMs, register blocking for the vocab one
+    if (N >= 8192) skinny_launch<WT, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
+    else if (N >= 1024) skinny_launch<WT, 2>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
     else skinny_launch<WT, 1>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -517,42 +519,54 @@ template <typename WT>
 void set_func_attrs() {
     const int smem = (int)(sizeof(float) * SK_BT * SK_KC);
     CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<WT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<WT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<WT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
 // Enqueue one decode step.  with_logits: final LN + tied vocab projection + argmax.
 template <typename WT>
-int enqueue_step(wb_ctx* ctx, int B, bool with_logits, const int* prompt_dev, const int* cur_tok,
+int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool with_logits, const int* prompt_dev,
                  const int* forced_dev, int max_new, int eot, int T_total) {
+    // One decode step for sequences [b0, b0+B) on stream `st` with its own step counter `state`:
+    // sub-batches of a decode run as independent chains on parallel graph branches.
     const wb_model_cfg& c = ctx->cfg;
     const int d = c.d_model, H = c.n_heads, Tk = c.n_audio_ctx;
     DecBufs& D = ctx->dec;
     ModelW& w = ctx->w;
-    int* state = D.state.p;
+    float* x = D.x.p + (size_t)b0 * d;
+    float* qkv = D.qkv.p + (size_t)b0 * 3 * d;
+    float* att = D.att.p + (size_t)b0 * d;
+    float* q = D.q.p + (size_t)b0 * d;
+    float* ffn = D.ffn.p + (size_t)b0 * c.ffn_dim;
+    float* logits = D.logits.p + (size_t)b0 * c.vocab;
+    int* cur_tok = D.tokens.p + (size_t)c.max_batch * T_total + b0;
     int n = 0;
-    embed_kernel<WT><<<B, 128, 0, ctx->stream>>>(state, prompt_dev, cur_tok, (const WT*)w.embed, w.dec_pos, D.x.p, d); ++n;
+    cudaStream_t saved = ctx->stream;
+    ctx->stream = st;                                        // skinny() launches on ctx->stream
+    embed_kernel<WT><<<B, 128, 0, st>>>(state, prompt_dev, cur_tok, (const WT*)w.embed, w.dec_pos, x, d); ++n;
     for (int l = 0; l < c.dec_layers; ++l) {
         const DecLayerW& L = w.dec[l];
-        WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + (size_t)l * c.max_batch * D.T_max * 2 * d;
-        const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + (size_t)l * c.max_batch * Tk * 2 * d;
-        skinny<WT>(ctx, D.x.p, B, d, L.qkv, &L.ln1, 0, nullptr, D.qkv.p); ++n;                 // K3c
-        self_attn_kernel<WT><<<dim3(H, B), 128, 0, ctx->stream>>>(state, D.qkv.p, skv, D.att.p, d, D.T_max); ++n;   // K3d
-        skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, D.x.p, D.x.p); ++n;                     // K3f
-        skinny<WT>(ctx, D.x.p, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
-        cross_attn_kernel<WT><<<dim3(H, B), 256, sizeof(float) * Tk, ctx->stream>>>(D.q.p, ckv, D.att.p, d, Tk); ++n;  // K3e
-        skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, D.x.p, D.x.p); ++n;
-        skinny<WT>(ctx, D.x.p, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                  // K3g
-        skinny<WT>(ctx, D.ffn.p, B, c.ffn_dim, L.fc2, nullptr, 0, D.x.p, D.x.p); ++n;
+        WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + ((size_t)l * c.max_batch + b0) * D.T_max * 2 * d;
+        const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + ((size_t)l * c.max_batch + b0) * Tk * 2 * d;
+        skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, qkv); ++n;                              // K3c
+        self_attn_kernel<WT><<<dim3(H, B), 128, 0, st>>>(state, qkv, skv, att, d, D.T_max); ++n;     // K3d
+        skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;                                      // K3f
+        skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
+        cross_attn_kernel<WT><<<dim3(H, B), 256, sizeof(float) * Tk, st>>>(q, ckv, att, d, Tk); ++n;  // K3e
+        skinny<WT>(ctx, att, B, d, L.co, nullptr, 0, x, x); ++n;
+        skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, ffn); ++n;                               // K3g
+        skinny<WT>(ctx, ffn, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
     }
-    if (with_logits) {                                                                           // K3h
+    if (with_logits) {                                                                               // K3h
         LinearW dummy;
-        skinny<WT>(ctx, D.x.p, B, d, dummy, &w.dec_ln, 0, nullptr, D.logits.p, c.vocab, w.embed); ++n;
-        argmax_kernel<<<B, 1024, 0, ctx->stream>>>(state, D.logits.p, c.vocab, D.sup_base.p, D.sup_first.p, forced_dev,
-                                                   max_new, eot, T_total, D.tokens.p, D.lens.p, D.finished.p, D.tokens.p + (size_t)c.max_batch * T_total); ++n;
+        skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, logits, c.vocab, w.embed); ++n;
+        argmax_kernel<<<B, 1024, 0, st>>>(state, logits, c.vocab, D.sup_base.p, D.sup_first.p,
+                                          forced_dev ? forced_dev + (size_t)b0 * max_new : nullptr, max_new, eot, T_total,
+                                          D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
     }
-    advance_kernel<<<1, 1, 0, ctx->stream>>>(state); ++n;
+    advance_kernel<<<1, 1, 0, st>>>(state); ++n;
+    ctx->stream = saved;
     CUDA_CHECK(cudaGetLastError());
-    (void)cur_tok;
     return n;
 }
 
@@ -574,7 +588,12 @@ void decoder_alloc(wb_ctx* ctx) {
     D.forced.reserve(B * (size_t)c.n_text_ctx);
     D.lens.reserve(B);
     D.finished.reserve(B);
-    D.state.reserve(4);
+    D.state.reserve(16);
+    for (int k = 0; k < 3; ++k) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&D.side[k], cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_join[k], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_fork, cudaEventDisableTiming));
     const size_t words = ((size_t)c.vocab + 31) / 32;
     D.sup_base.reserve(words);
     D.sup_first.reserve(words);
@@ -609,10 +628,10 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     CUDA_CHECK(cudaMemcpyAsync(D.tokens.p, tok.data(), sizeof(int) * tok.size(), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(D.sup_base.p, base.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(D.sup_first.p, first.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
-    std::vector<int> lens(B, P), st4 = {0, P, 0, 0};
+    std::vector<int> lens(B, P), st4 = {0, P, 0, 0, 0, P, 0, 0, 0, P, 0, 0, 0, P, 0, 0};
     CUDA_CHECK(cudaMemcpyAsync(D.lens.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(D.finished.p, 0, sizeof(int) * B, st));
-    CUDA_CHECK(cudaMemcpyAsync(D.state.p, st4.data(), sizeof(int) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.state.p, st4.data(), sizeof(int) * 16, cudaMemcpyHostToDevice, st));
     int* forced_dev = nullptr;
     std::vector<int> forced;
     if (p.forced) {
@@ -631,18 +650,38 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     const int steps = P + max_new - 1;
     int launches = 0;
     const bool bf = c.precision == WB_PREC_BF16;
+    // Sub-batches run as independent chains (own step counter, own stream / graph branch): a step is
+    // ~50 dependent small kernels, so two chains in flight hide each other's latency.
+    const char* senv = getenv("WB_DEC_SPLIT");
+    int nsplit = senv ? atoi(senv) : 1;      // measured on B200: 1 chain 102 ms, 2 chains 121 ms, 4 chains 166 ms
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 4) nsplit = 4;
+    if (p.want_logits || B < 8 * nsplit) nsplit = 1;
     auto enqueue_all = [&]() {
         int n = 0;
-        for (int s = 0; s < steps; ++s) {
-            const bool with_logits = s >= P - 1;
-            n += bf ? enqueue_step<bf16>(ctx, B, with_logits, prompt_dev, cur_tok, forced_dev, max_new, p.eot, T_total)
-                    : enqueue_step<float>(ctx, B, with_logits, prompt_dev, cur_tok, forced_dev, max_new, p.eot, T_total);
-            if (with_logits && p.want_logits) {
-                const int gi = s - (P - 1);
-                CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
-                                             D.logits.p, sizeof(float) * c.vocab, sizeof(float) * c.vocab, B,
-                                             cudaMemcpyDeviceToDevice, st));
+        if (nsplit > 1) {
+            CUDA_CHECK(cudaEventRecord(D.ev_fork, st));
+            for (int k = 1; k < nsplit; ++k) CUDA_CHECK(cudaStreamWaitEvent(D.side[k - 1], D.ev_fork, 0));
+        }
+        for (int k = 0; k < nsplit; ++k) {
+            const int lo = (int)((long long)B * k / nsplit), hi = (int)((long long)B * (k + 1) / nsplit);
+            cudaStream_t sk = k == 0 ? st : D.side[k - 1];
+            int* state_k = D.state.p + 4 * k;
+            for (int s = 0; s < steps; ++s) {
+                const bool with_logits = s >= P - 1;
+                n += bf ? enqueue_step<bf16>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total)
+                        : enqueue_step<float>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total);
+                if (with_logits && p.want_logits) {
+                    const int gi = s - (P - 1);
+                    CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
+                                                 D.logits.p, sizeof(float) * c.vocab, sizeof(float) * c.vocab, B,
+                                                 cudaMemcpyDeviceToDevice, st));
+                }
             }
+        }
+        for (int k = 1; k < nsplit; ++k) {
+            CUDA_CHECK(cudaEventRecord(D.ev_join[k - 1], D.side[k - 1]));
+            CUDA_CHECK(cudaStreamWaitEvent(st, D.ev_join[k - 1], 0));
         }
         return n;
     };
@@ -651,7 +690,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     if (use_graph) {
         // The whole decode (every step of every layer) is one CUDA graph: kernels read the step
         // index from device memory, so the captured sequence is replayable; one launch per decode.
-        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0, c.precision};
+        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0, c.precision * 8 + nsplit};
         bool same = D.graph_exec != nullptr;
         for (int i = 0; i < 6; ++i) same = same && D.g_key[i] == key[i];
         if (!same) {
