@@ -97,6 +97,7 @@ struct DecBufs {
     cudaGraphExec_t graph_exec = nullptr;
     int g_key[6] = {-1, -1, -1, -1, -1, -1};
     int g_launches = 0;
+    bool pdl = false;                  // programmatic dependent launch for the decode chain
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // parallel sub-batch chains
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };

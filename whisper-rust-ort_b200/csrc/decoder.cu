@@ -21,6 +21,27 @@ using bf16 = __nv_bfloat16;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+// Programmatic dependent launch: a kernel of the decode chain is launched while its predecessor
+// still runs; everything before pdl_sync() may only touch weights (constant during a decode), so
+// weight prefetch and launch latency overlap the predecessor.  pdl_sync() returns when the
+// predecessor grid has completed and its writes are visible; it then lets the successor launch.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 __device__ __forceinline__ void load4(const float* p, float (&f)[4]) {
     float4 v = *reinterpret_cast<const float4*>(p);
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
@@ -51,6 +72,7 @@ template <typename WT>
 __global__ void embed_kernel(const int* __restrict__ state, const int* __restrict__ prompt,
                              const int* __restrict__ cur_tok, const WT* __restrict__ E,
                              const float* __restrict__ P, float* __restrict__ x, int d) {
+    pdl_sync();
     const int b = blockIdx.x, s = state[0];
     const int tok = s < state[1] ? prompt[s] : cur_tok[b];
     for (int c = threadIdx.x; c < d; c += blockDim.x)
@@ -90,10 +112,12 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_groups = (N + SK_WARPS * R - 1) / (SK_WARPS * R);
     const bool single_chunk = K <= SK_KC;
+    bool synced = false;                            // pdl_sync() done (uniform across the CTA)
 
     for (int bt0 = 0; bt0 < B; bt0 += SK_BT) {
         const int nb = min(SK_BT, B - bt0);
         if (ln_w && !single_chunk) {      // stats straight from global (row longer than one chunk)
+            if (!synced) { pdl_sync(); synced = true; }
             for (int bb = warp; bb < SK_BT; bb += SK_WARPS) {
                 float mean = 0.f, sd = 1.f;
                 if (bb < nb) {
@@ -137,6 +161,7 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
             for (int k0 = 0; k0 < K; k0 += SK_KC) {
                 const int kc = min(SK_KC, K - k0);
                 if (!(single_chunk && g != (int)blockIdx.x)) {      // (re)stage X unless still resident
+                    if (!synced) { pdl_sync(); synced = true; }        // weights above were prefetched before this
                     __syncthreads();
                     // Each warp stages (and LayerNorms) its own rows: global -> registers -> smem, every
                     // load of the 4 rows in flight at once, statistics by warp shuffles, one CTA barrier.
@@ -198,14 +223,16 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
                             for (int rr = 0; rr < RPW; ++rr) { mean[rr] = s_mean[warp + rr * SK_WARPS]; sd[rr] = s_rstd[warp + rr * SK_WARPS]; }
                         }
 #pragma unroll
-                        for (int rr = 0; rr < RPW; ++rr)
+                        for (int rr = 0; rr < RPW; ++rr) {
+                            const float rs = 1.0f / sd[rr];               // one IEEE divide per row, not per element
 #pragma unroll
                             for (int i = 0; i < VPL; ++i) {
-                                xv[rr][i].x = (xv[rr][i].x - mean[rr]) / sd[rr] * gw[i].x + gb[i].x;
-                                xv[rr][i].y = (xv[rr][i].y - mean[rr]) / sd[rr] * gw[i].y + gb[i].y;
-                                xv[rr][i].z = (xv[rr][i].z - mean[rr]) / sd[rr] * gw[i].z + gb[i].z;
-                                xv[rr][i].w = (xv[rr][i].w - mean[rr]) / sd[rr] * gw[i].w + gb[i].w;
+                                xv[rr][i].x = (xv[rr][i].x - mean[rr]) * rs * gw[i].x + gb[i].x;
+                                xv[rr][i].y = (xv[rr][i].y - mean[rr]) * rs * gw[i].y + gb[i].y;
+                                xv[rr][i].z = (xv[rr][i].z - mean[rr]) * rs * gw[i].z + gb[i].z;
+                                xv[rr][i].w = (xv[rr][i].w - mean[rr]) * rs * gw[i].w + gb[i].w;
                             }
+                        }
                     }
 #pragma unroll
                     for (int rr = 0; rr < RPW; ++rr) {
@@ -277,6 +304,7 @@ self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, K
                  float* __restrict__ out, int d, int T_max) {
     __shared__ float s_q[64], s_p[512], s_red[4], s_acc[2][64];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_sync();
     const int s = state[0];
     const float* row = qkv + (size_t)b * 3 * d;
     KT* kv = cache + (size_t)b * T_max * 2 * d;
@@ -350,6 +378,7 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / LPR, li = tid % LPR;
     const KT* base = ckv + (size_t)b * Tk * 2 * d + h * 64 + li * DPL;
+    pdl_sync();
     float qv[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * DPL + i] * 0.125f;
@@ -445,6 +474,7 @@ argmax_kernel(const int* __restrict__ state, const float* __restrict__ logits, i
     __shared__ float s_v[32];
     __shared__ int s_i[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_sync();
     const int s = state[0], prompt_len = state[1];
     const int gi = s - (prompt_len - 1);
     const unsigned* sup = gi == 0 ? sup_first : sup_base;
@@ -485,7 +515,10 @@ argmax_kernel(const int* __restrict__ state, const float* __restrict__ logits, i
     }
 }
 
-__global__ void advance_kernel(int* state) { state[0] += 1; }
+__global__ void advance_kernel(int* state) {
+    pdl_sync();
+    state[0] += 1;
+}
 
 template <typename WT, int R>
 void skinny_launch(wb_ctx* ctx, const float* X, int B, int K, const WT* W, int N, const float* bias, const float* lw,
@@ -496,7 +529,7 @@ void skinny_launch(wb_ctx* ctx, const float* X, int B, int K, const WT* W, int N
     // single-chunk: persistent-style grid (<= 2 CTAs per SM) walking row groups; else one group per CTA
     const int cap = ctx->sm_count;                               // one resident CTA per SM (register-limited)
     const int grid = K <= SK_KC ? (groups < cap ? groups : cap) : groups;
-    skinny_gemm_kernel<WT, R><<<grid, SK_THREADS, smem, ctx->stream>>>(X, B, K, W, N, bias, lw, lb, act, residual, Y);
+    launch_k(skinny_gemm_kernel<WT, R>, dim3(grid), dim3(SK_THREADS), smem, ctx->stream, ctx->dec.pdl, X, B, K, W, N, bias, lw, lb, act, residual, Y);
 }
 
 template <typename WT>
@@ -526,7 +559,7 @@ void set_func_attrs() {
 // Enqueue one decode step.  with_logits: final LN + tied vocab projection + argmax.
 template <typename WT>
 int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool with_logits, const int* prompt_dev,
-                 const int* forced_dev, int max_new, int eot, int T_total) {
+                 const int* forced_dev, int max_new, int eot, int T_total, bool first) {
     // One decode step for sequences [b0, b0+B) on stream `st` with its own step counter `state`:
     // sub-batches of a decode run as independent chains on parallel graph branches.
     const wb_model_cfg& c = ctx->cfg;
@@ -543,16 +576,18 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
     int n = 0;
     cudaStream_t saved = ctx->stream;
     ctx->stream = st;                                        // skinny() launches on ctx->stream
-    embed_kernel<WT><<<B, 128, 0, st>>>(state, prompt_dev, cur_tok, (const WT*)w.embed, w.dec_pos, x, d); ++n;
+    const bool pdl = D.pdl;
+    // the first kernel of a chain follows memcpy nodes, not a kernel: plain launch
+    launch_k(embed_kernel<WT>, dim3(B), dim3(128), 0, st, pdl && !first, (const int*)state, prompt_dev, (const int*)cur_tok, (const WT*)w.embed, (const float*)w.dec_pos, x, d); ++n;
     for (int l = 0; l < c.dec_layers; ++l) {
         const DecLayerW& L = w.dec[l];
         WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + ((size_t)l * c.max_batch + b0) * D.T_max * 2 * d;
         const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + ((size_t)l * c.max_batch + b0) * Tk * 2 * d;
         skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, qkv); ++n;                              // K3c
-        self_attn_kernel<WT><<<dim3(H, B), 128, 0, st>>>(state, qkv, skv, att, d, D.T_max); ++n;     // K3d
+        launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)qkv, skv, att, d, D.T_max); ++n;   // K3d
         skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;                                      // K3f
         skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
-        cross_attn_kernel<WT><<<dim3(H, B), 256, sizeof(float) * Tk, st>>>(q, ckv, att, d, Tk); ++n;  // K3e
+        launch_k(cross_attn_kernel<WT>, dim3(H, B), dim3(256), sizeof(float) * Tk, st, pdl, (const float*)q, ckv, att, d, Tk); ++n;   // K3e
         skinny<WT>(ctx, att, B, d, L.co, nullptr, 0, x, x); ++n;
         skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, ffn); ++n;                               // K3g
         skinny<WT>(ctx, ffn, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
@@ -560,11 +595,12 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
     if (with_logits) {                                                                               // K3h
         LinearW dummy;
         skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, logits, c.vocab, w.embed); ++n;
-        argmax_kernel<<<B, 1024, 0, st>>>(state, logits, c.vocab, D.sup_base.p, D.sup_first.p,
-                                          forced_dev ? forced_dev + (size_t)b0 * max_new : nullptr, max_new, eot, T_total,
-                                          D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
+        launch_k(argmax_kernel, dim3(B), dim3(1024), 0, st, pdl, (const int*)state, (const float*)logits, c.vocab,
+                 (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p,
+                 forced_dev ? forced_dev + (size_t)b0 * max_new : (const int*)nullptr, max_new, eot, T_total,
+                 D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
     }
-    advance_kernel<<<1, 1, 0, st>>>(state); ++n;
+    launch_k(advance_kernel, dim3(1), dim3(1), 0, st, pdl, state); ++n;
     ctx->stream = saved;
     CUDA_CHECK(cudaGetLastError());
     return n;
@@ -669,8 +705,8 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
             int* state_k = D.state.p + 4 * k;
             for (int s = 0; s < steps; ++s) {
                 const bool with_logits = s >= P - 1;
-                n += bf ? enqueue_step<bf16>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total)
-                        : enqueue_step<float>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total);
+                n += bf ? enqueue_step<bf16>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0)
+                        : enqueue_step<float>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0);
                 if (with_logits && p.want_logits) {
                     const int gi = s - (P - 1);
                     CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
@@ -685,12 +721,14 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
         }
         return n;
     };
+    const char* penv = getenv("WB_PDL");
+    D.pdl = !(penv && penv[0] == '0') && !p.want_logits;
     const char* genv = getenv("WB_GRAPH");
     const bool use_graph = !p.want_logits && !(genv && genv[0] == '0');
     if (use_graph) {
         // The whole decode (every step of every layer) is one CUDA graph: kernels read the step
         // index from device memory, so the captured sequence is replayable; one launch per decode.
-        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0, c.precision * 8 + nsplit};
+        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0, c.precision * 16 + nsplit * 2 + (D.pdl ? 1 : 0)};
         bool same = D.graph_exec != nullptr;
         for (int i = 0; i < 6; ++i) same = same && D.g_key[i] == key[i];
         if (!same) {
