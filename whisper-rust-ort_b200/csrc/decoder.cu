@@ -520,6 +520,243 @@ __global__ void advance_kernel(int* state) {
     state[0] += 1;
 }
 
+
+// ---- tensor-core skinny GEMM for the bf16 build (mma.sync m16n8k16, f32 accumulate) ----
+// Swap-AB view: the weight rows are the M side (16 per warp tile), the <=32 sequences the N side
+// (4 n-tiles of 8), so no tensor-core lane is wasted on batch padding.  A fragments come straight
+// from global memory with one 128-bit load per thread and row: thread t of a quad takes the 8
+// consecutive k (32c+8t..+7) and uses them as the slots of TWO mma steps; the activation tile in
+// shared memory ([32][K] bf16, row stride K*2+64 B: conflict-free 128-bit reads) is read with the
+// same k permutation, so the contraction is unchanged.  All weight fragments of a warp are loaded
+// BEFORE pdl_sync() (weights are constant), so HBM/L2 latency hides behind the predecessor kernel
+// and the activation staging + LayerNorm.  8 warps = RW row tiles x KS k-slices; slices are summed
+// through shared memory before the bias/GELU/residual epilogue.
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr int MM_THREADS = 256;
+
+template <int RW, int KS, int NCH>       // NCH = 32-wide k chunks per warp = K / KS / 32
+__global__ void __launch_bounds__(MM_THREADS, 1)
+skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
+                  const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  int act, const float* residual, float* Y) {
+    static_assert(RW * KS == 8, "8 warps");
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    const int xstride = K * 2 + 64;                                  // bytes per activation row
+    unsigned char* xs = mm_smem;                                     // [32][K] bf16 (padded rows)
+    float* part = reinterpret_cast<float*>(mm_smem + 32 * xstride);  // [KS][RW*16][33]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int rt = warp / KS, ks = warp % KS;
+    const int rows_cta = RW * 16;
+    const int n_tiles = (N + rows_cta - 1) / rows_cta;
+    const int kbase = ks * NCH * 32;
+    bool synced = false;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n0 = tile * rows_cta + rt * 16;
+        // ---- weight fragments for this warp: every load in flight before anything else ----
+        uint4 wa[NCH], wb[NCH];
+        {
+            const int r0 = min(n0 + g, N - 1), r1 = min(n0 + g + 8, N - 1);
+            const bf16* p0 = W + (size_t)r0 * K + kbase + 8 * t;
+            const bf16* p1 = W + (size_t)r1 * K + kbase + 8 * t;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                wa[c] = *reinterpret_cast<const uint4*>(p0 + c * 32);
+                wb[c] = *reinterpret_cast<const uint4*>(p1 + c * 32);
+            }
+        }
+        if (!synced) {
+            pdl_sync();
+            synced = true;
+            // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
+            for (int k0 = 0; k0 < K; k0 += 512) {
+                const int kc = min(512, K - k0);
+                float4 xv[4][4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int bb = warp + rr * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = i * 128 + lane * 4;
+                        xv[rr][i] = (bb < B && c < kc) ? *reinterpret_cast<const float4*>(X + (size_t)bb * K + k0 + c)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (ln_w) {                                           // host guarantees K <= 512 here
+                    float4 gw[4], gb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = i * 128 + lane * 4;
+                        gw[i] = c < kc ? *reinterpret_cast<const float4*>(ln_w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        gb[i] = c < kc ? *reinterpret_cast<const float4*>(ln_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    float s1[4], mean[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        s1[rr] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s1[rr] += (xv[rr][i].x + xv[rr][i].y) + (xv[rr][i].z + xv[rr][i].w);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) s1[rr] += __shfl_xor_sync(0xffffffffu, s1[rr], o);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        mean[rr] = s1[rr] / (float)K;
+                        float q = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i * 128 + lane * 4 < kc) {
+                                float t0 = xv[rr][i].x - mean[rr], t1 = xv[rr][i].y - mean[rr], t2 = xv[rr][i].z - mean[rr], t3 = xv[rr][i].w - mean[rr];
+                                q += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                            }
+                        s1[rr] = q;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) s1[rr] += __shfl_xor_sync(0xffffffffu, s1[rr], o);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const float rs = 1.0f / sqrtf(s1[rr] / (float)K + 1e-5f);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            xv[rr][i].x = (xv[rr][i].x - mean[rr]) * rs * gw[i].x + gb[i].x;
+                            xv[rr][i].y = (xv[rr][i].y - mean[rr]) * rs * gw[i].y + gb[i].y;
+                            xv[rr][i].z = (xv[rr][i].z - mean[rr]) * rs * gw[i].z + gb[i].z;
+                            xv[rr][i].w = (xv[rr][i].w - mean[rr]) * rs * gw[i].w + gb[i].w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int bb = warp + rr * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = i * 128 + lane * 4;
+                        if (c < kc) {
+                            uint2 pk;
+                            pk.x = pack_bf16(xv[rr][i].x, xv[rr][i].y);
+                            pk.y = pack_bf16(xv[rr][i].z, xv[rr][i].w);
+                            *reinterpret_cast<uint2*>(xs + bb * xstride + (k0 + c) * 2) = pk;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- 16 rows x 32 sequences x (K / KS) on the tensor cores ----
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const uint4 xb = *reinterpret_cast<const uint4*>(xs + (nt * 8 + g) * xstride + (kbase + c * 32 + 8 * t) * 2);
+                mma_bf16(acc[nt], wa[c].x, wb[c].x, wa[c].y, wb[c].y, xb.x, xb.y);
+                mma_bf16(acc[nt], wa[c].z, wb[c].z, wa[c].w, wb[c].w, xb.z, xb.w);
+            }
+        }
+        // ---- combine k-slices, epilogue ----
+        if (KS > 1) {
+            __syncthreads();                                         // previous tile's readers are done
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                float* pr = part + ((size_t)ks * rows_cta + rt * 16) * 33;
+                pr[(g) * 33 + nt * 8 + 2 * t] = acc[nt][0];
+                pr[(g) * 33 + nt * 8 + 2 * t + 1] = acc[nt][1];
+                pr[(g + 8) * 33 + nt * 8 + 2 * t] = acc[nt][2];
+                pr[(g + 8) * 33 + nt * 8 + 2 * t + 1] = acc[nt][3];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < rows_cta * 32; idx += MM_THREADS) {
+                const int nl = idx % rows_cta, b = idx / rows_cta;
+                const int n = tile * rows_cta + nl;
+                if (b < B && n < N) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int k2 = 0; k2 < KS; ++k2) v += part[((size_t)k2 * rows_cta + nl) * 33 + b];
+                    if (bias) v += bias[n];
+                    if (act == 1) v = gelu_erf(v);
+                    if (residual) v += residual[(size_t)b * N + n];
+                    Y[(size_t)b * N + n] = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n = n0 + g + (i >> 1) * 8, b = nt * 8 + 2 * t + (i & 1);
+                    if (b < B && n < N) {
+                        float v = acc[nt][i];
+                        if (bias) v += bias[n];
+                        if (act == 1) v = gelu_erf(v);
+                        if (residual) v += residual[(size_t)b * N + n];
+                        Y[(size_t)b * N + n] = v;
+                    }
+                }
+        }
+    }
+}
+
+template <int RW, int KS, int NCH>
+void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
+                       const float* lb, int act, const float* residual, float* Y) {
+    const size_t smem = (size_t)32 * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * 33 : 0);
+    const int tiles = ceil_div(N, RW * 16);
+    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    launch_k(skinny_mma_kernel<RW, KS, NCH>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, ctx->dec.pdl, X, B, K, W, N, bias, lw, lb,
+             act, residual, Y);
+}
+
+// bf16 build: route a skinny GEMM to the tensor-core kernel when its shape has an instantiation.
+inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
+                       const float* lb, int act, const float* residual, float* Y) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("WB_DEC_MMA"); enabled = !(e && e[0] == '0'); }
+    if (!enabled || B > 32 || (lw && K > 512)) return false;
+    if (N >= 8192) {                               // vocabulary projection: 128 rows per CTA pass, grid-stride
+        if (K == 512) { skinny_mma_launch<8, 1, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+        if (K == 128) { skinny_mma_launch<8, 1, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+        return false;
+    }
+    if (N > 1024) {                                // qkv / fc1: 64 rows per CTA, 2 k-slices
+        if (K == 512) { skinny_mma_launch<4, 2, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+        return false;
+    }
+    if (K == 512) { skinny_mma_launch<2, 4, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // o / cq / co
+    if (K == 2048) { skinny_mma_launch<2, 4, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }  // fc2
+    if (K == 128) { skinny_mma_launch<2, 4, 1>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // toy
+    if (K == 256) { skinny_mma_launch<2, 4, 2>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // toy ffn
+    return false;
+}
+void skinny_mma_set_attrs() {       // once per process, outside any stream capture
+    const int smem = 32 * (2048 * 2 + 64) + (int)sizeof(float) * 8 * 16 * 33;
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+}
+inline bool skinny_mma(wb_ctx*, const float*, int, int, const float*, int, const float*, const float*, const float*, int,
+                       const float*, float*) { return false; }     // fp32 validation build stays on the SIMT kernel
+
 template <typename WT, int R>
 void skinny_launch(wb_ctx* ctx, const float* X, int B, int K, const WT* W, int N, const float* bias, const float* lw,
                    const float* lb, int act, const float* residual, float* Y) {
@@ -541,6 +778,7 @@ void skinny(wb_ctx* ctx, const float* X, int B, int K, const LinearW& L, const L
     const float* lw = ln ? ln->w : nullptr;
     const float* lb = ln ? ln->b : nullptr;
     const float* bias = (L.b && !W_override) ? L.b : nullptr;
+    if (skinny_mma(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y)) { CUDA_CHECK(cudaGetLastError()); return; }
     // rows per warp: enough CTAs to cover the chip for the per-layer GEMMs, register blocking for the vocab one
     if (N >= 8192) skinny_launch<WT, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
     else if (N >= 1024) skinny_launch<WT, 2>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
@@ -633,7 +871,7 @@ void decoder_alloc(wb_ctx* ctx) {
     const size_t words = ((size_t)c.vocab + 31) / 32;
     D.sup_base.reserve(words);
     D.sup_first.reserve(words);
-    if (c.precision == WB_PREC_BF16) set_func_attrs<bf16>(); else set_func_attrs<float>();
+    if (c.precision == WB_PREC_BF16) { set_func_attrs<bf16>(); skinny_mma_set_attrs(); } else set_func_attrs<float>();
 }
 
 void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
