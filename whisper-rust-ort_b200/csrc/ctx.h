@@ -91,6 +91,8 @@ struct DecBufs {
     DevBuf<int> tokens;                // [B][T_total] generated+prompt ids (device)
     DevBuf<int> forced;                // [B][max_new] teacher forcing (optional)
     DevBuf<int> lens, finished, state; // state: [0]=position t, [1]=#unfinished
+    DevBuf<float> xscratch;            // cross-attention split-key partials [B][H][XSPLIT][64+2]
+    DevBuf<int> xcount;                // arrival counters [B][H]
     DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
     int T_max = 0;
     // whole-decode CUDA graph (all steps), rebuilt when the key changes

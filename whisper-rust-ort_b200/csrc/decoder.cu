@@ -348,117 +348,171 @@ self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, K
 }
 
 // ---- cross-attention over the cached encoder K/V: the dominant HBM stream of a step ----
-// grid (H, B), 256 threads.  Every lane moves 32 bytes per row visit (two 128-bit loads), so a
-// 64-wide K or V row takes 8 lanes in f32 and 4 lanes in bf16 and a warp instruction always
-// covers 1 KB; UN rows per lane group are in flight before any of them is consumed.
-template <typename KT> struct RowLoad;
-template <> struct RowLoad<float> {
-    static constexpr int DPL = 8;                         // dims per lane
-    static __device__ __forceinline__ void load(const float* p, float (&f)[8]) { load8(p, f); }
+// grid (H, B, XSPLIT), 256 threads.  Single pass, flash-decoding style: every lane group (8 lanes
+// in f32, 4 in bf16: 32 bytes of a 64-wide row per lane) walks its keys with an online softmax,
+// loading the K and the V row of UN keys together (raw 128-bit registers, converted on use), so a
+// CTA exposes Tk / (groups * UN * XSPLIT) memory round trips instead of two passes over the keys.
+// Groups merge by shuffles, warps through shared memory, the XSPLIT key ranges of a (b,h) pair
+// through a global scratch + arrival counter: the last CTA to arrive writes the output.
+#ifndef WB_XSPLIT
+#define WB_XSPLIT 1
+#endif
+constexpr int XSPLIT = WB_XSPLIT;
+
+template <typename KT> struct RowRaw;
+template <> struct RowRaw<float> {
+    static constexpr int DPL = 8;
+    uint4 a, b;
+    // p points at the lane's first segment; the second segment lives 32 dims further (next 128-byte line)
+    __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const uint4*>(p); b = *reinterpret_cast<const uint4*>(p + 32); }
+    __device__ __forceinline__ void get(float (&f)[8]) const {
+        f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+        f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+    }
 };
-template <> struct RowLoad<bf16> {
+template <> struct RowRaw<bf16> {
     static constexpr int DPL = 16;
-    static __device__ __forceinline__ void load(const bf16* p, float (&f)[16]) {
-        float a[8], b[8];
-        load8(p, a); load8(p + 8, b);
+    uint4 a, b;
+    __device__ __forceinline__ void load(const bf16* p) { a = *reinterpret_cast<const uint4*>(p); b = *reinterpret_cast<const uint4*>(p + 32); }
+    __device__ __forceinline__ void get(float (&f)[16]) const {
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { f[i] = a[i]; f[8 + i] = b[i]; }
+        for (int i = 0; i < 8; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
     }
 };
 
 template <typename KT>
 __global__ void __launch_bounds__(256)
 cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out,
-                  int d, int Tk) {
-    constexpr int DPL = RowLoad<KT>::DPL, LPR = 64 / DPL, NG = 256 / LPR, UN = 4;
-    extern __shared__ float sm[];                 // scores [Tk]
-    float* s_p = sm;
-    __shared__ float s_red[8];
+                  float* __restrict__ scratch, int* __restrict__ counters, int d, int Tk) {
+    constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = 256 / LPR, UN = 4;
+    __shared__ float s_m[8], s_l[8];
     __shared__ float s_acc[8][64];
-    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_last;
+    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, H = gridDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / LPR, li = tid % LPR;
-    const KT* base = ckv + (size_t)b * Tk * 2 * d + h * 64 + li * DPL;
+    const int per = (Tk + XSPLIT - 1) / XSPLIT, k_lo = sp * per, k_hi = min(Tk, k_lo + per);
+    // lane li owns dims [li*DPL/2, +DPL/2) and [32 + li*DPL/2, +DPL/2): each 128-bit load instruction of a
+    // lane group then covers whole 32-byte sectors of consecutive bytes of the row
+    constexpr int HPL = DPL / 2;
+    const KT* kbase = ckv + (size_t)b * Tk * 2 * d + h * 64 + li * HPL;
+    const KT* vbase = kbase + d;
+
+    // the first K/V rows do not depend on the predecessor kernel: get them moving before the sync
+    RowRaw<KT> kr[UN], vr[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        const int j = min(k_lo + grp + u * NG, k_hi - 1);
+        kr[u].load(kbase + (size_t)j * 2 * d);
+        vr[u].load(vbase + (size_t)j * 2 * d);
+    }
     pdl_sync();
     float qv[DPL];
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * DPL + i] * 0.125f;
+    for (int i = 0; i < DPL; ++i) qv[i] = q[(size_t)b * d + h * 64 + (i < HPL ? li * HPL + i : 32 + li * HPL + (i - HPL))] * 0.125f;
 
-    float lmax = -INFINITY;
-    for (int j0 = grp; j0 < Tk; j0 += NG * UN) {
-        float kf[UN][DPL];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int j = min(j0 + u * NG, Tk - 1);           // clamp: uniform control flow, result discarded
-            RowLoad<KT>::load(base + (size_t)j * 2 * d, kf[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int j = j0 + u * NG;
-            float p = 0.f;
-#pragma unroll
-            for (int i = 0; i < DPL; ++i) p = fmaf(qv[i], kf[u][i], p);
-#pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-            if (j < Tk) {
-                if (li == 0) s_p[j] = p;
-                lmax = fmaxf(lmax, p);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-    if (lane == 0) s_red[warp] = lmax;
-    __syncthreads();
-    float m = s_red[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i]);
-    __syncthreads();
-    float sum = 0.f;
-    for (int j = tid; j < Tk; j += 256) { float e = expf(s_p[j] - m); s_p[j] = e; sum += e; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s_red[warp] = sum;
-    __syncthreads();
-    sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sum += s_red[i];
-    const float inv = 1.0f / sum;
-
-    float acc[DPL];
+    float m = -INFINITY, l = 0.f, acc[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-    const KT* vbase = base + d;
-    for (int j0 = grp; j0 < Tk; j0 += NG * UN) {
-        float vf[UN][DPL];
+    for (int j0 = k_lo + grp; j0 < k_hi; j0 += NG * UN) {
+        float sc[UN];
+        float mx = m;
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const int j = min(j0 + u * NG, Tk - 1);
-            RowLoad<KT>::load(vbase + (size_t)j * 2 * d, vf[u]);
+            float kf[DPL];
+            kr[u].get(kf);
+            float p = 0.f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) p = fmaf(qv[i], kf[i], p);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            sc[u] = (j0 + u * NG < k_hi) ? p : -INFINITY;
+            mx = fmaxf(mx, sc[u]);
         }
+        // next round of K rows can leave now; V rows of this round are consumed below
+        const int jn = j0 + NG * UN;
+        if (jn < k_hi) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) kr[u].load(kbase + (size_t)min(jn + u * NG, k_hi - 1) * 2 * d);
+        }
+        const float scale = (mx == -INFINITY) ? 1.f : expf(m - mx);      // m = -inf on the first round -> 0
+        l *= scale;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) acc[i] *= scale;
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const int j = j0 + u * NG;
-            const float p = j < Tk ? s_p[j] * inv : 0.f;
+            const float p = (sc[u] == -INFINITY) ? 0.f : expf(sc[u] - mx);
+            float vf[DPL];
+            vr[u].get(vf);
+            l += p;
 #pragma unroll
-            for (int i = 0; i < DPL; ++i) acc[i] = fmaf(p, vf[u][i], acc[i]);
+            for (int i = 0; i < DPL; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+        }
+        m = mx;
+        if (jn < k_hi) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) vr[u].load(vbase + (size_t)min(jn + u * NG, k_hi - 1) * 2 * d);
         }
     }
-    // reduce the lane groups of a warp, then the 8 warps
+    // merge lane groups inside the warp (l is replicated over the LPR lanes of a group)
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) {
+    for (int o = LPR; o < 32; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        const float mn = fmaxf(m, m2);
+        const float w1 = (m == -INFINITY) ? 0.f : expf(m - mn), w2 = (m2 == -INFINITY) ? 0.f : expf(m2 - mn);
 #pragma unroll
-        for (int o = LPR; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        for (int i = 0; i < DPL; ++i) acc[i] = acc[i] * w1 + __shfl_xor_sync(0xffffffffu, acc[i], o) * w2;
+        l = l * w1 + l2 * w2;
+        m = mn;
     }
     if (lane < LPR) {
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) s_acc[warp][lane * DPL + i] = acc[i];
+        for (int i = 0; i < DPL; ++i) s_acc[warp][i < HPL ? lane * HPL + i : 32 + lane * HPL + (i - HPL)] = acc[i];
+        if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
     }
     __syncthreads();
-    if (tid < 64) {
-        float a = 0.f;
+    float my = 0.f, mt = -INFINITY, lt = 0.f;
+    if (tid < 64) {                                     // merge the 8 warps: thread <-> output dim
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a += s_acc[w][tid];
-        out[(size_t)b * d + h * 64 + tid] = a;
+        for (int w = 0; w < 8; ++w) mt = fmaxf(mt, s_m[w]);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float wgt = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - mt);
+            my = fmaf(s_acc[w][tid], wgt, my);
+            lt = fmaf(s_l[w], wgt, lt);
+        }
+    }
+    if (XSPLIT == 1) {
+        if (tid < 64) out[(size_t)b * d + h * 64 + tid] = my / lt;
+        return;
+    }
+    // publish this key range, the last CTA of the (b,h) pair combines them
+    float* rec = scratch + ((size_t)(b * H + h) * XSPLIT + sp) * 66;
+    if (tid < 64) rec[tid] = my;
+    if (tid == 0) { rec[64] = mt; rec[65] = lt; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int prev = atomicAdd(counters + b * H + h, 1);
+        s_last = (prev == XSPLIT - 1);
+        if (s_last) counters[b * H + h] = 0;           // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last && tid < 64) {
+        __threadfence();
+        const float* r0 = scratch + (size_t)(b * H + h) * XSPLIT * 66;
+        float mm = -INFINITY;
+#pragma unroll
+        for (int s2 = 0; s2 < XSPLIT; ++s2) mm = fmaxf(mm, __ldcg(r0 + s2 * 66 + 64));
+        float a = 0.f, ll = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < XSPLIT; ++s2) {
+            const float wgt = expf(__ldcg(r0 + s2 * 66 + 64) - mm);
+            a = fmaf(__ldcg(r0 + s2 * 66 + tid), wgt, a);
+            ll = fmaf(__ldcg(r0 + s2 * 66 + 65), wgt, ll);
+        }
+        out[(size_t)b * d + h * 64 + tid] = a / ll;
     }
 }
 
@@ -825,7 +879,8 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
         launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)qkv, skv, att, d, D.T_max); ++n;   // K3d
         skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;                                      // K3f
         skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
-        launch_k(cross_attn_kernel<WT>, dim3(H, B), dim3(256), sizeof(float) * Tk, st, pdl, (const float*)q, ckv, att, d, Tk); ++n;   // K3e
+        launch_k(cross_attn_kernel<WT>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, (const float*)q, ckv, att,
+                 D.xscratch.p + (size_t)b0 * H * XSPLIT * 66, D.xcount.p + (size_t)b0 * H, d, Tk); ++n;   // K3e
         skinny<WT>(ctx, att, B, d, L.co, nullptr, 0, x, x); ++n;
         skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, ffn); ++n;                               // K3g
         skinny<WT>(ctx, ffn, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
@@ -863,6 +918,8 @@ void decoder_alloc(wb_ctx* ctx) {
     D.lens.reserve(B);
     D.finished.reserve(B);
     D.state.reserve(16);
+    D.xscratch.reserve(B * (size_t)c.n_heads * XSPLIT * 66);
+    D.xcount.reserve_zero(B * (size_t)c.n_heads);
     for (int k = 0; k < 3; ++k) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&D.side[k], cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_join[k], cudaEventDisableTiming));
@@ -1013,8 +1070,8 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
         const int l = i % c.dec_layers;
         if (k == "cross_attn") {
             const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * Tk * 2 * d * ctx->esz();
-            if (bf) cross_attn_kernel<bf16><<<dim3(H, B), 256, sizeof(float) * Tk, ctx->stream>>>(D.q.p, (const bf16*)ckv, D.att.p, d, Tk);
-            else cross_attn_kernel<float><<<dim3(H, B), 256, sizeof(float) * Tk, ctx->stream>>>(D.q.p, (const float*)ckv, D.att.p, d, Tk);
+            if (bf) cross_attn_kernel<bf16><<<dim3(H, B, XSPLIT), 256, 0, ctx->stream>>>(D.q.p, (const bf16*)ckv, D.att.p, D.xscratch.p, D.xcount.p, d, Tk);
+            else cross_attn_kernel<float><<<dim3(H, B, XSPLIT), 256, 0, ctx->stream>>>(D.q.p, (const float*)ckv, D.att.p, D.xscratch.p, D.xcount.p, d, Tk);
         } else if (k == "vocab_proj") {
             LinearW dummy;
             if (bf) skinny<bf16>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
