@@ -93,6 +93,9 @@ struct DecBufs {
     DevBuf<int> lens, finished, state; // state: [0]=position t, [1]=#unfinished
     DevBuf<float> xscratch;            // cross-attention split-key partials [B][H][XSPLIT][64+2]
     DevBuf<int> xcount;                // arrival counters [B][H]
+    DevBuf<float> amax_buf;            // fused arg-max partials of the vocabulary projection
+    float* amax_val = nullptr; int* amax_idx = nullptr; int* amax_state = nullptr; int amax_ctas = 0;
+    bool fuse_argmax = true, want_logits = false;
     DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
     int T_max = 0;
     // whole-decode CUDA graph (all steps), rebuilt when the key changes

@@ -569,6 +569,38 @@ argmax_kernel(const int* __restrict__ state, const float* __restrict__ logits, i
     }
 }
 
+// Second half of the fused arg-max: combine the per-CTA partials of the vocabulary projection.
+__global__ void __launch_bounds__(32)
+argmax_merge_kernel(const int* __restrict__ state, const float* __restrict__ pval, const int* __restrict__ pidx, int n_part,
+                    const int* __restrict__ forced, int max_new, int eot, int T_total, int* __restrict__ tokens,
+                    int* __restrict__ lens, int* __restrict__ finished, int* __restrict__ cur_tok) {
+    pdl_sync();
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int s = state[0], prompt_len = state[1], gi = s - (prompt_len - 1);
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int p = lane; p < n_part; p += 32) {
+        const float v = pval[p * 32 + b];
+        const int i = pidx[p * 32 + b];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        const int tok = (bi == 0x7fffffff) ? 0 : bi;
+        if (!finished[b]) {
+            tokens[(size_t)b * T_total + prompt_len + gi] = tok;
+            lens[b] = prompt_len + gi + 1;
+            if (tok == eot) finished[b] = 1;
+        }
+        cur_tok[b] = forced ? forced[(size_t)b * max_new + gi] : tok;
+    }
+}
+
 __global__ void advance_kernel(int* state) {
     pdl_sync();
     state[0] += 1;
@@ -601,7 +633,10 @@ template <int RW, int KS, int NCH>       // NCH = 32-wide k chunks per warp = K 
 __global__ void __launch_bounds__(MM_THREADS, 1)
 skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                  int act, const float* residual, float* Y) {
+                  int act, const float* residual, float* Y,
+                  // fused masked arg-max over the N rows (vocabulary projection, KS == 1 only): per-CTA partials
+                  const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
+                  float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     static_assert(RW * KS == 8, "8 warps");
     extern __shared__ __align__(16) unsigned char mm_smem[];
     const int xstride = K * 2 + 64;                                  // bytes per activation row
@@ -613,6 +648,11 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
     const int n_tiles = (N + rows_cta - 1) / rows_cta;
     const int kbase = ks * NCH * 32;
     bool synced = false;
+    float bestv[8];
+    int besti[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bestv[i] = -INFINITY; besti[i] = 0x7fffffff; }
+    const unsigned* sup = nullptr;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int n0 = tile * rows_cta + rt * 16;
@@ -631,6 +671,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
         if (!synced) {
             pdl_sync();
             synced = true;
+            if (amax_val) sup = (state[0] - (state[1] - 1) == 0) ? sup_first : sup_base;   // first generated token?
             // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
             for (int k0 = 0; k0 < K; k0 += 512) {
                 const int kc = min(512, K - k0);
@@ -750,31 +791,82 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                 }
             }
         } else {
+            bool ok[2] = {false, false};
+            if (amax_val) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int n = n0 + g + hh * 8;
+                    ok[hh] = n < N && !((sup[n >> 5] >> (n & 31)) & 1u);
+                }
+            }
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int n = n0 + g + (i >> 1) * 8, b = nt * 8 + 2 * t + (i & 1);
+                    float v = acc[nt][i];
+                    if (bias && n < N) v += bias[n];
+                    if (act == 1) v = gelu_erf(v);
                     if (b < B && n < N) {
-                        float v = acc[nt][i];
-                        if (bias) v += bias[n];
-                        if (act == 1) v = gelu_erf(v);
                         if (residual) v += residual[(size_t)b * N + n];
-                        Y[(size_t)b * N + n] = v;
+                        if (Y) Y[(size_t)b * N + n] = v;
+                    }
+                    if (amax_val && ok[i >> 1]) {           // strict '>' in increasing n: lowest index wins ties, NaN never
+                        const int slot = nt * 2 + (i & 1);
+                        if (v > bestv[slot] || (v == bestv[slot] && n < besti[slot])) { bestv[slot] = v; besti[slot] = n; }
                     }
                 }
+        }
+    }
+    if (KS == 1 && amax_val) {
+        // reduce over the 8 row lanes (g) that share a sequence, then over the 8 warps, one partial per CTA
+        float* sv = reinterpret_cast<float*>(mm_smem + 32 * xstride);      // [8 warps][32] (+ indices)
+        int* si = reinterpret_cast<int*>(sv + 8 * 32);
+#pragma unroll
+        for (int slot = 0; slot < 8; ++slot) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bestv[slot], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti[slot], o);
+                if (ov > bestv[slot] || (ov == bestv[slot] && oi < besti[slot])) { bestv[slot] = ov; besti[slot] = oi; }
+            }
+        }
+        __syncthreads();
+        if (g == 0) {
+#pragma unroll
+            for (int slot = 0; slot < 8; ++slot) {
+                const int b = (slot >> 1) * 8 + 2 * t + (slot & 1);
+                sv[warp * 32 + b] = bestv[slot];
+                si[warp * 32 + b] = besti[slot];
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float bv = sv[tid];
+            int bi = si[tid];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) {
+                const float ov = sv[w * 32 + tid];
+                const int oi = si[w * 32 + tid];
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            amax_val[blockIdx.x * 32 + tid] = bv;
+            amax_idx[blockIdx.x * 32 + tid] = bi;
         }
     }
 }
 
 template <int RW, int KS, int NCH>
 void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
-                       const float* lb, int act, const float* residual, float* Y) {
-    const size_t smem = (size_t)32 * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * 33 : 0);
+                       const float* lb, int act, const float* residual, float* Y, bool fused_argmax = false) {
+    const size_t smem = (size_t)32 * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * 33 : 8 * 32 * 8);
     const int tiles = ceil_div(N, RW * 16);
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-    launch_k(skinny_mma_kernel<RW, KS, NCH>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, ctx->dec.pdl, X, B, K, W, N, bias, lw, lb,
-             act, residual, Y);
+    DecBufs& D = ctx->dec;
+    launch_k(skinny_mma_kernel<RW, KS, NCH>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
+             act, residual, Y, (const int*)(fused_argmax ? D.amax_state : nullptr), (const unsigned*)D.sup_base.p,
+             (const unsigned*)D.sup_first.p, fused_argmax ? D.amax_val : (float*)nullptr, fused_argmax ? D.amax_idx : (int*)nullptr);
+    if (fused_argmax) D.amax_ctas = grid;
 }
 
 // bf16 build: route a skinny GEMM to the tensor-core kernel when its shape has an instantiation.
@@ -784,8 +876,9 @@ inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W,
     if (enabled < 0) { const char* e = getenv("WB_DEC_MMA"); enabled = !(e && e[0] == '0'); }
     if (!enabled || B > 32 || (lw && K > 512)) return false;
     if (N >= 8192) {                               // vocabulary projection: 128 rows per CTA pass, grid-stride
-        if (K == 512) { skinny_mma_launch<8, 1, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
-        if (K == 128) { skinny_mma_launch<8, 1, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+        const bool fa = ctx->dec.amax_state != nullptr;
+        if (K == 512) { skinny_mma_launch<8, 1, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
+        if (K == 128) { skinny_mma_launch<8, 1, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
         return false;
     }
     if (N > 1024) {                                // qkv / fc1: 64 rows per CTA, 2 k-slices
@@ -887,11 +980,25 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
     }
     if (with_logits) {                                                                               // K3h
         LinearW dummy;
-        skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, logits, c.vocab, w.embed); ++n;
-        launch_k(argmax_kernel, dim3(B), dim3(1024), 0, st, pdl, (const int*)state, (const float*)logits, c.vocab,
-                 (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p,
-                 forced_dev ? forced_dev + (size_t)b0 * max_new : (const int*)nullptr, max_new, eot, T_total,
-                 D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
+        // bf16 build: arg-max partials are produced by the vocabulary projection itself (no logits round trip
+        // unless the caller asked for logits); fp32 build: separate full arg-max over the logits.
+        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax;
+        D.amax_state = fuse ? state : nullptr;
+        const int slice = (int)((long long)b0 * 4 / c.max_batch);           // up to 4 concurrent sub-batch chains
+        D.amax_val = D.amax_buf.p + (size_t)slice * 64 * ctx->sm_count;      // per-chain slice: [ctas][32] val | idx
+        D.amax_idx = reinterpret_cast<int*>(D.amax_val + (size_t)32 * ctx->sm_count);
+        D.amax_ctas = 0;
+        skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, (fuse && !D.want_logits) ? nullptr : logits, c.vocab, w.embed); ++n;
+        D.amax_state = nullptr;
+        const int* fdev = forced_dev ? forced_dev + (size_t)b0 * max_new : (const int*)nullptr;
+        if (fuse && D.amax_ctas > 0) {
+            launch_k(argmax_merge_kernel, dim3(B), dim3(32), 0, st, pdl, (const int*)state, (const float*)D.amax_val, (const int*)D.amax_idx,
+                     D.amax_ctas, fdev, max_new, eot, T_total, D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
+        } else {
+            launch_k(argmax_kernel, dim3(B), dim3(1024), 0, st, pdl, (const int*)state, (const float*)logits, c.vocab,
+                     (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p, fdev, max_new, eot, T_total,
+                     D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
+        }
     }
     launch_k(advance_kernel, dim3(1), dim3(1), 0, st, pdl, state); ++n;
     ctx->stream = saved;
@@ -920,6 +1027,7 @@ void decoder_alloc(wb_ctx* ctx) {
     D.state.reserve(16);
     D.xscratch.reserve(B * (size_t)c.n_heads * XSPLIT * 66);
     D.xcount.reserve_zero(B * (size_t)c.n_heads);
+    D.amax_buf.reserve((size_t)4 * 64 * ctx->sm_count);
     for (int k = 0; k < 3; ++k) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&D.side[k], cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_join[k], cudaEventDisableTiming));
@@ -1016,6 +1124,9 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
         }
         return n;
     };
+    const char* fenv = getenv("WB_FUSE_ARGMAX");
+    D.fuse_argmax = !(fenv && fenv[0] == '0');
+    D.want_logits = p.want_logits;
     const char* penv = getenv("WB_PDL");
     D.pdl = !(penv && penv[0] == '0') && !p.want_logits;
     const char* genv = getenv("WB_GRAPH");
