@@ -37,6 +37,8 @@ EOT = 50257
 MAX_NEW = 128
 CLIP_S = 30.0
 BATCH = 32
+# dram bytes per cross_attn_kernel launch at B=32 from the committed ncu capture (profiles/r1_cross_attn_v3_raw.csv: 98.40 MB read + 4.25 MB write)
+NCU_TRAFFIC_BYTES = {"bf16": 102.65e6, "fp32": None}
 METRIC = "audio-sec/sec (RTFx) whisper-base"
 UNIT = "audio-s/s"
 
@@ -170,6 +172,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")           # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     prec = wb200.WB_PREC_BF16 if args.precision == "bf16" else wb200.WB_PREC_FP32
@@ -255,7 +258,9 @@ def run_ours(args, rank, world, local_rank):
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "clocks": clocks,
             "roofline": {"kernel": "cross_attn_kernel (decoder cross-attention over cached encoder K/V)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.precision),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture in profiles/ (B=32)",
                          "peak_source": peak_src, "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                          "share_of_step": share,
                          "also": {"vocab_proj": {"achieved": v_bytes / (v_ms * 1e-3) / 1e9, "ms_per_launch": v_ms, "bytes_per_launch": v_bytes}}},
