@@ -3,9 +3,11 @@
 whisper-base hot path (log-mel -> encoder -> 128-token KV-cache greedy decode) at batch 32 per GPU
 (BASELINE.json configs[3]; the config the metric "RTFx whisper-base at 1/2/4/8 B200" is quoted on).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32] [--in-flight S]
 
-One "step" = one pass of the hot path over one batch of 32 synthetic 30 s clips per GPU.
+One "step" = one pass of the hot path over one batch of 32 synthetic 30 s clips per GPU; S steps
+(default 4) are in flight per GPU at a time, each in its own context/stream, because one decode is a
+chain of small dependent kernels that leaves most SMs idle (`single_batch_in_flight` reports S = 1).
 `value`  : whole-job audio-s/s with the PCM already resident in HBM (device-timed, max over ranks).
 `e2e`    : same metric through the reference-facing C ABI call wb_transcribe_batch with HOST
            (pinned) PCM buffers — H2D of the PCM and D2H of the token ids inside the timed region.
@@ -176,62 +178,87 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     prec = wb200.WB_PREC_BF16 if args.precision == "bf16" else wb200.WB_PREC_FP32
-    B = args.batch
-    m = wb200.Whisper(wb200.default_cfg("base", precision=prec, max_batch=B, max_chunks=B), device=local_rank)
+    B, S = args.batch, max(1, args.in_flight)
+    # S independent contexts (own stream, activations, KV caches, decode graph) = S batches in flight per GPU:
+    # a decode step is ~50 dependent small kernels, so concurrent batches fill the SMs a single chain leaves idle.
+    ctxs = [wb200.Whisper(wb200.default_cfg("base", precision=prec, max_batch=B, max_chunks=B), device=local_rank) for _ in range(S)]
+    m = ctxs[0]
     sup, bsup = suppress_lists()
 
     # this rank's shard of the global clip list (global_batch = B * world, independent clips)
     lo, hi = shard_range(B * world, rank, world)
     clips = wb200.synth.fast_batch(B * world, seed=1)[lo:hi]
     n_clip = clips.shape[1]
-    pinned = torch.empty(clips.shape, dtype=torch.float32).pin_memory()
-    pinned.numpy()[:] = clips
+    pinned = []
+    for i in range(S):
+        t = torch.empty(clips.shape, dtype=torch.float32).pin_memory()
+        t.numpy()[:] = clips
+        pinned.append(t)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def run_workers(fn, n_steps):
+        """n_steps steps in total, dealt round-robin to the S contexts, one host thread per context."""
+        lat = [[] for _ in range(S)]
+        def work(i):
+            for _ in range(i, n_steps, S):
+                t1 = time.perf_counter()
+                fn(i)
+                lat[i].append(time.perf_counter() - t1)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(S)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return [x for l in lat for x in l]
+
     # ---- value: PCM resident in HBM ----
-    assert m.upload_pcm(clips) == B
-    toks = None
-    for _ in range(args.warmup):
-        toks = m.transcribe_resident(B, PROMPT, MAX_NEW, EOT, sup, bsup)
-    launches = 0
+    toks = [None] * S
+    for c in ctxs:
+        assert c.upload_pcm(clips) == B
+    def resident_step(i):
+        toks[i] = ctxs[i].transcribe_resident(B, PROMPT, MAX_NEW, EOT, sup, bsup)
+    run_workers(resident_step, args.warmup * S)
     barrier()
     with ClockSampler(local_rank) as clk:
         m.mark(0)
         t0 = time.perf_counter()
-        stage = {"mel_ms": 0.0, "encoder_ms": 0.0, "cross_kv_ms": 0.0, "decode_ms": 0.0}
-        for _ in range(args.steps):
-            toks = m.transcribe_resident(B, PROMPT, MAX_NEW, EOT, sup, bsup)
-            tm = m.timing()
-            launches += tm["mel_launches"] + tm["encoder_launches"] + tm["decode_launches"]
-            for k in stage:
-                stage[k] += tm[k]
+        lat_res = run_workers(resident_step, args.steps)
+        torch.cuda.synchronize(dev)
         m.mark(1)
         dev_ms = m.elapsed_ms(0, 1)
         barrier()
         wall = time.perf_counter() - t0
+    tm = m.timing()
+    launches_per_step = tm["mel_launches"] + tm["encoder_launches"] + tm["decode_launches"]
+    stage = {k: tm[k] for k in ("mel_ms", "encoder_ms", "cross_kv_ms", "decode_ms")}
     dev_s = dist_max(dev_ms / 1000.0, dist, dev)
     wall = dist_max(wall, dist, dev)
     audio_s = B * world * CLIP_S * args.steps
     value = audio_s / dev_s
 
     # ---- e2e: host (pinned) PCM through the C ABI, H2D + D2H inside the timed region ----
-    for _ in range(max(1, args.warmup // 2)):
-        m.transcribe_batch_ptr(pinned.data_ptr(), B, n_clip, PROMPT, MAX_NEW, EOT, sup, bsup)
+    def e2e_step(i):
+        ctxs[i].transcribe_batch_ptr(pinned[i].data_ptr(), B, n_clip, PROMPT, MAX_NEW, EOT, sup, bsup)
+    run_workers(e2e_step, max(1, args.warmup // 2) * S)
     barrier()
-    lat = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        t1 = time.perf_counter()
-        tk, lens = m.transcribe_batch_ptr(pinned.data_ptr(), B, n_clip, PROMPT, MAX_NEW, EOT, sup, bsup)
-        lat.append(time.perf_counter() - t1)
+    lat = run_workers(e2e_step, args.steps)
     barrier()
     e2e_s = dist_max(time.perf_counter() - t0, dist, dev)
     e2e_value = audio_s / e2e_s
     p95 = dist_max(float(np.percentile(lat, 95)), dist, dev)
+
+    # ---- one batch at a time on an otherwise idle GPU: the latency-optimal operating point ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        m.transcribe_batch_ptr(pinned[0].data_ptr(), B, n_clip, PROMPT, MAX_NEW, EOT, sup, bsup)
+    single_s = (time.perf_counter() - t0) / 3
+    tm1 = m.timing()
 
     # ---- roofline of the dominant kernel, measured live with CUDA events ----
     k_ms, k_bytes = m.bench_kernel("cross_attn", B, iters=30)
@@ -239,7 +266,7 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
     steps_dec = len(PROMPT) + MAX_NEW - 1
-    share = 6 * steps_dec * k_ms * args.steps / max(stage["decode_ms"] + stage["encoder_ms"] + stage["cross_kv_ms"] + stage["mel_ms"], 1e-9)
+    share = 6 * steps_dec * k_ms / max(tm1["decode_ms"] + tm1["encoder_ms"] + tm1["cross_kv_ms"] + tm1["mel_ms"], 1e-9)
 
     if rank == 0:
         clocks = clk.summary()
@@ -248,23 +275,26 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(B), "clips_per_gpu_per_step": B, "global_batch": B * world, "max_new_tokens": MAX_NEW,
+                       "batches_in_flight_per_gpu": S,
                        "weights": "seeded random-init whisper-base (no checkpoint offline)",
                        "l2": "working set per step (61 MB PCM + 145-290 MB weights + 0.6-1.2 GB cross-K/V) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"clips sharded over {world} GPU(s), one process per GPU, no collective on the data path"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4) * world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned[0].numel() * 4) * world,
                     "d2h_bytes_per_step": int(B * (len(PROMPT) + MAX_NEW) * 8 + B * 4) * world, "p95_latency_s_per_clip": p95},
-            "gpu_launches": int(launches),
+            "single_batch_in_flight": {"value": B * CLIP_S / single_s, "unit": UNIT, "latency_s_per_clip": single_s,
+                                       "stage_ms": {k: tm1[k] for k in ("mel_ms", "encoder_ms", "cross_kv_ms", "decode_ms")}},
+            "gpu_launches": int(launches_per_step * args.steps),
             "wall_s": wall,
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "stage_ms_per_step_under_load": stage,
             "clocks": clocks,
             "roofline": {"kernel": "cross_attn_kernel (decoder cross-attention over cached encoder K/V)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.precision),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture in profiles/ (B=32)",
                          "peak_source": peak_src, "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
-                         "share_of_step": share,
+                         "share_of_single_batch_step": share,
                          "also": {"vocab_proj": {"achieved": v_bytes / (v_ms * 1e-3) / 1e9, "ms_per_launch": v_ms, "bytes_per_launch": v_bytes}}},
-            "tokens_head": toks[0][:8],
+            "tokens_head": toks[0][0][:8],
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -275,9 +305,10 @@ def run_ours(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": CLIP_S / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"1 clip x 30 s, {MAX_NEW} new tokens, C log-mel + numpy Whisper fp32 ({dt:.1f} s)",
-                                    "tokens_match_gpu": bool(ref[0] == toks[0]) if args.precision == "fp32" else None}
+                                    "tokens_match_gpu": bool(ref[0] == toks[0][0]) if args.precision == "fp32" else None}
         print(json.dumps(line), flush=True)
-    m.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -285,11 +316,13 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("WB_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("WB_BENCH_IN_FLIGHT", "4")),
+                    help="independent batches of --batch clips in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

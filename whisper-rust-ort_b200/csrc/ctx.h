@@ -95,7 +95,7 @@ struct DecBufs {
     DevBuf<int> xcount;                // arrival counters [B][H]
     DevBuf<float> amax_buf;            // fused arg-max partials of the vocabulary projection
     float* amax_val = nullptr; int* amax_idx = nullptr; int* amax_state = nullptr; int amax_ctas = 0;
-    bool fuse_argmax = true, want_logits = false;
+    bool fuse_argmax = true, want_logits = false, fuse_chain = false;
     DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
     int T_max = 0;
     // whole-decode CUDA graph (all steps), rebuilt when the key changes

@@ -30,15 +30,26 @@ __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+static thread_local int g_cluster = 0;         // cluster size for the next launch_k (0 = none)
 template <typename... KArgs, typename... Args>
 void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (g_cluster > 0) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)g_cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+        g_cluster = 0;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
@@ -629,16 +640,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 constexpr int MM_THREADS = 256;
 
-template <int RW, int KS, int NCH>       // NCH = 32-wide k chunks per warp = K / KS / 32
-__global__ void __launch_bounds__(MM_THREADS, 1)
-skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
-                  const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                  int act, const float* residual, float* Y,
-                  // fused masked arg-max over the N rows (vocabulary projection, KS == 1 only): per-CTA partials
-                  const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
-                  float* __restrict__ amax_val, int* __restrict__ amax_idx) {
+// How a stage waits for its input: SYNC_PDL = the predecessor KERNEL (griddepcontrol), SYNC_CLUSTER =
+// the predecessor STAGE of the same kernel, run by the other CTAs of this thread-block cluster.
+enum { SYNC_PDL = 0, SYNC_CLUSTER = 1 };
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int MODE> __device__ __forceinline__ void stage_sync() {
+    if (MODE == SYNC_PDL) pdl_sync(); else cluster_barrier();
+}
+
+// One skinny GEMM "stage" executed by CTA `cta` of `ncta` cooperating CTAs (a whole grid, or one
+// thread-block cluster).  Activations are exchanged through global memory (L2): loads use ld.cg so a
+// value written by another CTA before the barrier is never served from a stale L1 line.
+template <int RW, int KS, int NCH, int MODE>       // NCH = 32-wide k chunks per warp = K / KS / 32
+__device__ __forceinline__ void
+mma_stage(unsigned char* mm_smem, int cta, int ncta,
+          const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
+          const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+          int act, const float* residual, float* Y,
+          // fused masked arg-max over the N rows (vocabulary projection, KS == 1 only): per-CTA partials
+          const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
+          float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     static_assert(RW * KS == 8, "8 warps");
-    extern __shared__ __align__(16) unsigned char mm_smem[];
     const int xstride = K * 2 + 64;                                  // bytes per activation row
     unsigned char* xs = mm_smem;                                     // [32][K] bf16 (padded rows)
     float* part = reinterpret_cast<float*>(mm_smem + 32 * xstride);  // [KS][RW*16][33]
@@ -654,7 +679,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
     for (int i = 0; i < 8; ++i) { bestv[i] = -INFINITY; besti[i] = 0x7fffffff; }
     const unsigned* sup = nullptr;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < n_tiles; tile += ncta) {
         const int n0 = tile * rows_cta + rt * 16;
         // ---- weight fragments for this warp: every load in flight before anything else ----
         uint4 wa[NCH], wb[NCH];
@@ -669,7 +694,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
             }
         }
         if (!synced) {
-            pdl_sync();
+            stage_sync<MODE>();
             synced = true;
             if (amax_val) sup = (state[0] - (state[1] - 1) == 0) ? sup_first : sup_base;   // first generated token?
             // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
@@ -682,7 +707,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = i * 128 + lane * 4;
-                        xv[rr][i] = (bb < B && c < kc) ? *reinterpret_cast<const float4*>(X + (size_t)bb * K + k0 + c)
+                        xv[rr][i] = (bb < B && c < kc) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)bb * K + k0 + c))
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
@@ -786,7 +811,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                     for (int k2 = 0; k2 < KS; ++k2) v += part[((size_t)k2 * rows_cta + nl) * 33 + b];
                     if (bias) v += bias[n];
                     if (act == 1) v = gelu_erf(v);
-                    if (residual) v += residual[(size_t)b * N + n];
+                    if (residual) v += __ldcg(residual + (size_t)b * N + n);
                     Y[(size_t)b * N + n] = v;
                 }
             }
@@ -808,7 +833,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                     if (bias && n < N) v += bias[n];
                     if (act == 1) v = gelu_erf(v);
                     if (b < B && n < N) {
-                        if (residual) v += residual[(size_t)b * N + n];
+                        if (residual) v += __ldcg(residual + (size_t)b * N + n);
                         if (Y) Y[(size_t)b * N + n] = v;
                     }
                     if (amax_val && ok[i >> 1]) {           // strict '>' in increasing n: lowest index wins ties, NaN never
@@ -850,9 +875,62 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                 const int oi = si[w * 32 + tid];
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            amax_val[blockIdx.x * 32 + tid] = bv;
-            amax_idx[blockIdx.x * 32 + tid] = bi;
+            amax_val[cta * 32 + tid] = bv;
+            amax_idx[cta * 32 + tid] = bi;
         }
+    }
+    if (!synced) stage_sync<MODE>();                // a CTA without tiles still takes part in the barrier
+}
+
+template <int RW, int KS, int NCH>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
+                  const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  int act, const float* residual, float* Y,
+                  const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
+                  float* __restrict__ amax_val, int* __restrict__ amax_idx) {
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    mma_stage<RW, KS, NCH, SYNC_PDL>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
+                                     state, sup_base, sup_first, amax_val, amax_idx);
+}
+
+// ---- cluster-chained decoder stages (bf16 build, d_model 512 / ffn 2048) ----
+// The GEMMs between two attention kernels form a chain with grid-wide dependencies (each needs the
+// full rows its predecessor produced).  Instead of one launch per GEMM, one thread-block cluster
+// of CL CTAs runs the whole chain: every CTA computes its share of a stage's output rows, the
+// hardware cluster barrier (release/acquire) replaces the kernel boundary, and the weights of the
+// next stage are already in flight when the barrier is reached.
+struct ChainStage {
+    const float* X; const bf16* W; const float* bias; const float* ln_w; const float* ln_b; const float* residual; float* Y;
+    int N, K, act;
+};
+struct ChainArgs {
+    ChainStage st[4];
+    int n_stages, B;
+};
+
+__device__ __forceinline__ int cluster_rank() { int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ int cluster_size() { int r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+
+template <int MODE>
+__device__ __forceinline__ void chain_stage(unsigned char* smem, int cta, int ncta, const ChainStage& s, int B) {
+    if (s.K == 512) {
+        if (s.N > 1024) mma_stage<4, 2, 8, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
+        else mma_stage<2, 4, 4, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
+    } else {    // K == 2048
+        mma_stage<2, 4, 16, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(MM_THREADS, 1)
+dec_chain_kernel(const ChainArgs a) {
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    const int cta = cluster_rank(), ncta = cluster_size();
+    chain_stage<SYNC_PDL>(mm_smem, cta, ncta, a.st[0], a.B);
+#pragma unroll 1
+    for (int i = 1; i < a.n_stages; ++i) {
+        __syncthreads();                            // this CTA is done with the shared tile of the previous stage
+        chain_stage<SYNC_CLUSTER>(mm_smem, cta, ncta, a.st[i], a.B);
     }
 }
 
@@ -900,6 +978,21 @@ void skinny_mma_set_attrs() {       // once per process, outside any stream capt
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+}
+
+constexpr int CHAIN_CLUSTER = 8;
+constexpr size_t CHAIN_SMEM = 32 * (2048 * 2 + 64) + sizeof(float) * 8 * 16 * 33;
+
+ChainStage chain_stage_of(const float* X, const LinearW& L, const LNW* ln, int act, const float* residual, float* Y) {
+    ChainStage c{};
+    c.X = X; c.W = reinterpret_cast<const bf16*>(L.w); c.bias = L.b; c.ln_w = ln ? ln->w : nullptr; c.ln_b = ln ? ln->b : nullptr;
+    c.residual = residual; c.Y = Y; c.N = L.out; c.K = L.in; c.act = act;
+    return c;
+}
+void launch_chain(wb_ctx* ctx, cudaStream_t st, const ChainArgs& a) {
+    g_cluster = CHAIN_CLUSTER;
+    launch_k(dec_chain_kernel, dim3(CHAIN_CLUSTER), dim3(MM_THREADS), CHAIN_SMEM, st, ctx->dec.pdl, a);
 }
 inline bool skinny_mma(wb_ctx*, const float*, int, int, const float*, int, const float*, const float*, const float*, int,
                        const float*, float*) { return false; }     // fp32 validation build stays on the SIMT kernel
@@ -964,19 +1057,41 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
     const bool pdl = D.pdl;
     // the first kernel of a chain follows memcpy nodes, not a kernel: plain launch
     launch_k(embed_kernel<WT>, dim3(B), dim3(128), 0, st, pdl && !first, (const int*)state, prompt_dev, (const int*)cur_tok, (const WT*)w.embed, (const float*)w.dec_pos, x, d); ++n;
+    // bf16 build at whisper-base widths: the GEMM chains between the attention kernels run as
+    // cluster-chained stages (dec_chain_kernel): 4 launches per layer instead of 8.
+    const bool chain = sizeof(WT) == 2 && D.fuse_chain && B <= 32 && d == 512 && c.ffn_dim == 2048;
     for (int l = 0; l < c.dec_layers; ++l) {
         const DecLayerW& L = w.dec[l];
         WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + ((size_t)l * c.max_batch + b0) * D.T_max * 2 * d;
         const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + ((size_t)l * c.max_batch + b0) * Tk * 2 * d;
-        skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, qkv); ++n;                              // K3c
+        if (!chain || l == 0) { skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, qkv); ++n; }              // K3c
         launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)qkv, skv, att, d, D.T_max); ++n;   // K3d
-        skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;                                      // K3f
-        skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
+        if (chain) {
+            ChainArgs a{};
+            a.B = B; a.n_stages = 2;
+            a.st[0] = chain_stage_of(att, L.o, nullptr, 0, x, x);                                             // K3f
+            a.st[1] = chain_stage_of(x, L.cq, &L.ln2, 0, nullptr, q);
+            launch_chain(ctx, st, a); ++n;
+        } else {
+            skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;
+            skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
+        }
         launch_k(cross_attn_kernel<WT>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, (const float*)q, ckv, att,
                  D.xscratch.p + (size_t)b0 * H * XSPLIT * 66, D.xcount.p + (size_t)b0 * H, d, Tk); ++n;   // K3e
-        skinny<WT>(ctx, att, B, d, L.co, nullptr, 0, x, x); ++n;
-        skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, ffn); ++n;                               // K3g
-        skinny<WT>(ctx, ffn, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
+        if (chain) {
+            ChainArgs a{};
+            a.B = B;
+            a.st[0] = chain_stage_of(att, L.co, nullptr, 0, x, x);
+            a.st[1] = chain_stage_of(x, L.fc1, &L.ln3, 1, nullptr, ffn);                                      // K3g
+            a.st[2] = chain_stage_of(ffn, L.fc2, nullptr, 0, x, x);
+            a.n_stages = 3;
+            if (l + 1 < c.dec_layers) { a.st[3] = chain_stage_of(x, w.dec[l + 1].qkv, &w.dec[l + 1].ln1, 0, nullptr, qkv); a.n_stages = 4; }
+            launch_chain(ctx, st, a); ++n;
+        } else {
+            skinny<WT>(ctx, att, B, d, L.co, nullptr, 0, x, x); ++n;
+            skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, ffn); ++n;
+            skinny<WT>(ctx, ffn, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
+        }
     }
     if (with_logits) {                                                                               // K3h
         LinearW dummy;
@@ -1124,6 +1239,10 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
         }
         return n;
     };
+    // Experimental: cluster-chained GEMM stages (dec_chain_kernel).  Correct, but measured SLOWER on B200
+    // (decode 111 ms vs 61 ms): 8 CTAs serialise the row tiles that 16-32 independent CTAs do in parallel.
+    const char* cenv = getenv("WB_DEC_CHAIN");
+    D.fuse_chain = cenv && cenv[0] == '1';
     const char* fenv = getenv("WB_FUSE_ARGMAX");
     D.fuse_argmax = !(fenv && fenv[0] == '0');
     D.want_logits = p.want_logits;
@@ -1134,7 +1253,8 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     if (use_graph) {
         // The whole decode (every step of every layer) is one CUDA graph: kernels read the step
         // index from device memory, so the captured sequence is replayable; one launch per decode.
-        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0, c.precision * 16 + nsplit * 2 + (D.pdl ? 1 : 0)};
+        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
+                            c.precision * 64 + nsplit * 8 + (D.pdl ? 4 : 0) + (D.fuse_chain ? 2 : 0) + (D.fuse_argmax ? 1 : 0)};
         bool same = D.graph_exec != nullptr;
         for (int i = 0; i < 6; ++i) same = same && D.g_key[i] == key[i];
         if (!same) {
