@@ -1,0 +1,53 @@
+"""GPU: whisper-large-v3 *widths* (128 mel bins, d=1280, 20 heads, ffn 5120, vocab 51866) on a
+2+2-layer model (BASELINE.json configs[4] shapes; depth cut so the CPU oracle finishes in
+seconds): every kernel must be shape-generic, not hard-wired to whisper-base."""
+import numpy as np
+import pytest
+
+import whisper_ref as wr
+
+pytestmark = pytest.mark.gpu
+
+
+def wide_cfg(wb, precision):
+    cfg = wb.default_cfg("large-v3", precision=precision, max_batch=2, max_chunks=2)
+    cfg.enc_layers = 2
+    cfg.dec_layers = 2
+    return cfg
+
+
+@pytest.fixture(scope="module")
+def oracle(wb):
+    mc = wb.binding.model_cfg_of(wide_cfg(wb, wb.WB_PREC_FP32))
+    return wr.WhisperRef(mc, wb.weights.generate(mc, 0))
+
+
+@pytest.fixture(scope="module")
+def mel():
+    rng = np.random.default_rng(3)
+    return (rng.normal(0.0, 0.5, (2, 128, 3000))).astype(np.float32)
+
+
+def test_large_v3_widths_fp32_parity(wb, oracle, mel):
+    m = wb.Whisper(wide_cfg(wb, wb.WB_PREC_FP32))
+    enc = m.encode(mel)
+    ref = oracle.encode(mel)
+    assert np.abs(enc - ref).max() <= 2e-4
+    prompt = [50258, 50259, 50360, 50364]
+    toks, lg = m.greedy_decode(2, prompt, 6, 50257, want_logits=True)
+    rt, rl = oracle.greedy(enc, prompt, 6, 50257, return_logits=True)
+    assert toks == rt
+    assert np.abs(lg - np.stack(rl, 1)).max() <= 2e-4
+    m.close()
+
+
+def test_large_v3_widths_bf16_within_tolerance(wb, oracle, mel):
+    m = wb.Whisper(wide_cfg(wb, wb.WB_PREC_BF16))
+    enc = m.encode(mel)
+    ref = oracle.encode(mel)
+    assert np.linalg.norm(enc - ref) / np.linalg.norm(ref) <= 2e-2
+    toks = m.greedy_decode(2, [50258, 50259, 50360, 50364], 6, 50257)
+    assert all(len(t) == 10 for t in toks)
+    with pytest.raises(wb.WbError, match="80-bin"):
+        m.log_mel([np.zeros(16000, np.float32)])          # the reference has no 128-bin frontend
+    m.close()

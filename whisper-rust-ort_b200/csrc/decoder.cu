@@ -948,11 +948,14 @@ void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W,
 }
 
 // bf16 build: route a skinny GEMM to the tensor-core kernel when its shape has an instantiation.
-inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
-                       const float* lb, int act, const float* residual, float* Y) {
+inline bool skinny_mma_enabled() {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("WB_DEC_MMA"); enabled = !(e && e[0] == '0'); }
-    if (!enabled || B > 32 || (lw && K > 512)) return false;
+    return enabled != 0;
+}
+inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
+                       const float* lb, int act, const float* residual, float* Y) {
+    if (!skinny_mma_enabled() || B > 32 || (lw && K > 512)) return false;
     if (N >= 8192) {                               // vocabulary projection: 128 rows per CTA pass, grid-stride
         const bool fa = ctx->dec.amax_state != nullptr;
         if (K == 512) { skinny_mma_launch<8, 1, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
@@ -1059,7 +1062,7 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
     launch_k(embed_kernel<WT>, dim3(B), dim3(128), 0, st, pdl && !first, (const int*)state, prompt_dev, (const int*)cur_tok, (const WT*)w.embed, (const float*)w.dec_pos, x, d); ++n;
     // bf16 build at whisper-base widths: the GEMM chains between the attention kernels run as
     // cluster-chained stages (dec_chain_kernel): 4 launches per layer instead of 8.
-    const bool chain = sizeof(WT) == 2 && D.fuse_chain && B <= 32 && d == 512 && c.ffn_dim == 2048;
+    const bool chain = sizeof(WT) == 2 && D.fuse_chain && skinny_mma_enabled() && B <= 32 && d == 512 && c.ffn_dim == 2048;
     for (int l = 0; l < c.dec_layers; ++l) {
         const DecLayerW& L = w.dec[l];
         WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + ((size_t)l * c.max_batch + b0) * D.T_max * 2 * d;
@@ -1097,7 +1100,7 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
         LinearW dummy;
         // bf16 build: arg-max partials are produced by the vocabulary projection itself (no logits round trip
         // unless the caller asked for logits); fp32 build: separate full arg-max over the logits.
-        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax;
+        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && (d == 512 || d == 128);   // widths with an mma vocab kernel
         D.amax_state = fuse ? state : nullptr;
         const int slice = (int)((long long)b0 * 4 / c.max_batch);           // up to 4 concurrent sub-batch chains
         D.amax_val = D.amax_buf.p + (size_t)slice * 64 * ctx->sm_count;      // per-chain slice: [ctas][32] val | idx
