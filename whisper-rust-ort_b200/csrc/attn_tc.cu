@@ -5,7 +5,8 @@
 //                    P -> bf16 -> shared memory in the UMMA K-major swizzled layout
 //   O_j = P.V        tcgen05.mma 128x64x128 (V consumed MN-major straight from the TMA tile) -> TMEM
 //   O += O_j         in registers (tcgen05.ld), rescaled by exp(m_old - m_new)
-// K/V tiles are double buffered by TMA; the PV MMA of block j overlaps the softmax of block j+1.
+// K tiles are double buffered by TMA, V single; two CTAs share an SM (96 KB smem, 256 TMEM columns each),
+// so the MMAs of one overlap the softmax of the other, and PV of block j overlaps the softmax of block j+1.
 // Replaces the Softmax(QK^T)V sub-graphs ONNX Runtime executes inside encoder.run
 // (/root/reference/src/main.rs:703); same math as oracle/whisper_ref.py::_attend.
 #include <cuda.h>
@@ -18,7 +19,7 @@ constexpr int AQ = 128, AK = 128, HD = 64;
 constexpr int ATT_THREADS = 160;                       // warp 0: TMA + MMA issue; warps 1-4: softmax / epilogue
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;          // one [128 x 64] bf16 tile, 128-byte rows
 constexpr uint32_t ATT_TMEM_COLS = 256;                // S: [0,128)  O_j: [128,192)
-constexpr size_t ATT_SMEM = 7 * TILE_BYTES + 1024 + 128;   // Q, K[2], V[2], P[2 halves]
+constexpr size_t ATT_SMEM = 6 * TILE_BYTES + 1024 + 128;   // Q, K[2], V, P[2 halves]: 97 KB -> two CTAs per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -94,23 +95,24 @@ __device__ __forceinline__ constexpr uint32_t idesc_of(int n, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int d, int H, int n_qb) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* sQ = smem;
     uint8_t* sK = smem + TILE_BYTES;                   // 2 buffers
-    uint8_t* sV = smem + 3 * TILE_BYTES;               // 2 buffers
-    uint8_t* sP = smem + 5 * TILE_BYTES;               // 2 halves of 64 keys
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE_BYTES);
+    uint8_t* sV = smem + 3 * TILE_BYTES;               // 1 buffer
+    uint8_t* sP = smem + 4 * TILE_BYTES;               // 2 halves of 64 keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
     uint64_t* bar_q = bars;            // 1
-    uint64_t* bar_kv = bars + 1;       // 2
-    uint64_t* bar_kvfree = bars + 3;   // 2
+    uint64_t* bar_k = bars + 1;        // 2: K tile landed
+    uint64_t* bar_kfree = bars + 3;    // 2: S MMA that read the K tile retired
     uint64_t* bar_s = bars + 5;
     uint64_t* bar_p = bars + 6;
-    uint64_t* bar_o = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bar_o = bars + 7;        // O_j ready == V tile free
+    uint64_t* bar_v = bars + 8;        // V tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x % n_qb, h = (blockIdx.x / n_qb) % H, b = blockIdx.x / (n_qb * H);
@@ -120,9 +122,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQKV)) : "memory");
             mbar_init(bar_q, 1);
-            mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
-            mbar_init(&bar_kvfree[0], 1); mbar_init(&bar_kvfree[1], 1);
-            mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+            mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
+            mbar_init(&bar_kfree[0], 1); mbar_init(&bar_kfree[1], 1);
+            mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_v, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -141,37 +143,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             const uint32_t idesc_s = idesc_of(128, 0), idesc_o = idesc_of(64, 1);
             mbar_expect_tx(bar_q, TILE_BYTES);
             tma_load_3d(&tmQKV, bar_q, sQ, h * HD, qb * AQ, b);
-            mbar_expect_tx(&bar_kv[0], 2 * TILE_BYTES);
-            tma_load_3d(&tmQKV, &bar_kv[0], sK, d + h * HD, 0, b);
-            tma_load_3d(&tmQKV, &bar_kv[0], sV, 2 * d + h * HD, 0, b);
+            mbar_expect_tx(&bar_k[0], TILE_BYTES);
+            tma_load_3d(&tmQKV, &bar_k[0], sK, d + h * HD, 0, b);
+            mbar_expect_tx(bar_v, TILE_BYTES);
+            tma_load_3d(&tmQKV, bar_v, sV, 2 * d + h * HD, 0, b);
             mbar_wait(bar_q, 0);
             const uint64_t dq = make_desc_sw128(smem_u32(sQ));
+            const uint64_t dv = make_desc_sw128(smem_u32(sV));
             for (int j = 0; j < n_kb; ++j) {
                 const int s = j & 1;
-                mbar_wait(&bar_kv[s], (uint32_t)((j >> 1) & 1));
+                mbar_wait(&bar_k[s], (uint32_t)((j >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t dk = make_desc_sw128(smem_u32(sK + s * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)                        // S = Q K^T, K dim = head_dim
                     umma(tS, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
                 umma_commit(bar_s);
-                if (j + 1 < n_kb) {                                      // prefetch K/V block j+1
+                umma_commit(&bar_kfree[s]);
+                if (j + 1 < n_kb) {                                      // prefetch K block j+1
                     const int s1 = (j + 1) & 1;
-                    if (j >= 1) mbar_wait(&bar_kvfree[s1], (uint32_t)(((j - 1) >> 1) & 1));
-                    mbar_expect_tx(&bar_kv[s1], 2 * TILE_BYTES);
-                    tma_load_3d(&tmQKV, &bar_kv[s1], sK + s1 * TILE_BYTES, d + h * HD, (j + 1) * AK, b);
-                    tma_load_3d(&tmQKV, &bar_kv[s1], sV + s1 * TILE_BYTES, 2 * d + h * HD, (j + 1) * AK, b);
+                    if (j >= 1) mbar_wait(&bar_kfree[s1], (uint32_t)(((j - 1) >> 1) & 1));
+                    mbar_expect_tx(&bar_k[s1], TILE_BYTES);
+                    tma_load_3d(&tmQKV, &bar_k[s1], sK + s1 * TILE_BYTES, d + h * HD, (j + 1) * AK, b);
                 }
                 mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, O_{j-1} consumed
+                mbar_wait(bar_v, (uint32_t)(j & 1));                     // V_j landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t dv = make_desc_sw128(smem_u32(sV + s * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < AK / 16; ++k) {                      // O_j = P_j V_j, K dim = keys
                     const uint64_t dp = make_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES)) + (uint64_t)((k & 3) * 2);
                     umma(tO, dp, dv + (uint64_t)(k * 128), idesc_o, (uint32_t)(k != 0));   // 16 keys = 16 rows x 128 B
                 }
                 umma_commit(bar_o);
-                umma_commit(&bar_kvfree[s]);
+                if (j + 1 < n_kb) {                                      // V tile is free once PV_j retired
+                    mbar_wait(bar_o, (uint32_t)(j & 1));
+                    mbar_expect_tx(bar_v, TILE_BYTES);
+                    tma_load_3d(&tmQKV, bar_v, sV, 2 * d + h * HD, (j + 1) * AK, b);
+                }
             }
         }
     } else {

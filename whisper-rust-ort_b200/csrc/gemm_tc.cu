@@ -17,7 +17,7 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 5, UMMA_K = 16;
-constexpr int TC_THREADS = 192;                              // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int TC_THREADS = 320;                              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
 constexpr uint32_t STAGE_A = BM * BK * 2, STAGE_B = BN * BK * 2;
 constexpr uint32_t TMEM_COLS = 256;                          // 2 accumulators x 128 fp32 columns
 constexpr size_t TC_SMEM = (size_t)STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 256 /*barriers*/;
@@ -108,6 +108,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-z * z);          // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -127,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -185,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ===== epilogue: TMEM -> registers -> bias/GELU/pos/residual -> global =====
         const int q = warp & 3;                                          // TMEM lane quadrant this warp may access
+        const int chalf = (warp - 2) >> 2;                               // which 64-column half of the tile
         const int row_in_tile = q * 32 + lane;
         int it = 0;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
@@ -197,18 +208,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = gm < a.M;
             const long long crow = (long long)z * a.sC + (long long)gm * a.ldc;
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+            for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(q * 32) << 16), r);
                 const int gn0 = nb * BN + ch * 32;
                 if (row_ok) {
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(r[j]);
-                        if (a.bias) x += __ldg(a.bias + gn0 + j);
-                        if (a.act == 1) x = gelu_erf(x);
-                        v[j] = x;
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (a.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + gn0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(bp + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
+                    }
+                    if (a.act == 1) {
+                        // bf16 outputs: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 rounding);
+                        // f32 outputs keep the exact erff
+                        if (a.tc == WB_BF16) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        }
                     }
                     if (a.rowadd) {
                         const float4* p = reinterpret_cast<const float4*>(a.rowadd + (long long)gm * a.ld_rowadd + gn0);
@@ -239,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&tempty[acc]);                                    // 128 arrivals release the accumulator
+            mbar_arrive(&tempty[acc]);                                    // 256 arrivals release the accumulator
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
