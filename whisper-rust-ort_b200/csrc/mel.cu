@@ -16,8 +16,8 @@
 namespace {
 
 constexpr int FPT = 32;                       // frames per tile (one CTA)
-constexpr int MEL_THREADS = 160;              // 8 FFT groups x 20 threads
-constexpr int FFTS = 8;                       // complex FFTs per pass = 16 frames
+constexpr int MEL_WARPS = 8;
+constexpr int MEL_THREADS = MEL_WARPS * 32;   // each warp owns 2 of the tile's 16 frame pairs
 constexpr int SPAN = (FPT - 1) * 160 + 400;   // padded samples a tile touches
 constexpr int SCR = 420;                      // 20 x 21 (padded) complex per FFT
 constexpr int POW_LD = 204;
@@ -44,22 +44,27 @@ __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-__global__ void __launch_bounds__(MEL_THREADS)
+// K1a.  One CTA = 32 frames of one file.  The PCM span is staged once (128-bit loads for interior
+// tiles); after that every warp works alone on its frame pairs — two real frames packed into one
+// complex 400-point FFT (20 lanes x 20-point DFT, twiddle, transpose through the warp's scratch,
+// 20-point DFT), Hermitian split into two power spectra, sparse mel, log10 — with warp-level
+// synchronisation only: no CTA barrier inside the frame loop.
+__global__ void __launch_bounds__(MEL_THREADS, 3)
 logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ file_off,
                   const int64_t* __restrict__ frame_off, const int* __restrict__ tile_off,
                   int n_files, const MelTables* __restrict__ tab, float* __restrict__ raw,
                   int* __restrict__ fmax) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* s_pcm = smem;                                       // SPAN
     float* s_win = s_pcm + SPAN;                               // 400
     float2* s_tw = reinterpret_cast<float2*>(s_win + 400);     // 400
-    float2* s_scr = s_tw + 400;                                // FFTS * SCR
-    float* s_pow = reinterpret_cast<float*>(s_scr + FFTS * SCR);  // 16 * POW_LD
-    float* s_fbw = s_pow + 16 * POW_LD;                        // 400
+    float* s_fbw = reinterpret_cast<float*>(s_tw + 400);       // 400
     int* s_fbi = reinterpret_cast<int*>(s_fbw + 400);          // start[80], len[80], off[80]
-    __shared__ float s_red[8];
+    float2* s_scr = reinterpret_cast<float2*>(s_fbi + 240);    // MEL_WARPS * SCR
+    float* s_pow = reinterpret_cast<float*>(s_scr + MEL_WARPS * SCR);   // MEL_WARPS * 2 * POW_LD
+    __shared__ float s_red[MEL_WARPS];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // tile -> file (binary search over the tile prefix sums)
     int lo = 0, hi = n_files - 1;
     const int tile = blockIdx.x;
@@ -79,67 +84,78 @@ logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ fil
         s_fbw[i] = tab->fb_w[i];
     }
     for (int i = tid; i < 240; i += MEL_THREADS) s_fbi[i] = tab->fb_idx[i];
-    for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j] = padded_sample(x, N, f0 * 160 + j);
+    {
+        const int64_t p0 = f0 * 160;                             // first padded sample of the tile
+        const float* src = x + (p0 - 200);
+        const bool interior = p0 >= 200 && p0 - 200 + SPAN <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        if (interior) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(s_pcm);
+            for (int j = tid; j < SPAN / 4; j += MEL_THREADS) d4[j] = __ldg(s4 + j);
+        } else {
+            for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j] = padded_sample(x, N, p0 + j);
+        }
+    }
     __syncthreads();
 
-    const int g = tid / 20, r = tid % 20;      // FFT group, row/col index
+    float2* scr = s_scr + warp * SCR;
+    float* pw = s_pow + warp * 2 * POW_LD;
     float tmax = -INFINITY;
-
-    for (int pass = 0; pass < FPT / 16; ++pass) {
-        // ---- step 1: 20-pt DFT over n1 for column n2 = r, twiddle, scatter ----
-        {
-            const int fa = pass * 16 + 2 * g;             // tile-local frame A (B = A + 1)
+    for (int pair = warp; pair < FPT / 2; pair += MEL_WARPS) {
+        const int fa = 2 * pair;                                 // tile-local frame A (B = A + 1)
+        // ---- step 1: 20-pt DFT over n1 for column n2 = lane, twiddle, scatter ----
+        if (lane < 20) {
             const float* pa = s_pcm + fa * 160;
             c32 v[20];
 #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
-                int i = 20 * n1 + r;
+                int i = 20 * n1 + lane;
                 float w = s_win[i];
                 v[n1] = {pa[i] * w, pa[160 + i] * w};
             }
             dft20(v);
-            float2* scr = s_scr + g * SCR;
 #pragma unroll
             for (int k1 = 0; k1 < 20; ++k1) {
-                float2 t = s_tw[r * k1];
+                float2 t = s_tw[lane * k1];
                 c32 z = cmul(v[k1], c32{t.x, t.y});
-                scr[k1 * 21 + r] = make_float2(z.x, z.y);
+                scr[k1 * 21 + lane] = make_float2(z.x, z.y);
             }
         }
-        __syncthreads();
-        // ---- step 2: 20-pt DFT over n2 for row k1 = r ----
+        __syncwarp();
+        // ---- step 2: 20-pt DFT over n2 for row k1 = lane ----
         {
-            float2* scr = s_scr + g * SCR;
             c32 v[20];
+            if (lane < 20) {
 #pragma unroll
-            for (int n2 = 0; n2 < 20; ++n2) {
-                float2 t = scr[r * 21 + n2];
-                v[n2] = {t.x, t.y};
+                for (int n2 = 0; n2 < 20; ++n2) {
+                    float2 t = scr[lane * 21 + n2];
+                    v[n2] = {t.x, t.y};
+                }
+                dft20(v);
             }
-            dft20(v);
-            __syncthreads();                               // everyone has read its row
+            __syncwarp();                                        // every row has been read
+            if (lane < 20) {
 #pragma unroll
-            for (int k2 = 0; k2 < 20; ++k2) scr[r + 20 * k2] = make_float2(v[k2].x, v[k2].y);
+                for (int k2 = 0; k2 < 20; ++k2) scr[lane + 20 * k2] = make_float2(v[k2].x, v[k2].y);
+            }
         }
-        __syncthreads();
+        __syncwarp();
         // ---- power spectra of both packed frames, k = 0..200 ----
-        for (int it = tid; it < FFTS * 201; it += MEL_THREADS) {
-            int gg = it / 201, k = it - gg * 201;
-            const float2* scr = s_scr + gg * SCR;
+        for (int k = lane; k < 201; k += 32) {
             float2 z = scr[k];
             float2 c = scr[k == 0 ? 0 : 400 - k];
             float ar = z.x + c.x, ai = z.y - c.y;          // 2*A[k]
             float br = z.x - c.x, bi = z.y + c.y;          // 2i*B[k]
-            s_pow[(2 * gg) * POW_LD + k] = 0.25f * (ar * ar + ai * ai);
-            s_pow[(2 * gg + 1) * POW_LD + k] = 0.25f * (br * br + bi * bi);
+            pw[k] = 0.25f * (ar * ar + ai * ai);
+            pw[POW_LD + k] = 0.25f * (br * br + bi * bi);
         }
-        __syncthreads();
+        __syncwarp();
         // ---- mel filterbank (sequential f32 sum in k order, main.rs:484-490), log10 ----
-        const int64_t fbase = f0 + pass * 16;
-        for (int it = tid; it < 16 * 80; it += MEL_THREADS) {
+        const int64_t fbase = f0 + fa;
+        for (int it = lane; it < 2 * 80; it += 32) {
             int fl = it / 80, m = it - fl * 80;
             if (fbase + fl < nf) {
-                const float* p = s_pow + fl * POW_LD + s_fbi[m];
+                const float* p = pw + fl * POW_LD + s_fbi[m];
                 const float* w = s_fbw + s_fbi[160 + m];
                 int len = s_fbi[80 + m];
                 float e = 0.0f;
@@ -149,16 +165,16 @@ logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ fil
                 tmax = fmaxf(tmax, lv);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     // ---- block max -> one atomic per tile ----
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if ((tid & 31) == 0) s_red[tid >> 5] = tmax;
+    if (lane == 0) s_red[warp] = tmax;
     __syncthreads();
     if (tid == 0) {
         float m = s_red[0];
-        for (int w = 1; w < MEL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+        for (int w = 1; w < MEL_WARPS; ++w) m = fmaxf(m, s_red[w]);
         if (m > -INFINITY) atomic_max_float(fmax + file, m);
     }
 }
@@ -231,7 +247,7 @@ __global__ void mel_transpose_in_kernel(const float* __restrict__ in, T* __restr
     }
 }
 
-constexpr size_t MEL_SMEM = sizeof(float) * (SPAN + 400 + 800 + 2 * FFTS * SCR + 16 * POW_LD + 400 + 240);
+constexpr size_t MEL_SMEM = sizeof(float) * (SPAN + 400 + 800 + 400 + 240 + 2 * MEL_WARPS * SCR + MEL_WARPS * 2 * POW_LD);
 
 }  // namespace
 
