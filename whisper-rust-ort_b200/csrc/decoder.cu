@@ -1022,6 +1022,7 @@ void skinny(wb_ctx* ctx, const float* X, int B, int K, const LinearW& L, const L
     const float* lb = ln ? ln->b : nullptr;
     const float* bias = (L.b && !W_override) ? L.b : nullptr;
     if (skinny_mma(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y)) { CUDA_CHECK(cudaGetLastError()); return; }
+    WB_REQUIRE(Y != nullptr, WB_EINVAL, "skinny gemm: no output buffer on the SIMT path (N=%d K=%d)", N, K);
     // rows per warp: enough CTAs to cover the chip for the per-layer GEMMs, register blocking for the vocab one
     if (N >= 8192) skinny_launch<WT, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
     else if (N >= 1024) skinny_launch<WT, 2>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
@@ -1100,7 +1101,7 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
         LinearW dummy;
         // bf16 build: arg-max partials are produced by the vocabulary projection itself (no logits round trip
         // unless the caller asked for logits); fp32 build: separate full arg-max over the logits.
-        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && (d == 512 || d == 128);   // widths with an mma vocab kernel
+        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && c.vocab >= 8192 && (d == 512 || d == 128);   // shapes with an mma vocab kernel
         D.amax_state = fuse ? state : nullptr;
         const int slice = (int)((long long)b0 * 4 / c.max_batch);           // up to 4 concurrent sub-batch chains
         D.amax_val = D.amax_buf.p + (size_t)slice * 64 * ctx->sm_count;      // per-chain slice: [ctas][32] val | idx
