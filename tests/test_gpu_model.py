@@ -91,6 +91,27 @@ def test_eot_stops_a_sequence_and_max_new_quirks(base, oracle, clips):
         assert [len(s) for s in out] == [5, 5] and out == oracle.greedy(enc, prompt, mn, EOT)
 
 
+def test_early_exit_when_every_sequence_hit_eot(base, oracle, clips):
+    """The device loop stops at a segment boundary once all sequences emitted EOT (the host looks at one
+    mapped int per 16 tokens, never per token); outputs stay those of main.rs:753-829."""
+    _, mel = clips
+    enc = base.encode(mel[:1])
+    prompt = [50258, 50259, 50359, 50363]
+    free = base.greedy_decode(1, prompt, 40, EOT)
+    assert base.timing()["decode_steps"] == len(prompt) + 40 - 1
+    first = free[0][len(prompt)]
+    got = base.greedy_decode(1, prompt, 40, first)                  # "eot" = the first generated token
+    assert got == oracle.greedy(enc, prompt, 40, first) == [prompt + [first]]
+    assert base.timing()["decode_steps"] == len(prompt) - 1 + 16     # prefix + one segment, then stop
+    # a batch only stops when ALL of its sequences are done
+    base.encode(mel)
+    both = base.greedy_decode(2, prompt, 40, first)
+    ref = oracle.greedy(oracle.encode(mel), prompt, 40, first)
+    assert both == ref
+    if any(len(s) == len(prompt) + 40 for s in ref):
+        assert base.timing()["decode_steps"] == len(prompt) + 40 - 1
+
+
 def test_transcribe_batch_end_to_end(wb, base, oracle):
     x = wb.synth.batch(3, seed=5)
     prompt = [50258, 50259, 50359, 50363]

@@ -193,7 +193,8 @@ void wb_destroy(wb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     weights_free(ctx);
-    if (ctx->dec.graph_exec) cudaGraphExecDestroy(ctx->dec.graph_exec);
+    for (auto& g : ctx->dec.graphs) cudaGraphExecDestroy(g.exec);
+    if (ctx->dec.unfinished_host) cudaFreeHost(ctx->dec.unfinished_host);
     for (int k = 0; k < 3; ++k) {
         if (ctx->dec.side[k]) cudaStreamDestroy(ctx->dec.side[k]);
         if (ctx->dec.ev_join[k]) cudaEventDestroy(ctx->dec.ev_join[k]);

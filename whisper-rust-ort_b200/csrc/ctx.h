@@ -84,6 +84,11 @@ struct EncBufs {
     int attn_group = 4;
     int B_valid = 0;                   // sequences encoded by the last wb_encode
 };
+struct DecGraph {
+    int key[8];
+    cudaGraphExec_t exec;
+    int launches;
+};
 struct DecBufs {
     DevBuf<float> x, qkv, att, q, ffn, logits;
     DevBuf<unsigned char> self_kv;     // [dec_layers][B][T_max][2d] compute dtype
@@ -98,10 +103,10 @@ struct DecBufs {
     bool fuse_argmax = true, want_logits = false, fuse_chain = false;
     DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
     int T_max = 0;
-    // whole-decode CUDA graph (all steps), rebuilt when the key changes
-    cudaGraphExec_t graph_exec = nullptr;
-    int g_key[6] = {-1, -1, -1, -1, -1, -1};
-    int g_launches = 0;
+    // decode-segment CUDA graphs (prompt prefix, SEG generated tokens, remainder), cached by key
+    std::vector<DecGraph> graphs;
+    int* unfinished_host = nullptr;    // mapped: sequences still running, written at the end of a segment
+    int* unfinished_dev = nullptr;
     bool pdl = false;                  // programmatic dependent launch for the decode chain
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // parallel sub-batch chains
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};

@@ -612,6 +612,15 @@ argmax_merge_kernel(const int* __restrict__ state, const float* __restrict__ pva
     }
 }
 
+// End of a segment: how many sequences have not emitted EOT yet (written to mapped host memory).
+__global__ void count_unfinished_kernel(const int* __restrict__ finished, int B, int* __restrict__ out) {
+    int n = 0;
+    for (int b = threadIdx.x; b < B; b += 32) n += finished[b] ? 0 : 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (threadIdx.x == 0) *out = n;
+}
+
 __global__ void advance_kernel(int* state) {
     pdl_sync();
     state[0] += 1;
@@ -1152,6 +1161,8 @@ void decoder_alloc(wb_ctx* ctx) {
         CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_join[k], cudaEventDisableTiming));
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&D.unfinished_host), sizeof(int), cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&D.unfinished_dev), D.unfinished_host, 0));
     const size_t words = ((size_t)c.vocab + 31) / 32;
     D.sup_base.reserve(words);
     D.sup_first.reserve(words);
@@ -1215,7 +1226,9 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     if (nsplit < 1) nsplit = 1;
     if (nsplit > 4) nsplit = 4;
     if (p.want_logits || B < 8 * nsplit) nsplit = 1;
-    auto enqueue_all = [&]() {
+    // enqueue `n_steps` consecutive steps (positions continue from the device-side counter); the last
+    // one is followed by a tiny kernel that publishes how many sequences are still running
+    auto enqueue_steps = [&](int n_steps, bool with_logits, int first_gi) {
         int n = 0;
         if (nsplit > 1) {
             CUDA_CHECK(cudaEventRecord(D.ev_fork, st));
@@ -1225,12 +1238,11 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
             const int lo = (int)((long long)B * k / nsplit), hi = (int)((long long)B * (k + 1) / nsplit);
             cudaStream_t sk = k == 0 ? st : D.side[k - 1];
             int* state_k = D.state.p + 4 * k;
-            for (int s = 0; s < steps; ++s) {
-                const bool with_logits = s >= P - 1;
+            for (int s = 0; s < n_steps; ++s) {
                 n += bf ? enqueue_step<bf16>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0)
                         : enqueue_step<float>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0);
                 if (with_logits && p.want_logits) {
-                    const int gi = s - (P - 1);
+                    const int gi = first_gi + s;
                     CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
                                                  D.logits.p, sizeof(float) * c.vocab, sizeof(float) * c.vocab, B,
                                                  cudaMemcpyDeviceToDevice, st));
@@ -1241,6 +1253,8 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
             CUDA_CHECK(cudaEventRecord(D.ev_join[k - 1], D.side[k - 1]));
             CUDA_CHECK(cudaStreamWaitEvent(st, D.ev_join[k - 1], 0));
         }
+        if (with_logits) { count_unfinished_kernel<<<1, 32, 0, st>>>(D.finished.p, B, D.unfinished_dev); ++n; }
+        CUDA_CHECK(cudaGetLastError());
         return n;
     };
     // Experimental: cluster-chained GEMM stages (dec_chain_kernel).  Correct, but measured SLOWER on B200
@@ -1254,42 +1268,75 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     D.pdl = !(penv && penv[0] == '0') && !p.want_logits;
     const char* genv = getenv("WB_GRAPH");
     const bool use_graph = !p.want_logits && !(genv && genv[0] == '0');
-    if (use_graph) {
-        // The whole decode (every step of every layer) is one CUDA graph: kernels read the step
-        // index from device memory, so the captured sequence is replayable; one launch per decode.
-        const int key[6] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
-                            c.precision * 64 + nsplit * 8 + (D.pdl ? 4 : 0) + (D.fuse_chain ? 2 : 0) + (D.fuse_argmax ? 1 : 0)};
-        bool same = D.graph_exec != nullptr;
-        for (int i = 0; i < 6; ++i) same = same && D.g_key[i] == key[i];
-        if (!same) {
-            if (D.graph_exec) { cudaGraphExecDestroy(D.graph_exec); D.graph_exec = nullptr; }
+    // A segment of steps is one CUDA graph (kernels read the position from device memory, so the
+    // captured sequence is replayable): prompt prefix, then segments of SEG generated tokens.  The
+    // host looks at one mapped int between segments — not per token — and stops early once every
+    // sequence has emitted EOT (main.rs:781-783, 820-822).
+    auto run_segment = [&](int n_steps, bool with_logits, int first_gi) {
+        if (!use_graph) return enqueue_steps(n_steps, with_logits, first_gi);
+        const int key[8] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
+                            c.precision * 64 + nsplit * 8 + (D.pdl ? 4 : 0) + (D.fuse_chain ? 2 : 0) + (D.fuse_argmax ? 1 : 0),
+                            n_steps, with_logits ? 1 : 0};
+        DecGraph* g = nullptr;
+        for (auto& e : D.graphs) {
+            bool same = true;
+            for (int i = 0; i < 8; ++i) same = same && e.key[i] == key[i];
+            if (same) { g = &e; break; }
+        }
+        if (!g) {
+            if (D.graphs.size() >= 12) {                     // bounded cache: drop everything on overflow
+                for (auto& e : D.graphs) cudaGraphExecDestroy(e.exec);
+                D.graphs.clear();
+            }
+            DecGraph e{};
             cudaGraph_t graph = nullptr;
             CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             try {
-                D.g_launches = enqueue_all();
+                e.launches = enqueue_steps(n_steps, with_logits, first_gi);
             } catch (...) {
                 cudaStreamEndCapture(st, &graph);
                 if (graph) cudaGraphDestroy(graph);
                 throw;
             }
             CUDA_CHECK(cudaStreamEndCapture(st, &graph));
-            cudaError_t ie = cudaGraphInstantiate(&D.graph_exec, graph, 0);
+            cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
             cudaGraphDestroy(graph);
             CUDA_CHECK(ie);
-            for (int i = 0; i < 6; ++i) D.g_key[i] = key[i];
+            for (int i = 0; i < 8; ++i) e.key[i] = key[i];
+            D.graphs.push_back(e);
+            g = &D.graphs.back();
         }
-        CUDA_CHECK(cudaEventRecord(e0.e, st));
-        CUDA_CHECK(cudaGraphLaunch(D.graph_exec, st));
-        launches = D.g_launches;
-    } else {
-        CUDA_CHECK(cudaEventRecord(e0.e, st));
-        launches = enqueue_all();
+        CUDA_CHECK(cudaGraphLaunch(g->exec, st));
+        return g->launches;
+    };
+
+    // graphs are built (first use) outside the timed region
+    const char* xenv = getenv("WB_DEC_SEG");
+    int SEG = xenv ? atoi(xenv) : 16;
+    if (SEG < 1) SEG = 1;
+    int steps_done = 0;
+    *D.unfinished_host = B;
+    CUDA_CHECK(cudaEventRecord(e0.e, st));
+    if (P > 1) { launches += run_segment(P - 1, false, 0); steps_done += P - 1; }
+    int gi = 0;
+    CudaEvent eseg;
+    while (gi < max_new) {
+        const int n = max_new - gi < SEG ? max_new - gi : SEG;
+        launches += run_segment(n, true, gi);
+        gi += n;
+        steps_done += n;
+        if (gi < max_new) {
+            CUDA_CHECK(cudaEventRecord(eseg.e, st));
+            CUDA_CHECK(cudaEventSynchronize(eseg.e));
+            if (*D.unfinished_host == 0 && !p.forced) break;      // every sequence emitted EOT
+        }
     }
     CUDA_CHECK(cudaEventRecord(e1.e, st));
     CUDA_CHECK(cudaEventSynchronize(e1.e));
     CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.decode_ms, e0.e, e1.e));
     ctx->timing.decode_launches = launches;
-    ctx->timing.decode_steps = steps;
+    ctx->timing.decode_steps = steps_done;
+    (void)steps;
 }
 
 // Microbenchmark hook for bench.py's roofline block: replays one kernel on live buffers.
