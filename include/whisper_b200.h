@@ -57,8 +57,10 @@ typedef struct wb_timing {
 int wb_default_cfg(wb_model_cfg* cfg, const char* name);
 
 /* Replaces ort::init + 3x build_session (main.rs:1090-1108, 169-202): loads weights to HBM.
- * weights_path: a .wb200 blob (weights.py::save_blob), or NULL = seeded random init of the named
- * architecture (BASELINE.json north_star), bit-identical to weights.py::generate(cfg, seed). */
+ * weights_path: a directory holding the reference's ONNX export (encoder_model.onnx +
+ * decoder_model.onnx: initializers are read straight from the protobuf, csrc/host/onnx.cpp), a
+ * .wb200 blob (weights.py::save_blob), or NULL = seeded random init of the named architecture
+ * (BASELINE.json north_star), bit-identical to weights.py::generate(cfg, seed). */
 int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* weights_path);
 void wb_destroy(wb_ctx* ctx);
 const char* wb_last_error(void);
@@ -176,6 +178,9 @@ int wb_host_special_tokens(const wb_tokenizer* tok, const char* language, const 
  * length (excluding NUL) or negative error. */
 int64_t wb_host_decode_tokens(const wb_tokenizer* tok, const int64_t* tokens, int n, char* out,
                               int64_t cap);
+
+/* Host-only test hook for the ONNX-initializer reader: one tensor by Hugging Face parameter name. */
+int wb_onnx_read_tensor(const char* onnx_dir, const wb_model_cfg* cfg, const char* name, float* out, int64_t n);
 
 /* The drop-in CLI (main.rs:23-86 flag surface, :1065-1271 driver) as a callable. */
 int wb_cli_main(int argc, const char* const* argv);

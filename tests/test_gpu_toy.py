@@ -39,3 +39,26 @@ def test_toy_end_to_end(wb, oracle, precision, B):
         assert np.linalg.norm(enc - r) / np.linalg.norm(r) <= 2e-2
         assert all(len(t) == len(q) for t, q in zip(toks, ref))
     m.close()
+
+
+def test_weights_from_onnx_export_and_blob(wb, tmp_path):
+    """north_star: 'Weights come from the whisper-base-with-past ONNX initializers when present'."""
+    from onnx_writer import export_like_optimum
+    mc = wb.weights.WHISPER_TOY
+    W = wb.weights.generate(mc, 3)
+    ref = wr.WhisperRef(mc, W)
+    mel = np.random.default_rng(1).normal(0, 0.5, (1, 80, 3000)).astype(np.float32)
+    want = ref.encode(mel)
+    onnx_dir = tmp_path / "onnx"
+    onnx_dir.mkdir()
+    export_like_optimum(mc, W, str(onnx_dir))
+    blob = tmp_path / "w.wb200"
+    wb.weights.save_blob(str(blob), mc, W)
+    for src in (str(onnx_dir), str(blob)):
+        m = wb.Whisper(wb.default_cfg("toy", max_batch=1, max_chunks=1), weights_path=src)
+        assert np.array_equal(m.tensor("model.decoder.layers.1.encoder_attn.k_proj.weight", (128, 128)),
+                              W["model.decoder.layers.1.encoder_attn.k_proj.weight"])
+        assert np.abs(m.encode(mel) - want).max() <= 1e-4
+        toks = m.greedy_decode(1, [1, 2, 3, 4], 4, 1030)
+        assert toks == ref.greedy(want, [1, 2, 3, 4], 4, 1030)
+        m.close()

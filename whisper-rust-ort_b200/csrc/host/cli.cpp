@@ -380,13 +380,15 @@ int run(const Args& args) {
 
     WB_REQUIRE(is_dir(args.onnx_dir), WB_EIO, "onnx_dir does not exist or is not a directory: %s", args.onnx_dir.c_str());
 
-    // weights: <onnx_dir>/weights.wb200 (or --weights) when present, else seeded random init of the
-    // named architecture (BASELINE.json north_star).  Raw .onnx initializers are not parsed yet.
+    // weights (BASELINE.json north_star): --weights / <onnx_dir>/weights.wb200, else the initializers of the
+    // reference's own encoder_model.onnx + decoder_model.onnx, else seeded random init of the architecture.
     std::string wpath = args.weights;
     if (wpath.empty() && is_file(join(args.onnx_dir, "weights.wb200"))) wpath = join(args.onnx_dir, "weights.wb200");
-    if (wpath.empty() && is_file(join(args.onnx_dir, "encoder_model.onnx")))
-        fprintf(stderr, "note: %s holds .onnx files but no weights.wb200; ONNX-initializer import is not built yet, "
-                        "using seeded random-init weights\n", args.onnx_dir.c_str());
+    if (wpath.empty() && is_file(join(args.onnx_dir, "encoder_model.onnx")) && is_file(join(args.onnx_dir, "decoder_model.onnx")))
+        wpath = args.onnx_dir;
+    if (wpath.empty())
+        fprintf(stderr, "note: no weights in %s (weights.wb200 or encoder_model.onnx + decoder_model.onnx): "
+                        "using seeded random-init %s weights\n", args.onnx_dir.c_str(), args.arch.c_str());
     wb_model_cfg mc;
     CK(wb_default_cfg(&mc, args.arch.c_str()));
     WB_REQUIRE(args.precision == "bf16" || args.precision == "fp32", WB_EINVAL, "--precision must be bf16 or fp32");

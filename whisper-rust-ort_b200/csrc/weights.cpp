@@ -7,8 +7,12 @@
 #include <cstring>
 #include <fstream>
 
+#include <sys/stat.h>
+
 #include "ctx.h"
 #include "host/json.h"
+
+void onnx_load_dir(const std::string& dir, const wb_model_cfg& c, std::map<std::string, std::vector<float>>& host);   // host/onnx.cpp
 
 namespace {
 
@@ -172,7 +176,14 @@ void weights_init(wb_ctx* ctx, const char* path) {
     const wb_model_cfg& c = ctx->cfg;
     auto specs = tensor_specs(c);
     auto& host = ctx->w.host;
-    if (path && path[0]) {
+    struct stat st;
+    if (path && path[0] && ::stat(path, &st) == 0 && S_ISDIR(st.st_mode)) {
+        onnx_load_dir(path, c, host);                       // optimum export: encoder_model.onnx + decoder_model.onnx
+        for (const auto& sp : specs) {
+            auto it = host.find(sp.name);
+            WB_REQUIRE(it != host.end() && (int64_t)it->second.size() == numel(sp), WB_EINVAL, "ONNX export did not yield tensor %s", sp.name.c_str());
+        }
+    } else if (path && path[0]) {
         load_blob(path, c, specs, host);
     } else {
         for (size_t i = 0; i < specs.size(); ++i) generate_tensor(specs[i], (int)i, c.seed, host[specs[i].name]);
