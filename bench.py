@@ -179,6 +179,10 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     prec = wb200.WB_PREC_BF16 if args.precision == "bf16" else wb200.WB_PREC_FP32
     B, S = args.batch, max(1, args.in_flight)
+    # waiting host threads spin by default; with more waiters than cores let them block instead
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if S * local_world > (os.cpu_count() or 1) // 2:
+        os.environ.setdefault("WB_BLOCKING_SYNC", "1")
     # S independent contexts (own stream, activations, KV caches, decode graph) = S batches in flight per GPU:
     # a decode step is ~50 dependent small kernels, so concurrent batches fill the SMs a single chain leaves idle.
     ctxs = [wb200.Whisper(wb200.default_cfg("base", precision=prec, max_batch=B, max_chunks=B), device=local_rank) for _ in range(S)]

@@ -72,7 +72,7 @@ void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_fil
     CUDA_CHECK(cudaMemcpyAsync(s.tile_off.p, s.h_tile_off.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(s.chunks.p, s.h_chunks.data(), sizeof(MelChunk) * s.n_chunks, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(e1.e, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(wb_stream_sync(st));
     CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.h2d_ms, e0.e, e1.e));
     if (n_chunks_out) *n_chunks_out = s.n_chunks;
 }
@@ -295,7 +295,7 @@ int wb_selftest_gemm(wb_ctx* ctx, int M, int N, int K, int lda, int batch, int f
     gemm_tc(ctx, g);
     g.C = c1.p; g.residual = dres1.p;
     gemm_simt(ctx, g);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(wb_stream_sync(ctx->stream));
     std::vector<unsigned char> h0(out_elems * esz), h1(out_elems * esz);
     CUDA_CHECK(cudaMemcpy(h0.data(), c0.p, h0.size(), cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(h1.data(), c1.p, h1.size(), cudaMemcpyDeviceToHost));
@@ -329,7 +329,7 @@ int wb_selftest_attn(wb_ctx* ctx, int B, float* max_diff_out, float* max_abs_out
     CUDA_CHECK(cudaMemset(o0.p, 0xFF, n_out * 2));
     attn_tc(ctx, ctx->enc.qkv.p, o0.p, B, T, d, c.n_heads);
     attention_simt(ctx, ctx->enc.qkv.p, o1.p, B);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(wb_stream_sync(ctx->stream));
     std::vector<__nv_bfloat16> h0(n_out), h1(n_out);
     CUDA_CHECK(cudaMemcpy(h0.data(), o0.p, n_out * 2, cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(h1.data(), o1.p, n_out * 2, cudaMemcpyDeviceToHost));
@@ -396,7 +396,7 @@ int wb_log_mel(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_file
         CUDA_CHECK(cudaEventRecord(e0.e, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(mel_out, s.export_buf.p, sizeof(float) * (size_t)s.total_frames * 80, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaEventRecord(e1.e, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CUDA_CHECK(wb_stream_sync(ctx->stream));
         CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.d2h_ms, e0.e, e1.e));
     }
     WB_CATCH
@@ -426,7 +426,7 @@ int wb_get_chunk_mel(wb_ctx* ctx, int chunk_begin, int n, float* out) {
         mel_launch_export(ctx, ch.file, ch.frame_start, WB_N_FRAMES, s.export_buf.p + (size_t)i * 80 * WB_N_FRAMES);
     }
     CUDA_CHECK(cudaMemcpyAsync(out, s.export_buf.p, sizeof(float) * (size_t)n * 80 * WB_N_FRAMES, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(wb_stream_sync(ctx->stream));
     WB_CATCH
 }
 
@@ -450,7 +450,7 @@ int wb_encode(wb_ctx* ctx, const float* mel, int chunk_begin, int B, float* hidd
     if (hidden_out) {
         CUDA_CHECK(cudaMemcpyAsync(hidden_out, ctx->enc.out.p, sizeof(float) * (size_t)B * c.n_audio_ctx * c.d_model,
                                    cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CUDA_CHECK(wb_stream_sync(ctx->stream));
     }
     WB_CATCH
 }
@@ -464,7 +464,7 @@ int wb_get_encoder_debug(wb_ctx* ctx, const char* what, float* out, int64_t n) {
     WB_REQUIRE(src && src->p, WB_EINVAL, "unknown debug tensor '%s'", w.c_str());
     WB_REQUIRE(n <= (int64_t)src->cap, WB_EINVAL, "debug tensor smaller than requested");
     CUDA_CHECK(cudaMemcpyAsync(out, src->p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(wb_stream_sync(ctx->stream));
     WB_CATCH
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -64,13 +65,27 @@ struct DevBuf {
     }
 };
 
+// WB_BLOCKING_SYNC=1: host waits yield the core instead of spinning (many contexts per host, e.g. 8 GPUs
+// x 4 batches in flight on a box with fewer cores than waiting threads).
+inline bool wb_blocking_sync() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("WB_BLOCKING_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 struct CudaEvent {
     cudaEvent_t e = nullptr;
-    CudaEvent() { cudaEventCreate(&e); }
+    CudaEvent() { cudaEventCreateWithFlags(&e, wb_blocking_sync() ? cudaEventBlockingSync : cudaEventDefault); }
     ~CudaEvent() { if (e) cudaEventDestroy(e); }
     CudaEvent(const CudaEvent&) = delete;
     CudaEvent& operator=(const CudaEvent&) = delete;
 };
 
+// stream synchronisation that honours WB_BLOCKING_SYNC
+inline cudaError_t wb_stream_sync(cudaStream_t st) {
+    if (!wb_blocking_sync()) return cudaStreamSynchronize(st);
+    CudaEvent ev;
+    cudaError_t e = cudaEventRecord(ev.e, st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ev.e);
+}
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

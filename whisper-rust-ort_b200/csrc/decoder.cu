@@ -1213,7 +1213,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
         forced_dev = D.forced.p;
     }
     if (p.want_logits) D.logits_all.reserve((size_t)B * max_new * c.vocab);
-    CUDA_CHECK(cudaStreamSynchronize(st));      // host staging vectors go out of scope below
+    CUDA_CHECK(wb_stream_sync(st));      // host staging vectors go out of scope below
 
     CudaEvent e0, e1;
     const int steps = P + max_new - 1;
@@ -1384,7 +1384,7 @@ void decoder_fetch(wb_ctx* ctx, const DecodeParams& p, int64_t* tokens_out, int3
     CUDA_CHECK(cudaMemcpyAsync(lens.data(), D.lens.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
     if (logits_out)
         CUDA_CHECK(cudaMemcpyAsync(logits_out, D.logits_all.p, sizeof(float) * (size_t)B * max_new * c.vocab, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(wb_stream_sync(ctx->stream));
     for (int b = 0; b < B; ++b) {
         if (lens_out) lens_out[b] = lens[b];
         for (int i = 0; i < T_total; ++i)
