@@ -18,7 +18,12 @@ void wb_set_error(const std::string& msg) { g_err = msg; }
 
 namespace {
 
-void require_ctx(const wb_ctx* c) { WB_REQUIRE(c != nullptr, WB_EINVAL, "null wb_ctx"); }
+// Every entry point may be called from a different host thread than the one that created the ctx; CUDA's
+// current device is per thread, so bind it to the ctx's device first (streams/events are device-bound).
+void require_ctx(const wb_ctx* c) {
+    WB_REQUIRE(c != nullptr, WB_EINVAL, "null wb_ctx");
+    CUDA_CHECK(cudaSetDevice(c->device));
+}
 
 // Stage file list + chunk table on the device (wb_upload_pcm).
 void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files, int64_t chunk_len,
