@@ -86,8 +86,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+    def __init__(self, index: int, enabled: bool = True):
+        # rank 0 only: nvidia-smi takes driver locks, and 8 ranks polling it stall each other's launches
+        self.index, self.rows, self.stop, self.enabled = index, [], threading.Event(), enabled
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -99,15 +100,17 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.05)
+            self.stop.wait(0.2)
 
     def __enter__(self):
-        self.th.start()
+        if self.enabled:
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.enabled:
+            self.th.join(timeout=6)
 
     def summary(self):
         if not self.rows:
@@ -227,7 +230,7 @@ def run_ours(args, rank, world, local_rank):
         toks[i] = ctxs[i].transcribe_resident(B, PROMPT, MAX_NEW, EOT, sup, bsup)
     run_workers(resident_step, args.warmup * S)
     barrier()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         m.mark(0)
         t0 = time.perf_counter()
         lat_res = run_workers(resident_step, args.steps)
