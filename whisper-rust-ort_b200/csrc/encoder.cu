@@ -14,47 +14,54 @@ template <typename T> __device__ __forceinline__ void put(T* p, float v);
 template <> __device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-constexpr int LN_MAX_PER_LANE = 40;   // d_model <= 1280
+constexpr int LN_MAX_VEC = 10;        // float4 per lane: d_model <= 1280
 
-// One warp per row.  out = (x-mean)/sqrt(var+eps)*w+b (two-pass, f32), optional second f32 copy.
-template <typename TO>
-__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                 const float* __restrict__ b, TO* __restrict__ out,
-                                 float* __restrict__ out_f32, int rows, int d) {
+__device__ __forceinline__ void put4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void put4(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&lo);
+    u.y = *reinterpret_cast<unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// One warp per row, 128-bit loads, row kept in registers (NV float4 per lane, d = 128*NV).
+// out = (x-mean)/sqrt(var+eps)*w+b with two-pass statistics like the oracle; optional second f32 copy.
+template <typename TO, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                 TO* __restrict__ out, float* __restrict__ out_f32, int rows) {
+    constexpr int d = NV * 128;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float* xr = x + (size_t)row * d;
-    float v[LN_MAX_PER_LANE];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
+    float4 v[NV];
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-        int c = lane + i * 32;
-        v[i] = c < d ? xr[c] : 0.0f;
-        s += v[i];
+    for (int i = 0; i < NV; ++i) {
+        v[i] = xr[lane + i * 32];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)d;
     float q = 0.0f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-        int c = lane + i * 32;
-        float t = c < d ? v[i] - mean : 0.0f;
-        v[i] = t;
-        q += t * t;
+    for (int i = 0; i < NV; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float sd = sqrtf(q / (float)d + 1e-5f);
+    const float rs = 1.0f / sqrtf(q / (float)d + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-        int c = lane + i * 32;
-        if (c < d) {
-            float y = v[i] / sd * w[c] + b[c];
-            put<TO>(out + (size_t)row * d + c, y);
-            if (out_f32) out_f32[(size_t)row * d + c] = y;
-        }
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + i * 32) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+        const float y0 = v[i].x * rs * g.x + bb.x, y1 = v[i].y * rs * g.y + bb.y, y2 = v[i].z * rs * g.z + bb.z, y3 = v[i].w * rs * g.w + bb.w;
+        put4(out + (size_t)row * d + c, y0, y1, y2, y3);
+        if (out_f32) put4(out_f32 + (size_t)row * d + c, y0, y1, y2, y3);
     }
 }
 
@@ -90,15 +97,27 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, int rows, int n) {
     }
 }
 
-void layernorm(wb_ctx* ctx, const float* x, const LNW& ln, void* out, float* out_f32, int rows) {
-    const int d = ctx->cfg.d_model;
+template <typename TO>
+void layernorm_t(wb_ctx* ctx, const float* x, const LNW& ln, TO* out, float* out_f32, int rows, int d) {
     const int wpb = 8;
     dim3 grid(ceil_div(rows, wpb));
-    if (ctx->cfg.precision == WB_PREC_BF16)
-        layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, (__nv_bfloat16*)out, out_f32, rows, d);
-    else
-        layernorm_kernel<float><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, (float*)out, out_f32, rows, d);
+    switch (d / 128) {
+        case 1: layernorm_kernel<TO, 1><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        case 2: layernorm_kernel<TO, 2><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        case 3: layernorm_kernel<TO, 3><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        case 4: layernorm_kernel<TO, 4><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        case 6: layernorm_kernel<TO, 6><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        case 8: layernorm_kernel<TO, 8><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        case 10: layernorm_kernel<TO, 10><<<grid, wpb * 32, 0, ctx->stream>>>(x, ln.w, ln.b, out, out_f32, rows); break;
+        default: WB_THROW(WB_EINVAL, "layernorm: unsupported d_model %d (128 x {1,2,3,4,6,8,10})", d);
+    }
     CUDA_CHECK(cudaGetLastError());
+}
+
+void layernorm(wb_ctx* ctx, const float* x, const LNW& ln, void* out, float* out_f32, int rows) {
+    const int d = ctx->cfg.d_model;
+    if (ctx->cfg.precision == WB_PREC_BF16) layernorm_t<__nv_bfloat16>(ctx, x, ln, (__nv_bfloat16*)out, out_f32, rows, d);
+    else layernorm_t<float>(ctx, x, ln, (float*)out, out_f32, rows, d);
 }
 
 }  // namespace
@@ -147,7 +166,7 @@ void encoder_alloc(wb_ctx* ctx) {
     const wb_model_cfg& c = ctx->cfg;
     const size_t B = c.max_batch, T = WB_N_FRAMES, Tc = c.n_audio_ctx, d = c.d_model, e = ctx->esz();
     WB_REQUIRE(c.n_audio_ctx * 2 == WB_N_FRAMES, WB_EINVAL, "n_audio_ctx must be 1500");
-    WB_REQUIRE(d <= 32 * LN_MAX_PER_LANE && d % 128 == 0 && c.ffn_dim % 128 == 0, WB_EINVAL, "unsupported d_model/ffn_dim");
+    WB_REQUIRE(d <= 128 * LN_MAX_VEC && d % 128 == 0 && c.ffn_dim % 128 == 0, WB_EINVAL, "unsupported d_model/ffn_dim");
     WB_REQUIRE(d / c.n_heads == 64 && d % c.n_heads == 0, WB_EINVAL, "head_dim must be 64");
     EncBufs& b = ctx->enc;
     b.mel_tm.reserve_zero((size_t)c.max_chunks * (T + 2) * c.n_mels * e);
