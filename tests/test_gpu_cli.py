@@ -79,3 +79,25 @@ def test_cli_unsupported_container_aborts_like_anyhow(wb, tmp_path):
                         "--out-json", str(tmp_path / "o.json"), "--out-summary-json", str(tmp_path / "s.json")],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 1 and "unsupported audio container" in r.stderr
+
+
+def test_cli_file_batch_gives_the_same_transcripts(wb, tmp_path):
+    """--file-batch packs the chunks of several files into shared GPU batches (the log-mel clamp stays
+    per file): transcripts must not depend on the grouping."""
+    audio, onnx = tmp_path / "audio", tmp_path / "onnx"
+    audio.mkdir(); onnx.mkdir()
+    for i, sec in enumerate([3.0, 33.0, 9.5, 30.0, 61.0]):
+        wb.synth.write_wav(str(audio / f"f{i}.wav"), wb.synth.clip(i, 8, sec) * (0.02 if i == 1 else 1.0), fmt="s16")
+    texts = {}
+    for fb in (1, 2, 5):
+        out = tmp_path / f"out{fb}"
+        r = subprocess.run([EXE, "--audio-dir", str(audio), "--onnx-dir", str(onnx), "--arch", "base", "--precision", "fp32",
+                            "--max-new-tokens", "5", "--batch", "4", "--file-batch", str(fb),
+                            "--out-csv", str(out / "a.csv"), "--out-json", str(out / "a.json"), "--out-summary-json", str(out / "s.json")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        rows = json.loads((out / "a.json").read_text())
+        texts[fb] = [(x["file"], x["text"]) for x in rows]
+        assert json.loads((out / "s.json").read_text())["n_files"] == 5
+    assert texts[1] == texts[2] == texts[5]
+    assert all(t.startswith("[TOKENS:") for _, t in texts[1])

@@ -47,6 +47,7 @@ struct Args {
     std::string precision = "bf16", weights, arch = "base";
     uint64_t seed = 0;
     int batch = 32;
+    size_t file_batch = 1;      // files transcribed together (1 = the reference's serial per-file loop)
 };
 
 struct OrtCfg {      // main.rs:91-100 — echoed only
@@ -82,6 +83,8 @@ const char* USAGE =
     "      --overlap-s <S>                [default: 5]\n"
     "B200 extensions:\n"
     "      --device <N>  --precision <bf16|fp32>  --batch <N>  --weights <file.wb200>  --arch <base|large-v3|toy>  --seed <N>\n"
+    "      --file-batch <N>               files whose chunks share GPU batches [default: 1 = serial like the reference];\n"
+    "                                     every file of a group is charged the group's preprocess/model/decode time\n"
     "  -h, --help\n";
 
 Args parse_args(int argc, const char* const* argv) {
@@ -136,6 +139,7 @@ Args parse_args(int argc, const char* const* argv) {
         else if (flag == "--arch") a.arch = need(i, flag, iv, has_inline);
         else if (flag == "--seed") a.seed = to_usize(need(i, flag, iv, has_inline), flag);
         else if (flag == "--batch") a.batch = (int)to_usize(need(i, flag, iv, has_inline), flag);
+        else if (flag == "--file-batch") a.file_batch = std::max<size_t>(1, to_usize(need(i, flag, iv, has_inline), flag));
         else throw UsageError("error: unexpected argument '" + tok + "' found");
     }
     return a;
@@ -289,9 +293,12 @@ struct Timing { double preprocess_s = 0, model_only_s = 0, decode_s = 0, end_to_
         if (_rc != WB_OK) throw WbError(_rc, wb_last_error());    \
     } while (0)
 
-// transcribe_longform_chunked, main.rs:834-1008
-std::string transcribe(wb_ctx* ctx, int max_batch, const float* pcm, int64_t n, const Args& a, const wb_tokenizer* tok,
-                       const GenCfg& gen, Timing& t) {
+// transcribe_longform_chunked, main.rs:834-1008, for a GROUP of files: one log-mel launch over all of them
+// (the clamp maximum stays per file, quirk Q1), all their chunks packed into GPU batches of max_batch, then
+// per-file detokenise + stitch.  With one file per group this is exactly the reference's per-file call.
+struct FilePcm { const float* p; int64_t n; };
+std::vector<std::string> transcribe(wb_ctx* ctx, int max_batch, const std::vector<FilePcm>& files, const Args& a,
+                                    const wb_tokenizer* tok, const GenCfg& gen, Timing& t) {
     auto t0 = Clock::now();
     int64_t sp[5];
     CK(wb_host_special_tokens(tok, a.language.c_str(), a.task.c_str(), sp));
@@ -303,9 +310,19 @@ std::string transcribe(wb_ctx* ctx, int max_batch, const float* pcm, int64_t n, 
     const int64_t step = std::max<int64_t>(chunk_len > overlap ? chunk_len - overlap : 0, 1);
 
     auto tp0 = Clock::now();
-    const int64_t offs[2] = {0, n};
+    std::vector<int64_t> offs(files.size() + 1, 0);
+    for (size_t i = 0; i < files.size(); ++i) offs[i + 1] = offs[i] + files[i].n;
+    const float* pcm = files[0].p;
+    std::vector<float> packed;
+    if (files.size() > 1) {                       // several files: one contiguous host buffer for the H2D copy
+        packed.resize((size_t)offs.back());
+        for (size_t i = 0; i < files.size(); ++i) std::memcpy(packed.data() + offs[i], files[i].p, sizeof(float) * (size_t)files[i].n);
+        pcm = packed.data();
+    }
     int n_chunks = 0;
-    CK(wb_log_mel(ctx, pcm, offs, 1, chunk_len, step, nullptr, nullptr, &n_chunks));
+    CK(wb_log_mel(ctx, pcm, offs.data(), (int)files.size(), chunk_len, step, nullptr, nullptr, &n_chunks));
+    std::vector<int32_t> chunk_file((size_t)n_chunks);
+    CK(wb_get_chunks(ctx, chunk_file.data(), nullptr, n_chunks));
     t.preprocess_s += since(tp0);
 
     const int mn = (int)std::max<size_t>(a.max_new_tokens, 1);
@@ -323,7 +340,7 @@ std::string transcribe(wb_ctx* ctx, int max_batch, const float* pcm, int64_t n, 
     t.model_only_s += since(tm0);
 
     auto td0 = Clock::now();
-    std::vector<std::string> texts;
+    std::vector<std::vector<std::string>> texts(files.size());
     for (int c = 0; c < n_chunks; ++c) {                                             // main.rs:925-943
         const int64_t* row = toks.data() + (size_t)c * stride;
         int len = lens[c];
@@ -336,10 +353,11 @@ std::string transcribe(wb_ctx* ctx, int max_batch, const float* pcm, int64_t n, 
         wb_host_decode_tokens(tok, g.data(), (int)g.size(), &text[0], need + 1);
         text.resize((size_t)need);
         if (text.empty()) text = "[EMPTY]";
-        if (text != "[EMPTY]") texts.push_back(text);
+        if (text != "[EMPTY]") texts[(size_t)chunk_file[c]].push_back(text);
     }
     t.decode_s += since(td0);
-    std::string full = wbtext::stitch_texts(texts);
+    std::vector<std::string> full;
+    for (const auto& tx : texts) full.push_back(wbtext::stitch_texts(tx));
     t.end_to_end_s = since(t0);
     return full;
 }
@@ -416,38 +434,50 @@ int run(const Args& args) {
     if (args.limit_files > 0 && files.size() > args.limit_files) files.resize(args.limit_files);
     WB_REQUIRE(!files.empty(), WB_EINVAL, "No audio files found in %s", args.audio_dir.c_str());
 
-    struct Pcm { float* p = nullptr; int64_t n = 0; double dur = 0; ~Pcm() { wb_host_free(p); } };
+    struct Pcm { float* p = nullptr; int64_t n = 0; double dur = 0; Pcm() = default; Pcm(const Pcm&) = delete; Pcm& operator=(const Pcm&) = delete; ~Pcm() { wb_host_free(p); } };
     if (args.warmup > 0) {                                                           // main.rs:1131-1152
         Pcm a0;
         CK(wb_host_load_audio_16k_mono(join(args.audio_dir, files[0]).c_str(), &a0.p, &a0.n, &a0.dur));
         WB_REQUIRE(a0.n > 0, WB_EINVAL, "Empty audio");
-        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, mc.max_batch, a0.p, a0.n, args, tk.t, gen, t); }
+        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, mc.max_batch, {FilePcm{a0.p, a0.n}}, args, tk.t, gen, t); }
     }
 
     struct Row { std::string file; double duration_s, end_to_end_s, rtf; std::string text; };
     std::vector<Row> rows;
     std::vector<double> e2e, load, pre, model, dec, rtfs;
     const std::string txt_dir = parent_of(args.out_csv);
-    for (const std::string& fnm : files) {                                           // main.rs:1164-1213
-        auto tl0 = Clock::now();
-        Pcm au;
-        CK(wb_host_load_audio_16k_mono(join(args.audio_dir, fnm).c_str(), &au.p, &au.n, &au.dur));
-        const double load_s = since(tl0);
-        WB_REQUIRE(au.n > 0, WB_EINVAL, "Empty audio");
+    for (size_t g0 = 0; g0 < files.size(); g0 += args.file_batch) {                  // main.rs:1164-1213
+        const size_t g1 = std::min(files.size(), g0 + args.file_batch);
+        std::vector<Pcm> au(g1 - g0);
+        std::vector<double> load_s(g1 - g0);
+        std::vector<FilePcm> group;
+        for (size_t i = g0; i < g1; ++i) {
+            auto tl0 = Clock::now();
+            Pcm& p = au[i - g0];
+            CK(wb_host_load_audio_16k_mono(join(args.audio_dir, files[i]).c_str(), &p.p, &p.n, &p.dur));
+            load_s[i - g0] = since(tl0);
+            WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
+            group.push_back(FilePcm{p.p, p.n});
+        }
         Timing t;
-        std::string text = transcribe(ctx, mc.max_batch, au.p, au.n, args, tk.t, gen, t);
-        const double end_to_end_s = load_s + t.end_to_end_s;
-        const double rtf = end_to_end_s / std::max(au.dur, 1e-9);
-        rows.push_back(Row{fnm, std::round(au.dur * 1000.0) / 1000.0, std::round(end_to_end_s * 10000.0) / 10000.0,
-                           std::round(rtf * 1000000.0) / 1000000.0, text});
-        load.push_back(load_s); pre.push_back(t.preprocess_s); model.push_back(t.model_only_s); dec.push_back(t.decode_s);
-        e2e.push_back(end_to_end_s); rtfs.push_back(rtf);
-        if (args.write_txt) {
-            size_t dot = fnm.find_last_of('.');
-            std::string stem = dot == std::string::npos ? fnm : fnm.substr(0, dot);
-            size_t b = text.find_first_not_of(" \t\r\n"), e = text.find_last_not_of(" \t\r\n");
-            std::string trimmed = b == std::string::npos ? "" : text.substr(b, e - b + 1);
-            write_file(join(txt_dir, stem + ".transcript.txt"), trimmed + "\n");
+        std::vector<std::string> texts = transcribe(ctx, mc.max_batch, group, args, tk.t, gen, t);
+        for (size_t i = g0; i < g1; ++i) {
+            const std::string& fnm = files[i];
+            const std::string& text = texts[i - g0];
+            const double dur = au[i - g0].dur;
+            const double end_to_end_s = load_s[i - g0] + t.end_to_end_s;
+            const double rtf = end_to_end_s / std::max(dur, 1e-9);
+            rows.push_back(Row{fnm, std::round(dur * 1000.0) / 1000.0, std::round(end_to_end_s * 10000.0) / 10000.0,
+                               std::round(rtf * 1000000.0) / 1000000.0, text});
+            load.push_back(load_s[i - g0]); pre.push_back(t.preprocess_s); model.push_back(t.model_only_s); dec.push_back(t.decode_s);
+            e2e.push_back(end_to_end_s); rtfs.push_back(rtf);
+            if (args.write_txt) {
+                size_t dot = fnm.find_last_of('.');
+                std::string stem = dot == std::string::npos ? fnm : fnm.substr(0, dot);
+                size_t b = text.find_first_not_of(" \t\r\n"), e = text.find_last_not_of(" \t\r\n");
+                std::string trimmed = b == std::string::npos ? "" : text.substr(b, e - b + 1);
+                write_file(join(txt_dir, stem + ".transcript.txt"), trimmed + "\n");
+            }
         }
     }
 
