@@ -150,23 +150,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             mbar_wait(bar_q, 0);
             const uint64_t dq = make_desc_sw128(smem_u32(sQ));
             const uint64_t dv = make_desc_sw128(smem_u32(sV));
-            for (int j = 0; j < n_kb; ++j) {
+            auto issue_s = [&](int j) {                                  // S_j = Q K_j^T into TMEM, then release the K slot
                 const int s = j & 1;
                 mbar_wait(&bar_k[s], (uint32_t)((j >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t dk = make_desc_sw128(smem_u32(sK + s * TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)                        // S = Q K^T, K dim = head_dim
+                for (int k = 0; k < HD / 16; ++k)                        // K dim = head_dim
                     umma(tS, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
                 umma_commit(bar_s);
                 umma_commit(&bar_kfree[s]);
-                if (j + 1 < n_kb) {                                      // prefetch K block j+1
-                    const int s1 = (j + 1) & 1;
-                    if (j >= 1) mbar_wait(&bar_kfree[s1], (uint32_t)(((j - 1) >> 1) & 1));
-                    mbar_expect_tx(&bar_k[s1], TILE_BYTES);
-                    tma_load_3d(&tmQKV, &bar_k[s1], sK + s1 * TILE_BYTES, d + h * HD, (j + 1) * AK, b);
+            };
+            auto load_k = [&](int j) {                                   // K block j into slot j&1 (free once S_{j-2} retired)
+                const int s = j & 1;
+                if (j >= 2) mbar_wait(&bar_kfree[s], (uint32_t)(((j - 2) >> 1) & 1));
+                mbar_expect_tx(&bar_k[s], TILE_BYTES);
+                tma_load_3d(&tmQKV, &bar_k[s], sK + s * TILE_BYTES, d + h * HD, j * AK, b);
+            };
+            issue_s(0);
+            if (n_kb > 1) load_k(1);
+            for (int j = 0; j < n_kb; ++j) {
+                mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, S_j and O_{j-1} consumed
+                // S_{j+1} goes first: the softmax warps start on it while P_j V_j is still running
+                if (j + 1 < n_kb) {
+                    issue_s(j + 1);
+                    if (j + 2 < n_kb) load_k(j + 2);
                 }
-                mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, O_{j-1} consumed
                 mbar_wait(bar_v, (uint32_t)(j & 1));                     // V_j landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
