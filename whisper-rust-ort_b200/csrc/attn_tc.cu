@@ -1,7 +1,7 @@
 // attn_tc.cu — encoder self-attention of the bf16 build on tcgen05 (kernel K2d): non-causal,
 // T = 1500, head_dim 64.  One CTA per (clip, head, 128-query block); per 128-key block:
 //   S = Q.K^T        tcgen05.mma 128x128x64 (both operands K-major, TMA 128B swizzle) -> TMEM
-//   softmax          4 warps, one query row per thread: tcgen05.ld S, online max/sum in registers,
+//   softmax          8 warps, two threads per query row (64 keys each): tcgen05.ld S, online max/sum in registers,
 //                    P -> bf16 -> shared memory in the UMMA K-major swizzled layout
 //   O_j = P.V        tcgen05.mma 128x64x128 (V consumed MN-major straight from the TMA tile) -> TMEM
 //   O += O_j         in registers (tcgen05.ld), rescaled by exp(m_old - m_new)
@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int AQ = 128, AK = 128, HD = 64;
-constexpr int ATT_THREADS = 160;                       // warp 0: TMA + MMA issue; warps 1-4: softmax / epilogue
+constexpr int ATT_THREADS = 288;                       // warp 0: TMA + MMA issue; warps 1-8: softmax / epilogue
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;          // one [128 x 64] bf16 tile, 128-byte rows
 constexpr uint32_t ATT_TMEM_COLS = 256;                // S: [0,128)  O_j: [128,192)
 constexpr size_t ATT_SMEM = 6 * TILE_BYTES + 1024 + 128;   // Q, K[2], V, P[2 halves]: 97 KB -> two CTAs per SM
@@ -114,6 +114,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
     uint64_t* bar_v = bars + 8;        // V tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
+    __shared__ float s_xmax[2][2][128];                // [block parity][key half][row]: partial row maxima
+    __shared__ float s_xl[2][128];                     // [key half][row]: partial row sums (end of the tile)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x % n_qb, h = (blockIdx.x / n_qb) % H, b = blockIdx.x / (n_qb * H);
     const int n_kb = (T + AK - 1) / AK;
@@ -124,7 +126,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             mbar_init(bar_q, 1);
             mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
             mbar_init(&bar_kfree[0], 1); mbar_init(&bar_kfree[1], 1);
-            mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_v, 1);
+            mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1); mbar_init(bar_v, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -192,38 +194,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             }
         }
     } else {
-        // ===== softmax + output: thread <-> query row =====
+        // ===== softmax + output: 8 warps, two per TMEM lane quadrant; a thread owns one query row and one
+        // 64-key half of the block (and 32 of the 64 output columns); the two threads of a row swap their
+        // partial row maximum through shared memory + a 64-thread named barrier =====
         const int q = warp & 3;                                          // TMEM lane quadrant of this warp
+        const int half = (warp - 1) >> 2;                                // warps 1-4: keys 0-63, warps 5-8: keys 64-127
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const float sc = 0.125f * 1.4426950408889634f;                   // head_dim^-0.5 * log2(e)
-        float m = -INFINITY, l = 0.f;
-        float o[HD];
+        float m = -INFINITY, l = 0.f;                                    // l: this thread's half of the row sum
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = 0.f;
-        uint8_t* prow = sP + row * 128;
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        uint8_t* prow = sP + half * TILE_BYTES + row * 128;
         const int sw = row & 7;
 
         for (int j = 0; j < n_kb; ++j) {
             mbar_wait(bar_s, (uint32_t)(j & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int valid = T - j * AK;                                // keys of this block that exist
-            // pass 1: row maximum
+            // pass 1: maximum over this thread's 64 keys, then over the row
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int ch = half * 2 + c2;
                 uint32_t r[32];
                 tmem_ld32(tS + lane_off + ch * 32, r);
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (ch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
             }
+            s_xmax[j & 1][half][row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");    // the two warps of this quadrant
+            mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]);
             const float m_new = fmaxf(m, mx * sc);
             const float alpha = ex2(m - m_new);                          // 0 on the first block (m = -inf)
-            // pass 2: p = exp2(s*sc - m_new) -> bf16 -> swizzled smem; row sum of the rounded values
+            // pass 2: p = exp2(s*sc - m_new) -> bf16 -> swizzled smem; partial row sum of the rounded values
             float sum = 0.f;
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int ch = half * 2 + c2;
                 uint32_t r[32];
                 tmem_ld32(tS + lane_off + ch * 32, r);
                 uint32_t pk[16];
@@ -235,49 +245,44 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
                     sum += __low2float(pb) + __high2float(pb);
                     pk[i] = *reinterpret_cast<uint32_t*>(&pb);
                 }
-                // 32 keys = 4 chunks of 16 bytes inside half (ch >> 1), chunk index (ch & 1) * 4 + c
-                uint8_t* half = prow + (ch >> 1) * TILE_BYTES;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int chunk = (ch & 1) * 4 + c;
-                    *reinterpret_cast<uint4*>(half + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                for (int c = 0; c < 4; ++c) {                            // 32 keys = chunks c2*4 .. c2*4+3 of this half
+                    const int chunk = c2 * 4 + c;
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 }
             }
             l = l * alpha + sum;
             m = m_new;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor core
-            if (j > 0) {                                                   // fold in O_{j-1}, then rescale
+            if (j > 0) {                                                   // fold in O_{j-1} (own 32 columns), then rescale
                 mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t r[32];
+                tmem_ld32(tO + lane_off + half * 32, r);
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld32(tO + lane_off + ch * 32, r);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[ch * 32 + i] = (o[ch * 32 + i] + __uint_as_float(r[i])) * alpha;
-                }
+                for (int i = 0; i < 32; ++i) o[i] = (o[i] + __uint_as_float(r[i])) * alpha;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(bar_p);
         }
         mbar_wait(bar_o, (uint32_t)((n_kb - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float inv = 1.0f / l;
+        s_xl[half][row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float inv = 1.0f / (l + s_xl[half ^ 1][row]);
         const int gq = qb * AQ + row;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+        {
             uint32_t r[32];
-            tmem_ld32(tO + lane_off + ch * 32, r);
+            tmem_ld32(tO + lane_off + half * 32, r);
             if (gq < T) {
-                uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * T + gq) * d + h * HD + ch * 32);
+                uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * T + gq) * d + h * HD + half * 32);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t w[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int e = c * 8 + 2 * i;
-                        __nv_bfloat162 v = __floats2bfloat162_rn((o[ch * 32 + e] + __uint_as_float(r[e])) * inv,
-                                                                 (o[ch * 32 + e + 1] + __uint_as_float(r[e + 1])) * inv);
+                        __nv_bfloat162 v = __floats2bfloat162_rn((o[e] + __uint_as_float(r[e])) * inv, (o[e + 1] + __uint_as_float(r[e + 1])) * inv);
                         w[i] = *reinterpret_cast<uint32_t*>(&v);
                     }
                     dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
