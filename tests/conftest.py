@@ -13,6 +13,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    # a fresh checkout has no built artefacts (they are git-ignored): build once, nvcc cross-compiles without a GPU
+    lib = os.path.join(ROOT, "whisper-rust-ort_b200", "libwhisper_b200.so")
+    cli = os.path.join(ROOT, "whisper-rust-ort_b200", "whisper_b200_cli")
+    if not (os.path.exists(lib) and os.path.exists(cli)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
