@@ -696,6 +696,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+
+// one cross-attention launch over B sequences
+template <typename WT>
+void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, float* scratch, int* counters,
+                       int H, int B, int d, int Tk) {
+    launch_k(cross_attn_kernel<WT>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, q, ckv, att, scratch, counters, d, Tk);
+}
+
 constexpr int MM_THREADS = 256;
 
 // How a stage waits for its input: SYNC_PDL = the predecessor KERNEL (griddepcontrol), SYNC_CLUSTER =
@@ -1138,8 +1146,8 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
             skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;
             skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
         }
-        launch_k(cross_attn_kernel<WT>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, (const float*)q, ckv, att,
-                 D.xscratch.p + (size_t)b0 * H * XSPLIT * 66, D.xcount.p + (size_t)b0 * H, d, Tk); ++n;   // K3e
+        launch_cross_attn<WT>(st, pdl, (const float*)q, ckv, att,
+                              D.xscratch.p + (size_t)b0 * H * XSPLIT * 66, D.xcount.p + (size_t)b0 * H, H, B, d, Tk); ++n;   // K3e
         if (chain) {
             ChainArgs a{};
             a.B = B;
@@ -1392,7 +1400,10 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
 void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg_ms, double* bytes) {
     const wb_model_cfg& c = ctx->cfg;
     DecBufs& D = ctx->dec;
-    const int d = c.d_model, H = c.n_heads, Tk = c.n_audio_ctx;
+    const int d = c.d_model, H = c.n_heads;
+    int Tk = c.n_audio_ctx;
+    if (const char* e = getenv("WB_BENCH_TK")) Tk = std::max(1, std::min(Tk, atoi(e)));     // timing sweeps only (rows alias)
+    const bool bench_pdl = getenv("WB_BENCH_PDL") != nullptr;
     WB_REQUIRE(B >= 1 && B <= ctx->enc.B_valid, WB_ESTATE, "bench needs %d encoded sequences", B);
     const bool bf = c.precision == WB_PREC_BF16;
     const std::string k(kernel);
@@ -1400,9 +1411,9 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
     auto launch = [&](int i) {
         const int l = i % c.dec_layers;
         if (k == "cross_attn") {
-            const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * Tk * 2 * d * ctx->esz();
-            if (bf) cross_attn_kernel<bf16><<<dim3(H, B, XSPLIT), 256, 0, ctx->stream>>>(D.q.p, (const bf16*)ckv, D.att.p, D.xscratch.p, D.xcount.p, d, Tk);
-            else cross_attn_kernel<float><<<dim3(H, B, XSPLIT), 256, 0, ctx->stream>>>(D.q.p, (const float*)ckv, D.att.p, D.xscratch.p, D.xcount.p, d, Tk);
+            const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * c.n_audio_ctx * 2 * d * ctx->esz();
+            if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, D.xscratch.p, D.xcount.p, H, B, d, Tk);
+            else launch_cross_attn<float>(ctx->stream, bench_pdl, D.q.p, (const float*)ckv, D.att.p, D.xscratch.p, D.xcount.p, H, B, d, Tk);
         } else if (k == "vocab_proj") {
             LinearW dummy;
             if (bf) skinny<bf16>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
