@@ -46,8 +46,20 @@ def test_large_v3_widths_bf16_within_tolerance(wb, oracle, mel):
     enc = m.encode(mel)
     ref = oracle.encode(mel)
     assert np.linalg.norm(enc - ref) / np.linalg.norm(ref) <= 2e-2
-    toks = m.greedy_decode(2, [50258, 50259, 50360, 50364], 6, 50257)
+    prompt = [50258, 50259, 50360, 50364]
+    toks = m.greedy_decode(2, prompt, 6, 50257)
     assert all(len(t) == 10 for t in toks)
+    # teacher-forced on the oracle's own tokens: the tensor-core decode GEMMs of these widths (K = 1280 / 5120,
+    # LayerNorm over 1280, fused masked arg-max) against the fp32 oracle
+    rt, rl = oracle.greedy(ref, prompt, 6, 50257, return_logits=True)
+    forced = np.array([t[len(prompt):] for t in rt])
+    ft, lg = m.greedy_decode(2, prompt, 6, 50257, forced=forced, want_logits=True)
+    rl = np.stack(rl, 1)
+    assert np.abs(lg - rl).max() <= 3e-2 * max(1.0, np.abs(rl).max()), (np.abs(lg - rl).max(), np.abs(rl).max())
+    top2 = np.sort(rl, -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 0.1
+    got = np.array([t[len(prompt):] for t in ft])
+    assert np.all(got[clear] == forced[clear])
     with pytest.raises(wb.WbError, match="80-bin"):
         m.log_mel([np.zeros(16000, np.float32)])          # the reference has no 128-bin frontend
     m.close()

@@ -720,7 +720,7 @@ template <int MODE> __device__ __forceinline__ void stage_sync() {
 // One skinny GEMM "stage" executed by CTA `cta` of `ncta` cooperating CTAs (a whole grid, or one
 // thread-block cluster).  Activations are exchanged through global memory (L2): loads use ld.cg so a
 // value written by another CTA before the barrier is never served from a stale L1 line.
-template <int RW, int KS, int NCH, int MODE>       // NCH = 32-wide k chunks per warp = K / KS / 32
+template <int RW, int KS, int NCH, int NP, int MODE>   // K = KS slices x NP passes x NCH chunks of 32
 __device__ __forceinline__ void
 mma_stage(unsigned char* mm_smem, int cta, int ncta,
           const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
@@ -731,13 +731,14 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
           float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     static_assert(RW * KS == 8, "8 warps");
     const int xstride = K * 2 + 64;                                  // bytes per activation row
-    unsigned char* xs = mm_smem;                                     // [32][K] bf16 (padded rows)
-    float* part = reinterpret_cast<float*>(mm_smem + 32 * xstride);  // [KS][RW*16][33]
+    const int rows_st = ((B + 7) >> 3) << 3;                         // staged sequences: whole n-tiles of 8
+    unsigned char* xs = mm_smem;                                     // [rows_st][K] bf16 (padded rows)
+    float* part = reinterpret_cast<float*>(mm_smem + rows_st * xstride);  // [KS][RW*16][33]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int rt = warp / KS, ks = warp % KS;
     const int rows_cta = RW * 16;
     const int n_tiles = (N + rows_cta - 1) / rows_cta;
-    const int kbase = ks * NCH * 32;
+    const int kbase = ks * NP * NCH * 32;
     bool synced = false;
     float bestv[8];
     int besti[8];
@@ -764,6 +765,45 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             synced = true;
             if (amax_val) sup = (state[0] - (state[1] - 1) == 0) ? sup_first : sup_base;   // first generated token?
             // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
+            if (ln_w && K > 512) {
+                // wide rows (d_model 1280): one row at a time, the whole row in registers (K <= 1280)
+                constexpr int LNV = 10;
+                for (int bb = warp; bb < rows_st; bb += 8) {
+                    float4 xv[LNV];
+                    float s1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < LNV; ++i) {
+                        const int c = i * 128 + lane * 4;
+                        xv[i] = (bb < B && c < K) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)bb * K + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        s1 += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    const float mean = s1 / (float)K;
+                    float qq = 0.f;
+#pragma unroll
+                    for (int i = 0; i < LNV; ++i)
+                        if (i * 128 + lane * 4 < K) {
+                            const float t0 = xv[i].x - mean, t1 = xv[i].y - mean, t2 = xv[i].z - mean, t3 = xv[i].w - mean;
+                            qq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                        }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                    const float rs = 1.0f / sqrtf(qq / (float)K + 1e-5f);
+#pragma unroll
+                    for (int i = 0; i < LNV; ++i) {
+                        const int c = i * 128 + lane * 4;
+                        if (c < K) {
+                            const float4 gw = *reinterpret_cast<const float4*>(ln_w + c), gb = *reinterpret_cast<const float4*>(ln_b + c);
+                            uint2 pk;
+                            pk.x = pack_bf16((xv[i].x - mean) * rs * gw.x + gb.x, (xv[i].y - mean) * rs * gw.y + gb.y);
+                            pk.y = pack_bf16((xv[i].z - mean) * rs * gw.z + gb.z, (xv[i].w - mean) * rs * gw.w + gb.w);
+                            if (bb >= B) pk = make_uint2(0u, 0u);
+                            *reinterpret_cast<uint2*>(xs + bb * xstride + c * 2) = pk;
+                        }
+                    }
+                }
+            } else
             for (int k0 = 0; k0 < K; k0 += 512) {
                 const int kc = min(512, K - k0);
                 float4 xv[4][4];
@@ -777,7 +817,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                if (ln_w) {                                           // host guarantees K <= 512 here
+                if (ln_w) {                                           // K <= 512 here (wider rows took the branch above)
                     float4 gw[4], gb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -830,7 +870,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = i * 128 + lane * 4;
-                        if (c < kc) {
+                        if (c < kc && bb < rows_st) {
                             uint2 pk;
                             pk.x = pack_bf16(xv[rr][i].x, xv[rr][i].y);
                             pk.y = pack_bf16(xv[rr][i].z, xv[rr][i].w);
@@ -848,12 +888,32 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int p = 0; p < NP; ++p) {
+            uint4 na[NCH], nb[NCH];
+            if (p + 1 < NP) {                       // next pass of weight fragments leaves before this pass computes
+                const int r0 = min(n0 + g, N - 1), r1 = min(n0 + g + 8, N - 1);
+                const bf16* p0 = W + (size_t)r0 * K + kbase + (p + 1) * NCH * 32 + 8 * t;
+                const bf16* p1 = W + (size_t)r1 * K + kbase + (p + 1) * NCH * 32 + 8 * t;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const uint4 xb = *reinterpret_cast<const uint4*>(xs + (nt * 8 + g) * xstride + (kbase + c * 32 + 8 * t) * 2);
-                mma_bf16(acc[nt], wa[c].x, wb[c].x, wa[c].y, wb[c].y, xb.x, xb.y);
-                mma_bf16(acc[nt], wa[c].z, wb[c].z, wa[c].w, wb[c].w, xb.z, xb.w);
+                for (int c = 0; c < NCH; ++c) {
+                    na[c] = *reinterpret_cast<const uint4*>(p0 + c * 32);
+                    nb[c] = *reinterpret_cast<const uint4*>(p1 + c * 32);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    if (nt * 8 < rows_st) {
+                        const uint4 xb = *reinterpret_cast<const uint4*>(xs + (nt * 8 + g) * xstride + (kbase + (p * NCH + c) * 32 + 8 * t) * 2);
+                        mma_bf16(acc[nt], wa[c].x, wb[c].x, wa[c].y, wb[c].y, xb.x, xb.y);
+                        mma_bf16(acc[nt], wa[c].z, wb[c].z, wa[c].w, wb[c].w, xb.z, xb.w);
+                    }
+                }
+            }
+            if (p + 1 < NP) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) { wa[c] = na[c]; wb[c] = nb[c]; }
             }
         }
         // ---- combine k-slices, epilogue ----
@@ -911,7 +971,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
     }
     if (KS == 1 && amax_val) {
         // reduce over the 8 row lanes (g) that share a sequence, then over the 8 warps, one partial per CTA
-        float* sv = reinterpret_cast<float*>(mm_smem + 32 * xstride);      // [8 warps][32] (+ indices)
+        float* sv = reinterpret_cast<float*>(mm_smem + rows_st * xstride); // [8 warps][32] (+ indices)
         int* si = reinterpret_cast<int*>(sv + 8 * 32);
 #pragma unroll
         for (int slot = 0; slot < 8; ++slot) {
@@ -948,7 +1008,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
     if (!synced) stage_sync<MODE>();                // a CTA without tiles still takes part in the barrier
 }
 
-template <int RW, int KS, int NCH>
+template <int RW, int KS, int NCH, int NP>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -956,7 +1016,7 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                   const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
                   float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     extern __shared__ __align__(16) unsigned char mm_smem[];
-    mma_stage<RW, KS, NCH, SYNC_PDL>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
+    mma_stage<RW, KS, NCH, NP, SYNC_PDL>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
                                      state, sup_base, sup_first, amax_val, amax_idx);
 }
 
@@ -981,10 +1041,10 @@ __device__ __forceinline__ int cluster_size() { int r; asm volatile("mov.u32 %0,
 template <int MODE>
 __device__ __forceinline__ void chain_stage(unsigned char* smem, int cta, int ncta, const ChainStage& s, int B) {
     if (s.K == 512) {
-        if (s.N > 1024) mma_stage<4, 2, 8, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
-        else mma_stage<2, 4, 4, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (s.N > 1024) mma_stage<4, 2, 8, 1, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
+        else mma_stage<2, 4, 4, 1, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
     } else {    // K == 2048
-        mma_stage<2, 4, 16, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
+        mma_stage<2, 4, 16, 1, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
     }
 }
 
@@ -1000,14 +1060,16 @@ dec_chain_kernel(const ChainArgs a) {
     }
 }
 
-template <int RW, int KS, int NCH>
+template <int RW, int KS, int NCH, int NP = 1>
 void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
                        const float* lb, int act, const float* residual, float* Y, bool fused_argmax = false) {
-    const size_t smem = (size_t)32 * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * 33 : 8 * 32 * 8);
+    static_assert(RW * KS == 8, "8 warps");
+    WB_REQUIRE(K == KS * NP * NCH * 32, WB_EINVAL, "skinny_mma: K=%d does not match the <%d,%d,%d> instantiation", K, KS, NCH, NP);
+    const size_t smem = (size_t)(((B + 7) / 8) * 8) * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * 33 : 8 * 32 * 8);
     const int tiles = ceil_div(N, RW * 16);
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     DecBufs& D = ctx->dec;
-    launch_k(skinny_mma_kernel<RW, KS, NCH>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
+    launch_k(skinny_mma_kernel<RW, KS, NCH, NP>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
              act, residual, Y, (const int*)(fused_argmax ? D.amax_state : nullptr), (const unsigned*)D.sup_base.p,
              (const unsigned*)D.sup_first.p, fused_argmax ? D.amax_val : (float*)nullptr, fused_argmax ? D.amax_idx : (int*)nullptr);
     if (fused_argmax) D.amax_ctas = grid;
@@ -1021,7 +1083,17 @@ inline bool skinny_mma_enabled() {
 }
 inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
                        const float* lb, int act, const float* residual, float* Y) {
-    if (!skinny_mma_enabled() || B > 32 || (lw && K > 512)) return false;
+    if (!skinny_mma_enabled() || B > 32 || (lw && K > 1280)) return false;
+    if (K == 1280) {                               // large-v3 widths: d_model 1280 as the contraction
+        if (N >= 8192) { skinny_mma_launch<8, 1, 5, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, ctx->dec.amax_state != nullptr); return true; }
+        if (N >= 2560) { skinny_mma_launch<2, 4, 10>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // qkv / fc1
+        skinny_mma_launch<1, 8, 5>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true;                       // o / cq / co
+    }
+    if (K == 5120) {                               // large-v3 fc2: the staged rows fit shared memory up to 16 sequences
+        if (B > 16 || lw) return false;
+        skinny_mma_launch<1, 8, 5, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true;
+    }
+    if (lw && K > 512) return false;
     if (N >= 8192) {                               // vocabulary projection: 128 rows per CTA pass, grid-stride
         const bool fa = ctx->dec.amax_state != nullptr;
         if (K == 512) { skinny_mma_launch<8, 1, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
@@ -1039,14 +1111,18 @@ inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W,
     return false;
 }
 void skinny_mma_set_attrs() {       // once per process, outside any stream capture
-    const int smem = 32 * (2048 * 2 + 64) + (int)sizeof(float) * 8 * 16 * 33;
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = 16 * (5120 * 2 + 64) + (int)sizeof(float) * 8 * 16 * 33;      // largest: fc2 of the large-v3 widths
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
@@ -1167,7 +1243,7 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
         LinearW dummy;
         // bf16 build: arg-max partials are produced by the vocabulary projection itself (no logits round trip
         // unless the caller asked for logits); fp32 build: separate full arg-max over the logits.
-        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && c.vocab >= 8192 && (d == 512 || d == 128);   // shapes with an mma vocab kernel
+        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && c.vocab >= 8192 && (d == 512 || d == 128 || d == 1280);   // shapes with an mma vocab kernel
         D.amax_state = fuse ? state : nullptr;
         const int slice = (int)((long long)b0 * 4 / c.max_batch);           // up to 4 concurrent sub-batch chains
         D.amax_val = D.amax_buf.p + (size_t)slice * 64 * ctx->sm_count;      // per-chain slice: [ctas][32] val | idx
