@@ -44,3 +44,23 @@ def test_decode_shape_grid(wb, oracle, mel, precision):
     with pytest.raises(wb.WbError, match="exceeds max_batch"):
         m.encode(np.zeros((8, 80, 3000), np.float32))
     m.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cross_attention_cta_shapes_agree(wb, precision):
+    """8 heads x 40 sequences = 320 (b,h) pairs overflow one wave of 8-warp CTAs on 148 SMs, so the
+    cross-attention runs its 4-warp shape; the first 20 sequences decoded alone take the 8-warp shape.
+    Same keys, different merge order: fp32 logits agree to rounding.  (bf16: batches above 32 also leave the
+    tensor-core decode GEMMs for the SIMT ones, which keep fp32 activations, so only the bf16 tolerance holds.)"""
+    prec = wb.WB_PREC_FP32 if precision == "fp32" else wb.WB_PREC_BF16
+    B = 40
+    m = wb.Whisper(wb.default_cfg("base", precision=prec, max_batch=B, max_chunks=B))
+    mel = np.random.default_rng(5).normal(0.0, 0.6, (B, 80, 3000)).astype(np.float32)
+    m.encode(mel, want_hidden=False)
+    prompt = [50258, 50259, 50359, 50363]
+    forced = np.random.default_rng(6).integers(0, 50000, (B, 3))
+    _, big = m.greedy_decode(B, prompt, 3, 50257, forced=forced, want_logits=True)
+    _, small = m.greedy_decode(20, prompt, 3, 50257, forced=forced[:20], want_logits=True)
+    assert np.isfinite(big).all()
+    assert np.abs(big[:20] - small).max() <= (1e-4 if precision == "fp32" else 5e-2)
+    m.close()

@@ -341,13 +341,13 @@ template <> struct RowRaw<bf16> {
     }
 };
 
-template <typename KT>
-__global__ void __launch_bounds__(256)
+template <typename KT, int NW>          // NW warps per CTA: 8, or 4 when H*B would not fit one wave of 8-warp CTAs
+__global__ void __launch_bounds__(NW * 32)
 cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out,
                   float* __restrict__ scratch, int* __restrict__ counters, int d, int Tk) {
-    constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = 256 / LPR, UN = 4;
-    __shared__ float s_m[8], s_l[8];
-    __shared__ float s_acc[8][64];
+    constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = NW * 32 / LPR, UN = 4;
+    __shared__ float s_m[NW], s_l[NW];
+    __shared__ float s_acc[NW][64];
     __shared__ int s_last;
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, H = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -435,11 +435,11 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
     }
     __syncthreads();
     float my = 0.f, mt = -INFINITY, lt = 0.f;
-    if (tid < 64) {                                     // merge the 8 warps: thread <-> output dim
+    if (tid < 64) {                                     // merge the warps: thread <-> output dim
 #pragma unroll
-        for (int w = 0; w < 8; ++w) mt = fmaxf(mt, s_m[w]);
+        for (int w = 0; w < NW; ++w) mt = fmaxf(mt, s_m[w]);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < NW; ++w) {
             const float wgt = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - mt);
             my = fmaf(s_acc[w][tid], wgt, my);
             lt = fmaf(s_l[w], wgt, lt);
@@ -701,7 +701,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <typename WT>
 void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, float* scratch, int* counters,
                        int H, int B, int d, int Tk) {
-    launch_k(cross_attn_kernel<WT>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, q, ckv, att, scratch, counters, d, Tk);
+    // 8-warp CTAs hold 2 per SM (register file), 4-warp CTAs 4 per SM.  When the (b,h) pairs overflow one wave of
+    // 8-warp CTAs but fit one wave of 4-warp CTAs, the smaller shape keeps every pair streaming at once instead of
+    // leaving a few CTAs to run alone at the end (large-v3 widths at batch 16: 320 pairs on 148 SMs).
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int units = H * B * XSPLIT;
+    if (units > 2 * sms && units <= 4 * sms)
+        launch_k(cross_attn_kernel<WT, 4>, dim3(H, B, XSPLIT), dim3(128), 0, st, pdl, q, ckv, att, scratch, counters, d, Tk);
+    else
+        launch_k(cross_attn_kernel<WT, 8>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, q, ckv, att, scratch, counters, d, Tk);
 }
 
 constexpr int MM_THREADS = 256;
