@@ -64,6 +64,9 @@ int wb_default_cfg(wb_model_cfg* cfg, const char* name);
 int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* weights_path);
 void wb_destroy(wb_ctx* ctx);
 const char* wb_last_error(void);
+/* Number of CUDA devices visible to this process (the CLI's --gpus scheduler maps worker r to device
+ * (device + r) % count).  WB_ECUDA when there is none. */
+int wb_device_count(int* count_out);
 int wb_get_cfg(const wb_ctx* ctx, wb_model_cfg* out);
 int wb_get_timing(const wb_ctx* ctx, wb_timing* out);
 /* Debug/test: keep copies of encoder intermediates for wb_get_encoder_debug (also WB_DEBUG=1). */

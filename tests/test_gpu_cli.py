@@ -101,3 +101,46 @@ def test_cli_file_batch_gives_the_same_transcripts(wb, tmp_path):
         assert json.loads((out / "s.json").read_text())["n_files"] == 5
     assert texts[1] == texts[2] == texts[5]
     assert all(t.startswith("[TOKENS:") for _, t in texts[1])
+
+
+def test_cli_scheduler_gpus_and_in_flight_give_the_same_rows(wb, tmp_path):
+    """The batch scheduler (--gpus N: one worker process per GPU, rows gathered by the parent;
+    --in-flight S: S contexts per GPU) only changes WHERE a file group runs: file order, durations and
+    transcripts are those of the serial loop.  On a 1-GPU box the second worker shares device 0."""
+    audio, onnx = tmp_path / "audio", tmp_path / "onnx"
+    audio.mkdir(); onnx.mkdir()
+    secs = [3.0, 33.0, 9.5, 30.0, 12.0, 5.0, 41.0]
+    for i, sec in enumerate(secs):
+        wb.synth.write_wav(str(audio / f"f{i}.wav"), wb.synth.clip(i, 8, sec), fmt="s16")
+    rows = {}
+    for name, extra in (("serial", []), ("inflight", ["--in-flight", "3"]), ("gpus", ["--gpus", "2", "--file-batch", "2"]),
+                        ("both", ["--gpus", "2", "--in-flight", "2", "--warmup", "1"])):
+        out = tmp_path / name
+        r = subprocess.run([EXE, "--audio-dir", str(audio), "--onnx-dir", str(onnx), "--arch", "base", "--precision", "fp32",
+                            "--max-new-tokens", "5", "--batch", "4", "--write-txt", *extra,
+                            "--out-csv", str(out / "a.csv"), "--out-json", str(out / "a.json"), "--out-summary-json", str(out / "s.json")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.startswith("DONE\n")
+        got = json.loads((out / "a.json").read_text())
+        rows[name] = [(x["file"], x["duration_s"], x["text"]) for x in got]
+        summ = json.loads((out / "s.json").read_text())
+        assert summ["n_files"] == len(secs) and summ["latency_end_to_end_s"]["min"] > 0
+        assert sorted(p.name for p in out.iterdir() if p.name.endswith(".transcript.txt")) == [f"f{i}.transcript.txt" for i in range(len(secs))]
+        assert not [p for p in out.iterdir() if p.name.endswith(".rows")]          # worker hand-off files are removed
+    assert rows["serial"] == rows["inflight"] == rows["gpus"] == rows["both"]
+    assert [f for f, _, _ in rows["serial"]] == [f"f{i}.wav" for i in range(len(secs))]
+
+
+def test_cli_scheduler_worker_failure_fails_the_run(wb, tmp_path):
+    audio, onnx = tmp_path / "audio", tmp_path / "onnx"
+    audio.mkdir(); onnx.mkdir()
+    for i in range(3):
+        wb.synth.write_wav(str(audio / f"f{i}.wav"), wb.synth.clip(i, 8, 4.0), fmt="s16")
+    (audio / "f1.mp3").write_bytes(b"ID3 not really audio")
+    out = tmp_path / "out"
+    r = subprocess.run([EXE, "--audio-dir", str(audio), "--onnx-dir", str(onnx), "--arch", "base", "--gpus", "2",
+                        "--out-csv", str(out / "a.csv"), "--out-json", str(out / "a.json"), "--out-summary-json", str(out / "s.json")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 1 and "Error:" in r.stderr
+    assert not (out / "a.csv").exists()

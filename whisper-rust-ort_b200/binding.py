@@ -60,6 +60,7 @@ def lib():
         "wb_mark": [vp, ci],
         "wb_elapsed_ms": [vp, ci, ci, f32p],
         "wb_bench_kernel": [vp, cp, ci, ci, f32p, f64p],
+        "wb_device_count": [C.POINTER(ci)],
         "wb_get_tensor": [vp, cp, f32p, C.c_int64],
         "wb_log_mel": [vp, f32p, i64p, ci, C.c_int64, C.c_int64, f32p, i64p, C.POINTER(ci)],
         "wb_upload_pcm": [vp, f32p, i64p, ci, C.c_int64, C.c_int64, C.POINTER(ci)],

@@ -137,6 +137,19 @@ extern "C" {
 
 const char* wb_last_error(void) { return g_err.c_str(); }
 
+int wb_device_count(int* count_out) {
+    WB_TRY
+    WB_REQUIRE(count_out != nullptr, WB_EINVAL, "count_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        *count_out = 0;
+        WB_THROW(WB_ECUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    *count_out = n;
+    WB_CATCH
+}
+
 int wb_default_cfg(wb_model_cfg* cfg, const char* name) {
     WB_TRY
     WB_REQUIRE(cfg && name, WB_EINVAL, "wb_default_cfg: null argument");

@@ -1,16 +1,23 @@
 // cli.cpp — the drop-in command line (replaces Args + main of /root/reference/src/main.rs:23-86,
 // 1065-1271 and transcribe_longform_chunked :834-1008).  Same flags, same three output files, same
 // stdout lines; ORT-only knobs are accepted and echoed in `config_used` but have no effect.  The
-// per-file loop is kept serial like the reference (so per-file latency means the same thing); the
-// parallelism the reference gets from rayon over chunks is the GPU batch dimension here.
+// per-file loop is kept serial like the reference by default (so per-file latency means the same
+// thing); the parallelism the reference gets from rayon over chunks is the GPU batch dimension here.
+// Batch scheduler (BASELINE.json north_star (4)): --gpus N deals the file groups to N worker processes,
+// one per GPU (clips are independent: no collective, the parent gathers the per-file rows on the host);
+// --in-flight S keeps S groups in flight per GPU, each in its own wb_ctx (stream, caches, graphs).
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <dirent.h>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -48,6 +55,8 @@ struct Args {
     uint64_t seed = 0;
     int batch = 32;
     size_t file_batch = 1;      // files transcribed together (1 = the reference's serial per-file loop)
+    size_t gpus = 1;            // worker processes, one per GPU: devices device .. device+gpus-1
+    size_t in_flight = 1;       // file groups in flight per GPU (one wb_ctx each)
 };
 
 struct OrtCfg {      // main.rs:91-100 — echoed only
@@ -85,6 +94,8 @@ const char* USAGE =
     "      --device <N>  --precision <bf16|fp32>  --batch <N>  --weights <file.wb200>  --arch <base|large-v3|toy>  --seed <N>\n"
     "      --file-batch <N>               files whose chunks share GPU batches [default: 1 = serial like the reference];\n"
     "                                     every file of a group is charged the group's preprocess/model/decode time\n"
+    "      --gpus <N>                     shard the file groups over N GPUs, one worker process per GPU [default: 1]\n"
+    "      --in-flight <S>                file groups in flight per GPU, one context each [default: 1]\n"
     "  -h, --help\n";
 
 Args parse_args(int argc, const char* const* argv) {
@@ -140,6 +151,8 @@ Args parse_args(int argc, const char* const* argv) {
         else if (flag == "--seed") a.seed = to_usize(need(i, flag, iv, has_inline), flag);
         else if (flag == "--batch") a.batch = (int)to_usize(need(i, flag, iv, has_inline), flag);
         else if (flag == "--file-batch") a.file_batch = std::max<size_t>(1, to_usize(need(i, flag, iv, has_inline), flag));
+        else if (flag == "--gpus") a.gpus = std::max<size_t>(1, to_usize(need(i, flag, iv, has_inline), flag));
+        else if (flag == "--in-flight") a.in_flight = std::max<size_t>(1, to_usize(need(i, flag, iv, has_inline), flag));
         else throw UsageError("error: unexpected argument '" + tok + "' found");
     }
     return a;
@@ -362,6 +375,114 @@ std::vector<std::string> transcribe(wb_ctx* ctx, int max_batch, const std::vecto
     return full;
 }
 
+// ---- batch scheduler: groups of files -> worker contexts -> per-file results ----
+struct FileResult { bool done = false; double dur = 0, load_s = 0; Timing t; std::string text; };
+struct Job {            // shared, read-only
+    const Args& args;
+    const std::vector<std::string>& files;
+    const wb_tokenizer* tok;
+    const GenCfg& gen;
+    wb_model_cfg mc;
+    std::string wpath;
+};
+struct Pcm {
+    float* p = nullptr; int64_t n = 0; double dur = 0;
+    Pcm() = default; Pcm(const Pcm&) = delete; Pcm& operator=(const Pcm&) = delete;
+    ~Pcm() { wb_host_free(p); }
+};
+
+// One worker = one wb_ctx on `device`: warm up like main.rs:1131-1152, then take groups off the cursor.
+void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, size_t>>& groups, size_t rank, size_t world,
+                std::atomic<size_t>& cursor, std::vector<FileResult>& out) {
+    const Args& args = J.args;
+    wb_ctx* ctx = nullptr;
+    CK(wb_create(&ctx, device, &J.mc, J.wpath.empty() ? nullptr : J.wpath.c_str()));
+    struct Guard { wb_ctx* c; ~Guard() { wb_destroy(c); } } guard{ctx};
+    if (args.warmup > 0) {
+        Pcm a0;
+        CK(wb_host_load_audio_16k_mono(join(args.audio_dir, J.files[0]).c_str(), &a0.p, &a0.n, &a0.dur));
+        WB_REQUIRE(a0.n > 0, WB_EINVAL, "Empty audio");
+        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, J.mc.max_batch, {FilePcm{a0.p, a0.n}}, args, J.tok, J.gen, t); }
+    }
+    for (;;) {
+        const size_t k = cursor.fetch_add(1);                 // k-th group of this rank
+        const size_t g = rank + k * world;
+        if (g >= groups.size()) break;
+        const size_t g0 = groups[g].first, g1 = groups[g].second;
+        std::vector<Pcm> au(g1 - g0);
+        std::vector<double> load_s(g1 - g0);
+        std::vector<FilePcm> group;
+        for (size_t i = g0; i < g1; ++i) {
+            auto tl0 = Clock::now();
+            Pcm& p = au[i - g0];
+            CK(wb_host_load_audio_16k_mono(join(args.audio_dir, J.files[i]).c_str(), &p.p, &p.n, &p.dur));
+            load_s[i - g0] = since(tl0);
+            WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
+            group.push_back(FilePcm{p.p, p.n});
+        }
+        Timing t;
+        std::vector<std::string> texts = transcribe(ctx, J.mc.max_batch, group, args, J.tok, J.gen, t);
+        for (size_t i = g0; i < g1; ++i) {
+            FileResult& fr = out[i];
+            fr.dur = au[i - g0].dur; fr.load_s = load_s[i - g0]; fr.t = t; fr.text = texts[i - g0];
+            fr.done = true;
+        }
+    }
+}
+
+// All groups of one rank (= one GPU), `in_flight` workers at a time.  Files stay in listing order inside a
+// worker, so --in-flight 1 is the reference's serial loop.
+void run_rank(const Job& J, int device, const std::vector<std::pair<size_t, size_t>>& groups, size_t rank, size_t world,
+              std::vector<FileResult>& out) {
+    std::atomic<size_t> cursor{0};
+    const size_t mine = groups.size() > rank ? (groups.size() - rank + world - 1) / world : 0;
+    const size_t n_workers = std::max<size_t>(1, std::min(J.args.in_flight, mine));
+    if (n_workers == 1) { run_worker(J, device, groups, rank, world, cursor, out); return; }
+    std::mutex mu;
+    std::string first_error;
+    std::vector<std::thread> th;
+    for (size_t w = 0; w < n_workers; ++w)
+        th.emplace_back([&] {
+            try { run_worker(J, device, groups, rank, world, cursor, out); }
+            catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (first_error.empty()) first_error = e.what();
+                cursor.store(groups.size());                  // stop handing out work
+            }
+        });
+    for (auto& t : th) t.join();
+    if (!first_error.empty()) WB_THROW(WB_ESTATE, "%s", first_error.c_str());
+}
+
+// rows of one worker process, one JSON object per line (f64 printed shortest-round-trip, so nothing is lost)
+void write_rows(const std::string& path, const std::vector<FileResult>& rs) {
+    std::string s;
+    for (size_t i = 0; i < rs.size(); ++i) {
+        if (!rs[i].done) continue;
+        const FileResult& r = rs[i];
+        s += "{\"i\": " + std::to_string(i) + ", \"dur\": " + wbjson::fmt_f64(r.dur) + ", \"load\": " + wbjson::fmt_f64(r.load_s) +
+             ", \"pre\": " + wbjson::fmt_f64(r.t.preprocess_s) + ", \"model\": " + wbjson::fmt_f64(r.t.model_only_s) +
+             ", \"dec\": " + wbjson::fmt_f64(r.t.decode_s) + ", \"e2e\": " + wbjson::fmt_f64(r.t.end_to_end_s) +
+             ", \"text\": " + wbjson::escape(r.text) + "}\n";
+    }
+    write_file(path, s);
+}
+void read_rows(const std::string& path, std::vector<FileResult>& rs) {
+    std::istringstream in(read_file(path));
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        wbjson::Value v = wbjson::parse(line);
+        const size_t i = (size_t)v["i"].num();
+        WB_REQUIRE(i < rs.size(), WB_ESTATE, "worker row %zu out of range", i);
+        FileResult& r = rs[i];
+        r.dur = v["dur"].num(); r.load_s = v["load"].num();
+        r.t.preprocess_s = v["pre"].num(); r.t.model_only_s = v["model"].num(); r.t.decode_s = v["dec"].num(); r.t.end_to_end_s = v["e2e"].num();
+        r.text = v["text"].str();
+        r.done = true;
+    }
+}
+
 std::string stat_json(const std::vector<double>& xs, int indent) {                  // keys sorted (serde_json BTreeMap)
     double o[6];
     wb_host_stat_block(xs.data(), (int)xs.size(), o);
@@ -414,10 +535,6 @@ int run(const Args& args) {
     mc.max_batch = std::max(1, args.batch);
     mc.max_chunks = std::max(1024, mc.max_batch);
     mc.seed = args.seed;
-    wb_ctx* ctx = nullptr;
-    CK(wb_create(&ctx, args.device, &mc, wpath.empty() ? nullptr : wpath.c_str()));
-    struct Guard { wb_ctx* c; ~Guard() { wb_destroy(c); } } guard{ctx};
-
     // list audio files (main.rs:1111-1128)
     std::vector<std::string> files;
     DIR* d = ::opendir(args.audio_dir.c_str());
@@ -434,50 +551,73 @@ int run(const Args& args) {
     if (args.limit_files > 0 && files.size() > args.limit_files) files.resize(args.limit_files);
     WB_REQUIRE(!files.empty(), WB_EINVAL, "No audio files found in %s", args.audio_dir.c_str());
 
-    struct Pcm { float* p = nullptr; int64_t n = 0; double dur = 0; Pcm() = default; Pcm(const Pcm&) = delete; Pcm& operator=(const Pcm&) = delete; ~Pcm() { wb_host_free(p); } };
-    if (args.warmup > 0) {                                                           // main.rs:1131-1152
-        Pcm a0;
-        CK(wb_host_load_audio_16k_mono(join(args.audio_dir, files[0]).c_str(), &a0.p, &a0.n, &a0.dur));
-        WB_REQUIRE(a0.n > 0, WB_EINVAL, "Empty audio");
-        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, mc.max_batch, {FilePcm{a0.p, a0.n}}, args, tk.t, gen, t); }
+    // file groups in listing order; group g belongs to worker process g % gpus
+    std::vector<std::pair<size_t, size_t>> groups;
+    for (size_t g0 = 0; g0 < files.size(); g0 += args.file_batch) groups.push_back({g0, std::min(files.size(), g0 + args.file_batch)});
+    const size_t world = std::min(args.gpus, groups.size());
+    const Job job{args, files, tk.t, gen, mc, wpath};
+    std::vector<FileResult> results(files.size());
+    if (world <= 1) {
+        run_rank(job, args.device, groups, 0, 1, results);
+    } else {
+        // one process per GPU.  The parent has not touched CUDA, so a plain fork() is safe; every child
+        // creates its own contexts on its own device and hands its rows back through a file.
+        fflush(stdout); fflush(stderr);
+        std::vector<pid_t> pids(world);
+        std::vector<std::string> row_files(world);
+        for (size_t r = 0; r < world; ++r) {
+            row_files[r] = args.out_csv + ".rank" + std::to_string(r) + ".rows";
+            pid_t pid = ::fork();
+            WB_REQUIRE(pid >= 0, WB_EIO, "fork failed for worker %zu", r);
+            if (pid == 0) {
+                int rc = 1;
+                try {
+                    int n_dev = 0;
+                    CK(wb_device_count(&n_dev));
+                    const int dev = (args.device + (int)r) % n_dev;
+                    if (args.device + (int)r >= n_dev)
+                        fprintf(stderr, "note: worker %zu shares GPU %d (%d visible, --gpus %zu)\n", r, dev, n_dev, args.gpus);
+                    run_rank(job, dev, groups, r, world, results);
+                    write_rows(row_files[r], results);
+                    rc = 0;
+                } catch (const std::exception& e) {
+                    fprintf(stderr, "Error: [gpu %d] %s\n", args.device + (int)r, e.what());
+                }
+                fflush(stdout); fflush(stderr);
+                ::_exit(rc);
+            }
+            pids[r] = pid;
+        }
+        bool ok = true;
+        for (size_t r = 0; r < world; ++r) {
+            int st = 0;
+            if (::waitpid(pids[r], &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) ok = false;
+        }
+        if (ok) for (size_t r = 0; r < world; ++r) read_rows(row_files[r], results);
+        for (size_t r = 0; r < world; ++r) ::unlink(row_files[r].c_str());
+        WB_REQUIRE(ok, WB_ESTATE, "a GPU worker process failed");
     }
 
     struct Row { std::string file; double duration_s, end_to_end_s, rtf; std::string text; };
     std::vector<Row> rows;
     std::vector<double> e2e, load, pre, model, dec, rtfs;
     const std::string txt_dir = parent_of(args.out_csv);
-    for (size_t g0 = 0; g0 < files.size(); g0 += args.file_batch) {                  // main.rs:1164-1213
-        const size_t g1 = std::min(files.size(), g0 + args.file_batch);
-        std::vector<Pcm> au(g1 - g0);
-        std::vector<double> load_s(g1 - g0);
-        std::vector<FilePcm> group;
-        for (size_t i = g0; i < g1; ++i) {
-            auto tl0 = Clock::now();
-            Pcm& p = au[i - g0];
-            CK(wb_host_load_audio_16k_mono(join(args.audio_dir, files[i]).c_str(), &p.p, &p.n, &p.dur));
-            load_s[i - g0] = since(tl0);
-            WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
-            group.push_back(FilePcm{p.p, p.n});
-        }
-        Timing t;
-        std::vector<std::string> texts = transcribe(ctx, mc.max_batch, group, args, tk.t, gen, t);
-        for (size_t i = g0; i < g1; ++i) {
-            const std::string& fnm = files[i];
-            const std::string& text = texts[i - g0];
-            const double dur = au[i - g0].dur;
-            const double end_to_end_s = load_s[i - g0] + t.end_to_end_s;
-            const double rtf = end_to_end_s / std::max(dur, 1e-9);
-            rows.push_back(Row{fnm, std::round(dur * 1000.0) / 1000.0, std::round(end_to_end_s * 10000.0) / 10000.0,
-                               std::round(rtf * 1000000.0) / 1000000.0, text});
-            load.push_back(load_s[i - g0]); pre.push_back(t.preprocess_s); model.push_back(t.model_only_s); dec.push_back(t.decode_s);
-            e2e.push_back(end_to_end_s); rtfs.push_back(rtf);
-            if (args.write_txt) {
-                size_t dot = fnm.find_last_of('.');
-                std::string stem = dot == std::string::npos ? fnm : fnm.substr(0, dot);
-                size_t b = text.find_first_not_of(" \t\r\n"), e = text.find_last_not_of(" \t\r\n");
-                std::string trimmed = b == std::string::npos ? "" : text.substr(b, e - b + 1);
-                write_file(join(txt_dir, stem + ".transcript.txt"), trimmed + "\n");
-            }
+    for (size_t i = 0; i < files.size(); ++i) {                                      // main.rs:1164-1213
+        const FileResult& fr = results[i];
+        WB_REQUIRE(fr.done, WB_ESTATE, "no result for %s", files[i].c_str());
+        const std::string& fnm = files[i];
+        const double end_to_end_s = fr.load_s + fr.t.end_to_end_s;
+        const double rtf = end_to_end_s / std::max(fr.dur, 1e-9);
+        rows.push_back(Row{fnm, std::round(fr.dur * 1000.0) / 1000.0, std::round(end_to_end_s * 10000.0) / 10000.0,
+                           std::round(rtf * 1000000.0) / 1000000.0, fr.text});
+        load.push_back(fr.load_s); pre.push_back(fr.t.preprocess_s); model.push_back(fr.t.model_only_s); dec.push_back(fr.t.decode_s);
+        e2e.push_back(end_to_end_s); rtfs.push_back(rtf);
+        if (args.write_txt) {
+            size_t dot = fnm.find_last_of('.');
+            std::string stem = dot == std::string::npos ? fnm : fnm.substr(0, dot);
+            size_t b = fr.text.find_first_not_of(" \t\r\n"), e = fr.text.find_last_not_of(" \t\r\n");
+            std::string trimmed = b == std::string::npos ? "" : fr.text.substr(b, e - b + 1);
+            write_file(join(txt_dir, stem + ".transcript.txt"), trimmed + "\n");
         }
     }
 
