@@ -81,6 +81,37 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s for a kernel timed inside a long step (the sustained figure)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 2250.0, "fallback (nominal dense bf16 2.25 PFLOP/s)"
+
+
+# algorithmic work per 30 s clip of whisper-base (DESIGN.md section 4): encoder flops incl. conv stem and attention;
+# log-mel bytes = f32 PCM in + f32 log-mel out; decode bytes per step = cached cross K/V of the sequence
+ENC_FLOP_PER_CLIP = 87.368e9
+MEL_BYTES_PER_CLIP = 30 * 16000 * 4 + 80 * 3000 * 4
+DEC_WEIGHT_PARAMS = 6 * 14 * 512 * 512 + 51865 * 512          # 6 layers x (qkv 3 + o + cq + co + fc 8) d^2 + tied vocab projection
+
+
+def stage_rooflines(tm, B, esz, hbm_peak, tc_peak):
+    """north_star: each stage as a fraction of its roofline (HBM for log-mel and decode, tensor peak for the encoder),
+    from the stage times of one batch alone on the GPU."""
+    steps = len(PROMPT) + MAX_NEW - 1
+    dec_bytes = steps * (B * 6 * 2 * 1500 * 512 * esz + DEC_WEIGHT_PARAMS * esz)
+    mel = B * MEL_BYTES_PER_CLIP / (tm["mel_ms"] * 1e-3) / 1e9
+    enc = B * ENC_FLOP_PER_CLIP / (tm["encoder_ms"] * 1e-3) / 1e12
+    dec = dec_bytes / (tm["decode_ms"] * 1e-3) / 1e9
+    return {"log_mel": {"bound": "hbm", "achieved": mel, "unit": "GB/s", "frac": mel / hbm_peak},
+            "encoder": {"bound": "tensor", "achieved": enc, "unit": "TFLOP/s", "frac": enc / tc_peak},
+            "decode": {"bound": "hbm", "achieved": dec, "unit": "GB/s", "frac": dec / hbm_peak,
+                       "bytes_per_step": dec_bytes / steps, "ms_per_step": tm["decode_ms"] / steps}}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -293,6 +324,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches_per_step * args.steps),
             "wall_s": wall,
             "stage_ms_per_step_under_load": stage,
+            "stage_rooflines_single_batch": stage_rooflines(tm1, B, 2 if args.precision == "bf16" else 4, peak, measured_tensor_peak()[0]),
             "clocks": clocks,
             "roofline": {"kernel": "cross_attn_kernel (decoder cross-attention over cached encoder K/V)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -95,6 +95,54 @@ __device__ __forceinline__ constexpr uint32_t idesc_of(int n, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+
+// Softmax halves of one key block for one query row (thread): 64 scores in two tcgen05.ld chunks of 32.
+// MASK = the ragged last block (keys >= valid do not exist); full blocks carry no per-score predicate.
+template <bool MASK>
+__device__ __forceinline__ float row_max64(uint32_t taddr, int half, int valid) {
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; ++c2) {
+        const int ch = half * 2 + c2;
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (!MASK || ch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
+    return mx;
+}
+template <bool MASK>
+__device__ __forceinline__ float exp_store64(uint32_t taddr, int half, int valid, float sc, float m_new, uint8_t* prow, int sw) {
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; ++c2) {
+        const int ch = half * 2 + c2;
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), sc, -m_new));
+            float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), sc, -m_new));
+            if (MASK) {
+                if (ch * 32 + 2 * i >= valid) p0 = 0.f;
+                if (ch * 32 + 2 * i + 1 >= valid) p1 = 0.f;
+            }
+            sum0 += p0;
+            sum1 += p1;
+            __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                            // 32 keys = chunks c2*4 .. c2*4+3 of this half
+            const int chunk = c2 * 4 + c;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+    }
+    return sum0 + sum1;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int d, int H, int n_qb) {
     extern __shared__ uint8_t smem_raw[];
@@ -213,44 +261,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             mbar_wait(bar_s, (uint32_t)(j & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int valid = T - j * AK;                                // keys of this block that exist
-            // pass 1: maximum over this thread's 64 keys, then over the row
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c2 = 0; c2 < 2; ++c2) {
-                const int ch = half * 2 + c2;
-                uint32_t r[32];
-                tmem_ld32(tS + lane_off + ch * 32, r);
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (ch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-            }
+            // pass 1: maximum over this thread's 64 keys, then over the row (only the last key block is ragged)
+            const bool full = valid >= AK;
+            const float mx_own = full ? row_max64<false>(tS + lane_off, half, valid) : row_max64<true>(tS + lane_off, half, valid);
+            float mx = mx_own;
             s_xmax[j & 1][half][row] = mx;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");    // the two warps of this quadrant
             mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]);
             const float m_new = fmaxf(m, mx * sc);
             const float alpha = ex2(m - m_new);                          // 0 on the first block (m = -inf)
-            // pass 2: p = exp2(s*sc - m_new) -> bf16 -> swizzled smem; partial row sum of the rounded values
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c2 = 0; c2 < 2; ++c2) {
-                const int ch = half * 2 + c2;
-                uint32_t r[32];
-                tmem_ld32(tS + lane_off + ch * 32, r);
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = (ch * 32 + 2 * i < valid) ? ex2(fmaf(__uint_as_float(r[2 * i]), sc, -m_new)) : 0.f;
-                    float p1 = (ch * 32 + 2 * i + 1 < valid) ? ex2(fmaf(__uint_as_float(r[2 * i + 1]), sc, -m_new)) : 0.f;
-                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                    sum += __low2float(pb) + __high2float(pb);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&pb);
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {                            // 32 keys = chunks c2*4 .. c2*4+3 of this half
-                    const int chunk = c2 * 4 + c;
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                }
-            }
+            // pass 2: p = exp2(s*sc - m_new) -> bf16 -> swizzled smem; partial row sum in f32
+            const float sum = full ? exp_store64<false>(tS + lane_off, half, valid, sc, m_new, prow, sw)
+                                   : exp_store64<true>(tS + lane_off, half, valid, sc, m_new, prow, sw);
             l = l * alpha + sum;
             m = m_new;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor core
