@@ -270,6 +270,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]);
             const float m_new = fmaxf(m, mx * sc);
             const float alpha = ex2(m - m_new);                          // 0 on the first block (m = -inf)
+            // P is single-buffered and S_j was issued BEFORE P_{j-1} V_{j-1}: bar_s(j) does not imply that the tensor
+            // core is done reading P_{j-1}.  Wait for that MMA (bar_o) before overwriting P -- normally long complete.
+            if (j > 0) mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
             // pass 2: p = exp2(s*sc - m_new) -> bf16 -> swizzled smem; partial row sum in f32
             const float sum = full ? exp_store64<false>(tS + lane_off, half, valid, sc, m_new, prow, sw)
                                    : exp_store64<true>(tS + lane_off, half, valid, sc, m_new, prow, sw);
@@ -277,7 +280,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
             m = m_new;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor core
             if (j > 0) {                                                   // fold in O_{j-1} (own 32 columns), then rescale
-                mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t r[32];
                 tmem_ld32(tO + lane_off + half * 32, r);
