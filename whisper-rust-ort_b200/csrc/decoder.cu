@@ -774,7 +774,8 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             synced = true;
             if (amax_val) sup = (state[0] - (state[1] - 1) == 0) ? sup_first : sup_base;   // first generated token?
             // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
-            if (ln_w && K > 512) {
+            constexpr int KT = KS * NP * NCH * 32;                   // == K (checked at launch): prunes the unused LayerNorm path
+            if (KT > 512 && ln_w) {
                 // wide rows (d_model 1280): one row at a time, the whole row in registers (K <= 1280)
                 constexpr int LNV = 10;
                 for (int bb = warp; bb < rows_st; bb += 8) {
@@ -826,7 +827,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                if (ln_w) {                                           // K <= 512 here (wider rows took the branch above)
+                if (KT <= 512 && ln_w) {                              // wider rows took the branch above
                     float4 gw[4], gb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
