@@ -40,3 +40,32 @@ def test_contexts_in_flight_match_a_solo_run(wb):
         assert len(got[i]) == 4
         for g in got[i]:
             assert g == want
+
+
+def test_contexts_created_while_others_capture_and_decode(wb):
+    """What the CLI's --in-flight workers do: every thread creates ITS OWN context and starts right away, so one
+    thread's wb_create (allocation, uploads) overlaps another's first decode (CUDA-graph capture).  Nothing on
+    that path may be a device-wide operation (cudaDeviceSynchronize is illegal while any stream captures)."""
+    B, S, n_new = 8, 4, 6
+    pcm = wb.synth.batch(B, seed=43, seconds=30.0)
+    out, errs = [None] * S, []
+
+    def work(i):
+        try:
+            for rep in range(2):               # second round: fresh contexts while the others are mid-flight
+                m = wb.Whisper(wb.default_cfg("base", precision=wb.WB_PREC_BF16, max_batch=B, max_chunks=B))
+                for n in (n_new, n_new + 1 + i):          # a second shape = a second capture later on
+                    r = m.transcribe_batch(list(pcm), PROMPT, n, EOT)[0]
+                    if n == n_new:
+                        out[i] = r
+                m.close()
+        except Exception as e:
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(S)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert all(o == out[0] for o in out)

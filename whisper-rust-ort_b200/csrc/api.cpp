@@ -4,6 +4,7 @@
 #include <cstring>
 #include <mutex>
 
+#include <chrono>
 #include "ctx.h"
 
 static thread_local std::string g_err;
@@ -184,15 +185,32 @@ int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* wei
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        // WB_TRACE_CREATE=1: where context creation spends its time (stderr)
+        const bool tr = getenv("WB_TRACE_CREATE") != nullptr;
+        auto t_last = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!tr) return;
+            auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[wb_create dev %d] %-14s %.3f s\n", device, what, std::chrono::duration<double>(now - t_last).count());
+            t_last = now;
+        };
+        lap("cuda init");
         mel_build_tables(ctx->mel_tables);
         CUDA_CHECK(cudaMalloc(&ctx->mel_tables_dev, sizeof(MelTables)));
         CUDA_CHECK(cudaMemcpy(ctx->mel_tables_dev, &ctx->mel_tables, sizeof(MelTables), cudaMemcpyHostToDevice));
+        lap("mel tables");
         weights_init(ctx, weights_path);
+        lap("weights");
         encoder_alloc(ctx);
+        lap("encoder alloc");
         decoder_alloc(ctx);
+        lap("decoder alloc");
         const char* dbg = getenv("WB_DEBUG");
         ctx->debug = dbg && dbg[0] == '1';
-        CUDA_CHECK(cudaDeviceSynchronize());
+        // not cudaDeviceSynchronize(): another context of this process may be capturing its decode graph on this
+        // device right now, and a device-wide sync is illegal while any stream captures
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
         *out = ctx;
         return WB_OK;
     } catch (const WbError& e) {
@@ -209,7 +227,9 @@ int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* wei
 void wb_destroy(wb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);          // own work only (see wb_create)
+    for (int k = 0; k < 3; ++k)
+        if (ctx->dec.side[k]) cudaStreamSynchronize(ctx->dec.side[k]);
     weights_free(ctx);
     for (auto& g : ctx->dec.graphs) cudaGraphExecDestroy(g.exec);
     if (ctx->dec.unfinished_host) cudaFreeHost(ctx->dec.unfinished_host);
@@ -372,8 +392,9 @@ int wb_set_debug(wb_ctx* ctx, int on) {
 int wb_get_tensor(wb_ctx* ctx, const char* name, float* out, int64_t n) {
     WB_TRY
     require_ctx(ctx);
-    auto it = ctx->w.host.find(name ? name : "");
-    WB_REQUIRE(it != ctx->w.host.end(), WB_EINVAL, "unknown tensor '%s'", name ? name : "");
+    WB_REQUIRE(ctx->w.store != nullptr, WB_ESTATE, "context has no weights");
+    auto it = ctx->w.store->host.find(name ? name : "");
+    WB_REQUIRE(it != ctx->w.store->host.end(), WB_EINVAL, "unknown tensor '%s'", name ? name : "");
     WB_REQUIRE((int64_t)it->second.size() == n, WB_EINVAL, "tensor '%s' has %zu elements, caller asked for %lld",
                name, it->second.size(), (long long)n);
     std::memcpy(out, it->second.data(), sizeof(float) * (size_t)n);

@@ -62,6 +62,7 @@ struct DevBuf {
         if (n <= cap) return;
         reserve(n);
         CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+        CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));      // the users run on non-blocking streams
     }
 };
 

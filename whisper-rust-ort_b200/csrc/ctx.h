@@ -3,6 +3,7 @@
 #pragma once
 #include <cmath>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -61,8 +62,17 @@ struct ModelW {
     float* dec_pos = nullptr;      // [n_text_ctx][d] f32
     std::vector<DecLayerW> dec;
     LNW dec_ln;
+    std::shared_ptr<struct WeightStore> store;        // owns the device allocations + f32 originals; shared by every
+                                                      // context of the process with the same device/source/config
+};
+// One uploaded copy of a model per (device, source, architecture, precision): contexts in flight on a GPU read
+// the same weights (read-only during runs), so the second and later wb_create skip generation/parse + upload.
+struct WeightStore {
+    int device = 0;
     std::vector<void*> allocs;
     std::map<std::string, std::vector<float>> host;   // f32 originals by HF name
+    ModelW view;                                      // the pointer table (view.store stays empty)
+    ~WeightStore();
 };
 
 // ---------------- activations ----------------

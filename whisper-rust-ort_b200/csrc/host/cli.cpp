@@ -35,6 +35,18 @@ namespace {
 using Clock = std::chrono::steady_clock;
 double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
 
+// WB_CLI_TRACE=1: milestones with seconds since process start on stderr (where does a run spend its wall clock?)
+const Clock::time_point g_t0 = Clock::now();
+bool trace_on() { static const bool on = std::getenv("WB_CLI_TRACE") != nullptr; return on; }
+#define TRACE(...)                                                        \
+    do {                                                                  \
+        if (trace_on()) {                                                 \
+            fprintf(stderr, "[trace %8.3f s] ", since(g_t0));             \
+            fprintf(stderr, __VA_ARGS__);                                 \
+            fputc('\n', stderr);                                          \
+        }                                                                 \
+    } while (0)
+
 struct Args {
     std::string audio_dir = "audio", model_id = "openai/whisper-base", onnx_dir = "whisper-base-with-past";
     std::string language = "en", task = "transcribe";
@@ -396,13 +408,16 @@ void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, si
                 std::atomic<size_t>& cursor, std::vector<FileResult>& out) {
     const Args& args = J.args;
     wb_ctx* ctx = nullptr;
+    TRACE("worker on gpu %d: creating context", device);
     CK(wb_create(&ctx, device, &J.mc, J.wpath.empty() ? nullptr : J.wpath.c_str()));
     struct Guard { wb_ctx* c; ~Guard() { wb_destroy(c); } } guard{ctx};
+    TRACE("worker on gpu %d: context ready", device);
     if (args.warmup > 0) {
         Pcm a0;
         CK(wb_host_load_audio_16k_mono(join(args.audio_dir, J.files[0]).c_str(), &a0.p, &a0.n, &a0.dur));
         WB_REQUIRE(a0.n > 0, WB_EINVAL, "Empty audio");
         for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, J.mc.max_batch, {FilePcm{a0.p, a0.n}}, args, J.tok, J.gen, t); }
+        TRACE("worker on gpu %d: warm-up done", device);
     }
     for (;;) {
         const size_t k = cursor.fetch_add(1);                 // k-th group of this rank
@@ -422,6 +437,8 @@ void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, si
         }
         Timing t;
         std::vector<std::string> texts = transcribe(ctx, J.mc.max_batch, group, args, J.tok, J.gen, t);
+        TRACE("gpu %d: group %zu (%zu files) load %.3f s, preprocess %.3f s, model %.3f s, detokenise %.3f s", device, g, g1 - g0,
+              [&] { double a = 0; for (double x : load_s) a += x; return a; }(), t.preprocess_s, t.model_only_s, t.decode_s);
         for (size_t i = g0; i < g1; ++i) {
             FileResult& fr = out[i];
             fr.dur = au[i - g0].dur; fr.load_s = load_s[i - g0]; fr.t = t; fr.text = texts[i - g0];
@@ -556,6 +573,7 @@ int run(const Args& args) {
     for (size_t g0 = 0; g0 < files.size(); g0 += args.file_batch) groups.push_back({g0, std::min(files.size(), g0 + args.file_batch)});
     const size_t world = std::min(args.gpus, groups.size());
     const Job job{args, files, tk.t, gen, mc, wpath};
+    TRACE("%zu files in %zu groups, %zu worker process(es) x %zu in flight", files.size(), groups.size(), world, args.in_flight);
     std::vector<FileResult> results(files.size());
     if (world <= 1) {
         run_rank(job, args.device, groups, 0, 1, results);
@@ -598,6 +616,7 @@ int run(const Args& args) {
         WB_REQUIRE(ok, WB_ESTATE, "a GPU worker process failed");
     }
 
+    TRACE("all groups done");
     struct Row { std::string file; double duration_s, end_to_end_s, rtf; std::string text; };
     std::vector<Row> rows;
     std::vector<double> e2e, load, pre, model, dec, rtfs;
@@ -674,6 +693,7 @@ int run(const Args& args) {
     sum += "  \"tokenizer_json\": " + wbjson::escape(tk.path) + "\n}";
     write_file(args.out_summary_json, sum);
 
+    TRACE("outputs written");
     printf("DONE\n");                                                                // main.rs:1261-1268
     printf("Config used:\n%s\n", cfg_json(cfg, 0).c_str());
     printf("Per-file CSV: %s\n", args.out_csv.c_str());

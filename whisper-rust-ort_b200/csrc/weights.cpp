@@ -6,6 +6,7 @@
 // same integer hash, one f32 multiply + one f32 add) so host oracle and device agree bit-for-bit.
 #include <cstring>
 #include <fstream>
+#include <mutex>
 
 #include <sys/stat.h>
 
@@ -154,7 +155,7 @@ struct Uploader {
     float* f32(const std::vector<float>& v) {
         float* p = nullptr;
         CUDA_CHECK(cudaMalloc(&p, v.size() * sizeof(float)));
-        ctx->w.allocs.push_back(p);
+        ctx->w.store->allocs.push_back(p);
         CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
         return p;
     }
@@ -164,7 +165,7 @@ struct Uploader {
         for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
         void* p = nullptr;
         CUDA_CHECK(cudaMalloc(&p, h.size() * 2));
-        ctx->w.allocs.push_back(p);
+        ctx->w.store->allocs.push_back(p);
         CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
         return p;
     }
@@ -172,10 +173,63 @@ struct Uploader {
 
 }  // namespace
 
+WeightStore::~WeightStore() {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    for (void* p : allocs) cudaFree(p);
+    cudaSetDevice(prev);
+}
+
+namespace {
+std::mutex g_store_mu;
+std::map<std::string, std::weak_ptr<WeightStore>> g_stores;
+
+// identity of an uploaded model: device, precision, architecture, and the source (seed, or path + mtime + size)
+std::string store_key(const wb_ctx* ctx, const char* path) {
+    const wb_model_cfg& c = ctx->cfg;
+    char b[512];
+    snprintf(b, sizeof(b), "dev%d|p%d|%d.%d.%d.%d.%d.%d.%d.%d.%d|", ctx->device, c.precision, c.n_mels, c.d_model, c.n_heads, c.ffn_dim,
+             c.enc_layers, c.dec_layers, c.vocab, c.n_audio_ctx, c.n_text_ctx);
+    std::string k = b;
+    struct stat st;
+    if (path && path[0]) {
+        k += std::string("path:") + path;
+        if (::stat(path, &st) == 0) k += "|" + std::to_string((long long)st.st_mtime) + "|" + std::to_string((long long)st.st_size);
+    } else {
+        k += "seed:" + std::to_string((unsigned long long)c.seed);
+    }
+    return k;
+}
+void weights_build(wb_ctx* ctx, const char* path);
+}  // namespace
+
 void weights_init(wb_ctx* ctx, const char* path) {
+    // creation is serialised: the first context of a (device, source) builds and uploads, the others wait and share
+    std::lock_guard<std::mutex> lk(g_store_mu);
+    const std::string key = store_key(ctx, path);
+    auto it = g_stores.find(key);
+    if (it != g_stores.end()) {
+        if (std::shared_ptr<WeightStore> st = it->second.lock()) {
+            ctx->w = st->view;
+            ctx->w.store = st;
+            return;
+        }
+    }
+    ctx->w = ModelW{};
+    ctx->w.store = std::make_shared<WeightStore>();
+    ctx->w.store->device = ctx->device;
+    weights_build(ctx, path);
+    ctx->w.store->view = ctx->w;
+    ctx->w.store->view.store.reset();
+    g_stores[key] = ctx->w.store;
+}
+
+namespace {
+void weights_build(wb_ctx* ctx, const char* path) {
     const wb_model_cfg& c = ctx->cfg;
     auto specs = tensor_specs(c);
-    auto& host = ctx->w.host;
+    auto& host = ctx->w.store->host;
     struct stat st;
     if (path && path[0] && ::stat(path, &st) == 0 && S_ISDIR(st.st_mode)) {
         onnx_load_dir(path, c, host);                       // optimum export: encoder_model.onnx + decoder_model.onnx
@@ -273,7 +327,8 @@ void weights_init(wb_ctx* ctx, const char* path) {
     m.dec_ln = lnw(dd + ".layer_norm");
 }
 
+}  // namespace
+
 void weights_free(wb_ctx* ctx) {
-    for (void* p : ctx->w.allocs) cudaFree(p);
-    ctx->w.allocs.clear();
+    ctx->w = ModelW{};          // the store frees the device copy when its last context goes
 }
