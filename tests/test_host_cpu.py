@@ -85,9 +85,13 @@ def test_linear_resample_to_16k(wb, L, tmp_path, sr):
 
 
 def test_unsupported_audio_is_an_error(wb, L, tmp_path):
+    # FLAC: symphonia decodes it to S32, which the reference's match rejects (main.rs:303) -- same message here
     (tmp_path / "x.flac").write_bytes(b"fLaC" + b"\0" * 64)
-    with pytest.raises(RuntimeError, match="unsupported audio container"):
+    with pytest.raises(RuntimeError, match="Unsupported decoded sample format"):
         load_audio(L, tmp_path / "x.flac")
+    (tmp_path / "x.mp3").write_bytes(b"ID3" + b"\0" * 64)
+    with pytest.raises(RuntimeError, match="unsupported audio container"):
+        load_audio(L, tmp_path / "x.mp3")
     with pytest.raises(RuntimeError, match="Failed to open audio"):
         load_audio(L, tmp_path / "missing.wav")
     # 24-bit PCM decodes to S24 in symphonia, which the reference rejects (main.rs:303)

@@ -1,7 +1,8 @@
 // audio.cpp — host-side audio ingest (replaces load_audio_16k_mono + resample_linear,
-// /root/reference/src/main.rs:207-316, which sit on the symphonia crate).  RIFF/WAVE only: the
-// image has no offline flac/mp3 decoder, so those containers are reported as unsupported
-// (the reference would decode them; SURVEY.md §8f3 ranks that "next").
+// /root/reference/src/main.rs:207-316, which sit on the symphonia crate).  RIFF/WAVE in the sample
+// formats the reference accepts (U8 / S16 / F32; its match bails on S24 / S32 / F64, and so on every FLAC
+// file, which symphonia decodes to S32).  MP3 is the one container the reference reads and this does
+// not (no decoder offline; SURVEY.md §8f3 ranks that "next"): reported as unsupported.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,6 +54,9 @@ void load_wav(const char* path, std::vector<float>& mono, uint32_t& sr) {
     size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
     std::fclose(f);
     WB_REQUIRE(got == buf.size() && buf.size() >= 12, WB_EIO, "short read: %s", path);
+    // FLAC: symphonia's FLAC decoder hands back S32 buffers, which the reference's match rejects (main.rs:265-303,
+    // `_ => bail!`), so a faithful drop-in fails on .flac too -- with the reference's own message.
+    if (std::memcmp(buf.data(), "fLaC", 4) == 0) WB_THROW(WB_EINVAL, "Unsupported decoded sample format");
     if (std::memcmp(buf.data(), "RIFF", 4) != 0 || std::memcmp(buf.data() + 8, "WAVE", 4) != 0)
         WB_THROW(WB_EINVAL, "unsupported audio container (only RIFF/WAVE is decodable offline): %s", path);
     int fmt_tag = 0, channels = 0, bits = 0;
