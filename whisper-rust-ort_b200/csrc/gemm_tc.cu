@@ -20,7 +20,8 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 5, UMMA_K = 16;
 constexpr int TC_THREADS = 320;                              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
 constexpr uint32_t STAGE_A = BM * BK * 2, STAGE_B = BN * BK * 2;
 constexpr uint32_t TMEM_COLS = 256;                          // 2 accumulators x 128 fp32 columns
-constexpr size_t TC_SMEM = (size_t)STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t STAGE_C = BM * 64 * 2;                    // one 64-column half of a bf16 output tile (TMA-store staging)
+constexpr size_t TC_SMEM = (size_t)STAGES * (STAGE_A + STAGE_B) + 2 * STAGE_C + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcArgs {
     void* C;
@@ -33,6 +34,7 @@ struct TcArgs {
     int ld_rowadd;
     const float* residual;
     int tiles_m, tiles_n, num_tiles, num_kb;
+    int tma_store;              // bf16 output without residual: tiles leave through shared memory + TMA (coalesced)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,13 +122,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);          // SWIZZLE_128B wants 1024-byte alignment
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * STAGE_A;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (STAGE_A + STAGE_B));
+    uint8_t* sC = smem + STAGES * (STAGE_A + STAGE_B);                    // 2 x [128 rows][128 B], 128B-swizzled
+    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * STAGE_C);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -207,6 +211,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int gm = mb * BM + row_in_tile;
             const bool row_ok = gm < a.M;
             const long long crow = (long long)z * a.sC + (long long)gm * a.ldc;
+            if (a.tma_store) {
+                // bf16 tile out through shared memory: a thread owns one row x 64 columns = eight 16-byte chunks, written
+                // in the 128B-swizzle pattern (conflict-free), then one TMA store per 128x64 half; rows >= M are clipped
+                // by the tensor map.  Replaces 32 scattered 16-byte global stores per warp instruction.
+                uint32_t pk[32];
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const int ch = chalf * 2 + c2;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(q * 32) << 16), r);
+                    const int gn0 = nb * BN + ch * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (a.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + gn0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(bp + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
+                    }
+                    if (a.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                    }
+                    if (a.rowadd && row_ok) {
+                        const float4* p = reinterpret_cast<const float4*>(a.rowadd + (long long)gm * a.ld_rowadd + gn0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(p + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 pb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        pk[c2 * 16 + j] = *reinterpret_cast<unsigned*>(&pb);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&tempty[acc]);                                // values are in registers: release the accumulator
+                const bool issuer = ((warp - 2) & 3) == 0 && lane == 0;   // one thread per column half
+                uint8_t* sCh = sC + chalf * STAGE_C;
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left the staging
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
+                {
+                    uint8_t* prow = sCh + row_in_tile * 128;
+                    const int sw = row_in_tile & 7;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
+                if (issuer) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(sCh)), "r"(nb * BN + chalf * 64), "r"(mb * BM), "r"(z)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
                 uint32_t r[32];
@@ -263,6 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty[acc]);                                    // 256 arrivals release the accumulator
         }
+        if (a.tma_store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its last store
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -298,6 +360,12 @@ void make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
 
 }  // namespace
 
+bool tma_store_enabled() {                          // WB_TC_TMA_STORE=0: direct global stores from the epilogue warps
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("WB_TC_TMA_STORE"); enabled = !(e && e[0] == '0'); }
+    return enabled != 0;
+}
+
 bool gemm_tc_eligible(const GemmArgs& g) {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("WB_TC"); enabled = !(e && e[0] == '0'); }
@@ -312,7 +380,8 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
         CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         attr = true;
     }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
+    const bool tma_store = g.tc == WB_BF16 && g.residual == nullptr && tma_store_enabled();
     {
         cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, (cuuint64_t)g.batch};
         cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)(g.batch > 1 ? g.sAo : (long long)g.M * g.lda) * 2};
@@ -325,12 +394,21 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
         cuuint32_t box[2] = {BK, BN};
         make_map(&tmB, g.B, 2, dims, str, box);
     }
+    if (tma_store) {
+        cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)g.M, (cuuint64_t)g.batch};
+        cuuint64_t str[2] = {(cuuint64_t)g.ldc * 2, (cuuint64_t)(g.batch > 1 ? g.sCo : (long long)g.M * g.ldc) * 2};
+        cuuint32_t box[3] = {64, BM, 1};
+        make_map(&tmC, g.C, 3, dims, str, box);
+    } else {
+        tmC = tmA;                                  // unused
+    }
     TcArgs a{};
+    a.tma_store = tma_store ? 1 : 0;
     a.C = g.C; a.tc = g.tc; a.M = g.M; a.N = g.N; a.K = g.K; a.ldc = g.ldc; a.sC = g.sCo;
     a.bias = g.bias; a.act = g.act; a.rowadd = g.rowadd; a.ld_rowadd = g.ld_rowadd; a.residual = g.residual;
     a.tiles_m = ceil_div(g.M, BM); a.tiles_n = g.N / BN; a.num_tiles = a.tiles_m * a.tiles_n * g.batch;
     a.num_kb = ceil_div(g.K, BK);
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(tmA, tmB, a);
+    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(tmA, tmB, tmC, a);
     CUDA_CHECK(cudaGetLastError());
 }
