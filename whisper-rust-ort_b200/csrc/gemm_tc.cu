@@ -16,12 +16,20 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 5, UMMA_K = 16;
+// Output tile 128 x BN with BN = 128 or 256.  The encoder GEMMs run at the L2 -> SM throughput cap with 128x128
+// tiles (ncu: 10.7-13.7 TB/s of TMA reads, profiles/r1_gemm_tc_v5_raw.csv), so the wider tile is the lever: per
+// k-block it loads 16 KB of A + 32 KB of B for twice the flops (87 instead of 64 flop per byte from L2).
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int TC_THREADS = 320;                              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
-constexpr uint32_t STAGE_A = BM * BK * 2, STAGE_B = BN * BK * 2;
-constexpr uint32_t TMEM_COLS = 256;                          // 2 accumulators x 128 fp32 columns
-constexpr uint32_t STAGE_C = BM * 64 * 2;                    // one 64-column half of a bf16 output tile (TMA-store staging)
-constexpr size_t TC_SMEM = (size_t)STAGES * (STAGE_A + STAGE_B) + 2 * STAGE_C + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t STAGE_A = BM * BK * 2;
+constexpr uint32_t STAGE_C = BM * 64 * 2;                    // one 128 x 64 bf16 sub-tile (TMA-store staging)
+template <int BN> struct TileCfg {
+    static constexpr int STAGES = BN == 128 ? 5 : 3;         // 160 KB / 144 KB of operands in flight
+    static constexpr uint32_t STAGE_B = BN * BK * 2;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;            // 2 accumulators x BN fp32 columns
+    static constexpr int SUB = BN / 128;                     // 64-column staging sub-tiles per column half
+    static constexpr size_t SMEM = (size_t)STAGES * (STAGE_A + STAGE_B) + 2 * SUB * STAGE_C + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct TcArgs {
     void* C;
@@ -81,7 +89,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -121,16 +130,19 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);          // SWIZZLE_128B wants 1024-byte alignment
+    constexpr int STAGES = TileCfg<BN>::STAGES, SUB = TileCfg<BN>::SUB, NCH = BN / 64;   // NCH: 32-column chunks per thread
+    constexpr uint32_t STAGE_B = TileCfg<BN>::STAGE_B, TMEM_COLS = TileCfg<BN>::TMEM_COLS;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * STAGE_A;
-    uint8_t* sC = smem + STAGES * (STAGE_A + STAGE_B);                    // 2 x [128 rows][128 B], 128B-swizzled
-    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * STAGE_C);
+    uint8_t* sC = smem + STAGES * (STAGE_A + STAGE_B);                    // 2*SUB x [128 rows][128 B], 128B-swizzled
+    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * SUB * STAGE_C);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -172,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc = make_idesc<BN>();
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -215,61 +227,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // bf16 tile out through shared memory: a thread owns one row x 64 columns = eight 16-byte chunks, written
                 // in the 128B-swizzle pattern (conflict-free), then one TMA store per 128x64 half; rows >= M are clipped
                 // by the tensor map.  Replaces 32 scattered 16-byte global stores per warp instruction.
-                uint32_t pk[32];
-#pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const int ch = chalf * 2 + c2;
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(q * 32) << 16), r);
-                    const int gn0 = nb * BN + ch * 32;
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (a.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(a.bias + gn0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(bp + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
-                    }
-                    if (a.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-                    }
-                    if (a.rowadd && row_ok) {
-                        const float4* p = reinterpret_cast<const float4*>(a.rowadd + (long long)gm * a.ld_rowadd + gn0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(p + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat162 pb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        pk[c2 * 16 + j] = *reinterpret_cast<unsigned*>(&pb);
-                    }
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&tempty[acc]);                                // values are in registers: release the accumulator
                 const bool issuer = ((warp - 2) & 3) == 0 && lane == 0;   // one thread per column half
-                uint8_t* sCh = sC + chalf * STAGE_C;
+                uint8_t* sCh = sC + chalf * SUB * STAGE_C;
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left the staging
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
-                {
-                    uint8_t* prow = sCh + row_in_tile * 128;
+#pragma unroll 1
+                for (int sub = 0; sub < SUB; ++sub) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int ch = chalf * NCH + sub * 2 + c2;
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(q * 32) << 16), r);
+                        const int gn0 = nb * BN + ch * 32;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (a.bias) {
+                            const float4* bp = reinterpret_cast<const float4*>(a.bias + gn0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(bp + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
+                        }
+                        if (a.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                        }
+                        if (a.rowadd && row_ok) {
+                            const float4* p = reinterpret_cast<const float4*>(a.rowadd + (long long)gm * a.ld_rowadd + gn0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(p + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat162 pb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            pk[c2 * 16 + j] = *reinterpret_cast<unsigned*>(&pb);
+                        }
+                    }
+                    uint8_t* prow = sCh + sub * STAGE_C + row_in_tile * 128;
                     const int sw = row_in_tile & 7;
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&tempty[acc]);                                // accumulator drained
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
                 if (issuer) {
-                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(sCh)), "r"(nb * BN + chalf * 64), "r"(mb * BM), "r"(z)
-                                 : "memory");
+#pragma unroll
+                    for (int sub = 0; sub < SUB; ++sub)
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(sCh + sub * STAGE_C)),
+                                       "r"(nb * BN + chalf * (BN / 2) + sub * 64), "r"(mb * BM), "r"(z)
+                                     : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 continue;
             }
 #pragma unroll 1
-            for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
+            for (int ch = chalf * NCH; ch < (chalf + 1) * NCH; ++ch) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(q * 32) << 16), r);
                 const int gn0 = nb * BN + ch * 32;
@@ -369,7 +385,7 @@ bool tma_store_enabled() {                          // WB_TC_TMA_STORE=0: direct
 bool gemm_tc_eligible(const GemmArgs& g) {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("WB_TC"); enabled = !(e && e[0] == '0'); }
-    return enabled && g.ta == WB_BF16 && g.tb == WB_BF16 && !g.b_kn && g.alpha == 1.0f && g.N % BN == 0 && g.K % 8 == 0 &&
+    return enabled && g.ta == WB_BF16 && g.tb == WB_BF16 && !g.b_kn && g.alpha == 1.0f && g.N % 128 == 0 && g.K % 8 == 0 &&
            g.lda % 8 == 0 && g.ldb % 8 == 0 && g.ldc % 8 == 0 && g.sAi == 0 && g.sBo == 0 && g.sBi == 0 && g.sCi == 0 &&
            (g.batch == 1 || (g.sAo % 8 == 0 && g.inner <= 1)) && (g.ld_rowadd % 4 == 0);
 }
@@ -377,9 +393,13 @@ bool gemm_tc_eligible(const GemmArgs& g) {
 void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
     static bool attr = false;
     if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128>::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<256>::SMEM));
         attr = true;
     }
+    static int wide = -1;                           // WB_TC_BN256=0: 128-wide tiles everywhere
+    if (wide < 0) { const char* e = getenv("WB_TC_BN256"); wide = !(e && e[0] == '0'); }
+    const int BN = (wide && g.N % 256 == 0) ? 256 : 128;
     CUtensorMap tmA, tmB, tmC;
     const bool tma_store = g.tc == WB_BF16 && g.residual == nullptr && tma_store_enabled();
     {
@@ -391,7 +411,7 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.N};
         cuuint64_t str[1] = {(cuuint64_t)g.ldb * 2};
-        cuuint32_t box[2] = {BK, BN};
+        cuuint32_t box[2] = {BK, (cuuint32_t)BN};
         make_map(&tmB, g.B, 2, dims, str, box);
     }
     if (tma_store) {
@@ -409,6 +429,7 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
     a.tiles_m = ceil_div(g.M, BM); a.tiles_n = g.N / BN; a.num_tiles = a.tiles_m * a.tiles_n * g.batch;
     a.num_kb = ceil_div(g.K, BK);
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(tmA, tmB, tmC, a);
+    if (BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, TileCfg<256>::SMEM, ctx->stream>>>(tmA, tmB, tmC, a);
+    else gemm_tc_kernel<128><<<grid, TC_THREADS, TileCfg<128>::SMEM, ctx->stream>>>(tmA, tmB, tmC, a);
     CUDA_CHECK(cudaGetLastError());
 }
