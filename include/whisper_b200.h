@@ -147,6 +147,10 @@ int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* av
  * |difference| and the largest |SIMT value| (flags bit0: f32 output instead of bf16). */
 int wb_selftest_gemm(wb_ctx* ctx, int M, int N, int K, int lda, int batch, int flags, float* max_diff_out, float* max_abs_out);
 
+/* Test hook (host only, no GPU): the 400-point FFT data flow of the log-mel kernel (20 x 20 four-step, the same
+ * mel_math.h code the device runs) on one complex input of 400 points. */
+int wb_selftest_fft400(const float* re, const float* im, float* out_re, float* out_im);
+
 /* Test hook (bf16 build): seeded q|k|v for B clips through the tcgen05 attention kernel and the
  * SIMT attention path; returns the largest |difference| and the largest |SIMT value|. */
 int wb_selftest_attn(wb_ctx* ctx, int B, float* max_diff_out, float* max_abs_out);

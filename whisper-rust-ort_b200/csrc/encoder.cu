@@ -10,10 +10,6 @@
 
 namespace {
 
-template <typename T> __device__ __forceinline__ void put(T* p, float v);
-template <> __device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
-
 constexpr int LN_MAX_VEC = 10;        // float4 per lane: d_model <= 1280
 
 __device__ __forceinline__ void put4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
