@@ -6,6 +6,11 @@
 // the CPU (wb_selftest_fft400) before it ever meets a GPU.
 // Replaces rustfft's 400-point plan (reference call sites /root/reference/src/main.rs:440-441,473).
 #pragma once
+#ifdef __CUDA_ARCH__
+#define WB_UNROLL _Pragma("unroll")
+#else
+#define WB_UNROLL            /* host build of the same code (wb_selftest_fft400) */
+#endif
 #ifdef __CUDACC__
 #define WB_HD __host__ __device__ __forceinline__
 #else
@@ -66,7 +71,7 @@ WB_HD c32 w20(int j) {
 WB_HD void dft20(c32 (&v)[20]) {
     // n = 5a + b ; k = c + 4e
     c32 u[5][4];
-#pragma unroll
+WB_UNROLL
     for (int b = 0; b < 5; ++b) {
         c32 a0 = v[b], a1 = v[5 + b], a2 = v[10 + b], a3 = v[15 + b];
         dft4(a0, a1, a2, a3);
@@ -75,7 +80,7 @@ WB_HD void dft20(c32 (&v)[20]) {
         u[b][2] = (b == 0) ? a2 : cmul(a2, w20(b * 2));
         u[b][3] = (b == 0) ? a3 : cmul(a3, w20(b * 3));
     }
-#pragma unroll
+WB_UNROLL
     for (int c = 0; c < 4; ++c) {
         c32 y0 = u[0][c], y1 = u[1][c], y2 = u[2][c], y3 = u[3][c], y4 = u[4][c];
         dft5(y0, y1, y2, y3, y4);
