@@ -399,7 +399,9 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
     }
     static int wide = -1;                           // WB_TC_BN256=0: 128-wide tiles everywhere
     if (wide < 0) { const char* e = getenv("WB_TC_BN256"); wide = !(e && e[0] == '0'); }
-    const int BN = (wide && g.N % 256 == 0) ? 256 : 128;
+    // wide tiles where there are enough of them: at N = 512 the 128x256 grid is 5.07 waves of 148 CTAs and the
+    // out-projection got slower under ncu (81 -> 89 us), fc2 unchanged; N >= 1024 gained 25-40 % (qkv 111 -> 77 us)
+    const int BN = (wide && g.N % 256 == 0 && g.N >= 1024) ? 256 : 128;
     CUtensorMap tmA, tmB, tmC;
     const bool tma_store = g.tc == WB_BF16 && g.residual == nullptr && tma_store_enabled();
     {
