@@ -220,3 +220,43 @@ def test_cli_early_errors_mirror_anyhow(tmp_path):
     assert (tmp_path / "o").is_dir()                                       # parents are created first (main.rs:1069-1071)
     r = run_cli("--tokenizer-json", str(tmp_path / "tok.json"), "--onnx-dir", str(tmp_path), *out)
     assert r.returncode == 1 and "tokenizer_json not found" in r.stderr
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_cli_scheduler_flags_and_file_listing_errors(wb, tmp_path):
+    r = run_cli("--help")
+    for flag in ("--file-batch", "--gpus", "--in-flight", "--device", "--precision", "--batch", "--weights", "--arch", "--seed"):
+        assert flag in r.stdout, flag
+    assert run_cli("--gpus", "x").returncode == 2 and run_cli("--in-flight").returncode == 2
+    out = ["--out-csv", str(tmp_path / "o/a.csv"), "--out-json", str(tmp_path / "o/a.json"), "--out-summary-json", str(tmp_path / "o/s.json")]
+    onnx, audio = tmp_path / "onnx", tmp_path / "audio"
+    onnx.mkdir(); audio.mkdir()
+    r = run_cli("--onnx-dir", str(onnx), "--audio-dir", str(tmp_path / "missing"), *out)
+    assert r.returncode == 1 and "cannot read audio dir" in r.stderr
+    (audio / "notes.txt").write_text("not audio")
+    r = run_cli("--onnx-dir", str(onnx), "--audio-dir", str(audio), *out)
+    assert r.returncode == 1 and "No audio files found" in r.stderr             # main.rs:1126-1128
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the loud failure of a box WITHOUT a GPU")
+def test_cli_without_a_gpu_fails_loudly_in_both_scheduler_modes(wb, tmp_path):
+    """No CPU fallback: the serial path dies in wb_create, the --gpus path in its worker processes (the parent then
+    fails the run and removes the workers' hand-off files)."""
+    onnx, audio = tmp_path / "onnx", tmp_path / "audio"
+    onnx.mkdir(); audio.mkdir()
+    for i in range(3):
+        wb.synth.write_wav(str(audio / f"f{i}.wav"), wb.synth.clip(i, 8, 1.0), fmt="s16")
+    for extra, msg in (([], "no CPU fallback"), (["--gpus", "2"], "a GPU worker process failed")):
+        out_dir = tmp_path / ("o" + str(len(extra)))
+        r = run_cli("--onnx-dir", str(onnx), "--audio-dir", str(audio), "--arch", "toy", *extra,
+                    "--out-csv", str(out_dir / "a.csv"), "--out-json", str(out_dir / "a.json"), "--out-summary-json", str(out_dir / "s.json"))
+        assert r.returncode == 1 and msg in r.stderr, r.stderr
+        assert not (out_dir / "a.csv").exists()
+        assert not [p for p in out_dir.iterdir() if p.name.endswith(".rows")]
