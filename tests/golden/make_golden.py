@@ -115,6 +115,31 @@ def main():
             margin=(top2[..., 1] - top2[..., 0]).astype(np.float32))
         print(tag, "tokens", toks[0][:12], "min margin", float((top2[..., 1] - top2[..., 0]).min()))
 
+    # ---- whisper-large-v3 WIDTHS (128 mels, d=1280, 20 heads, ffn 5120, vocab 51866) on 2+2 layers: BASELINE.json
+    # configs[4] shapes at a depth the CPU finishes in seconds.  No 128-bin frontend exists in the reference, so the
+    # input is a seeded random log-mel (the same one tests/test_gpu_wide.py feeds the GPU). ----
+    import dataclasses
+    cfg = dataclasses.replace(weights.WHISPER_LARGE_V3, enc_layers=2, dec_layers=2)
+    W = weights.generate(cfg, seed=0)
+    m = hf_model(cfg, W)
+    mel = torch.from_numpy(np.random.default_rng(3).normal(0.0, 0.5, (2, 128, 3000)).astype(np.float32)[:1])
+    with torch.no_grad():
+        eo = m.model.encoder(mel, output_hidden_states=True)
+    enc = eo.last_hidden_state
+    prompt = [50258, 50259, 50360, 50364]
+    toks, logits = hf_greedy(m, enc, prompt, 6, [], [])
+    lg = np.stack(logits, 1)
+    top2 = np.sort(lg, -1)[..., -2:]
+    np.savez_compressed(
+        os.path.join(HERE, "hf_whisper_wide_seed0.npz"),
+        rows=np.arange(0, cfg.n_audio_ctx, 50),
+        stem=eo.hidden_states[0][:, ::50].numpy().astype(np.float32),
+        enc=enc[:, ::50].numpy().astype(np.float32),
+        tokens=np.asarray(toks, dtype=np.int64), prompt=np.asarray(prompt, dtype=np.int64),
+        logit_cols=np.arange(0, cfg.vocab, 97), logits=lg[:, :, ::97].astype(np.float32),
+        margin=(top2[..., 1] - top2[..., 0]).astype(np.float32))
+    print("wide tokens", toks[0], "min margin", float((top2[..., 1] - top2[..., 0]).min()))
+
 
 if __name__ == "__main__":
     main()

@@ -73,6 +73,23 @@ def test_whisper_oracle_matches_hf_golden(wb, golden_dir, tag):
     assert np.abs(np.stack(lg, 1)[:, :, g["logit_cols"]] - g["logits"]).max() <= 2e-5
 
 
+def test_whisper_oracle_matches_hf_golden_at_large_v3_widths(wb, golden_dir):
+    """BASELINE.json configs[4] shapes (128 mels, d=1280, 20 heads, ffn 5120, vocab 51866) on 2+2 layers: pins the
+    oracle that tests/test_gpu_wide.py holds the GPU against (same seeded weights, same random log-mel)."""
+    import dataclasses
+    cfg = dataclasses.replace(wb.weights.WHISPER_LARGE_V3, enc_layers=2, dec_layers=2)
+    g = np.load(f"{golden_dir}/hf_whisper_wide_seed0.npz")
+    m = wr.WhisperRef(cfg, wb.weights.generate(cfg, 0))
+    mel = np.random.default_rng(3).normal(0.0, 0.5, (2, 128, 3000)).astype(np.float32)[:1]
+    enc, layers = m.encode(mel, return_layers=True)
+    assert np.abs(layers[0][:, g["rows"]] - g["stem"]).max() <= 3e-5
+    assert np.abs(enc[:, g["rows"]] - g["enc"]).max() <= 5e-5
+    steps = g["tokens"].shape[1] - len(g["prompt"])
+    toks, lg = m.greedy(enc, g["prompt"], steps, 50257, return_logits=True)
+    assert np.array_equal(np.array(toks), g["tokens"])
+    assert np.abs(np.stack(lg, 1)[:, :, g["logit_cols"]] - g["logits"]).max() <= 5e-5
+
+
 def test_greedy_loop_control_matches_reference_quirks(wb):
     cfg = wb.weights.WHISPER_TOY
     m = wr.WhisperRef(cfg, wb.weights.generate(cfg, 0))
