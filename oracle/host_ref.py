@@ -91,8 +91,11 @@ def percentile(xs, p: float) -> float:
 def stat_block(xs) -> dict:
     """main.rs:1033-1048 (median = upper median)."""
     v = sorted(xs)
+    total = 0.0
+    for x in v:                 # Rust's iter().sum::<f64>() is a plain left-to-right fold over the SORTED values;
+        total += x              # Python >= 3.12 sum() is Neumaier-compensated and can differ in the last bit
     return {"min": v[0], "median": v[len(v) // 2], "p90": percentile(xs, 90.0), "p95": percentile(xs, 95.0),
-            "max": v[-1], "mean": sum(v) / len(v)}
+            "max": v[-1], "mean": total / len(v)}
 
 
 def special_tokens(language: str, task: str, token_to_id=None):
