@@ -170,6 +170,10 @@ int64_t wb_host_stitch_texts(const char* const* chunks, int n, char* out, int64_
 /* percentile / stat_block (main.rs:1021-1048): out6 = {min, median, p90, p95, max, mean}. */
 double wb_host_percentile(const double* xs, int n, double p);
 int wb_host_stat_block(const double* xs, int n, double* out6);
+/* How the output files print an f64 (serde_json = ryu's shortest round-trip digits in its "pretty" layout:
+ * "14.884440201999999", "1.0", "0.000482736", "4.82e-6", "1e16", non-finite -> "null"; main.rs:1232-1259).
+ * Returns the needed length (excluding NUL), writes up to cap bytes. */
+int64_t wb_host_format_f64(double v, char* out, int64_t cap);
 
 /* tokenizer.json reader + byte-level BPE id->text decoder (replaces the `tokenizers` crate uses:
  * Tokenizer::from_file main.rs:580, token_to_id :531, decode(ids, skip_special=true) :640). */

@@ -75,3 +75,52 @@ def test_resample_matches_oracle(L, n, sr, seed):
     out = np.zeros(max(m, 1), np.float32)
     L.wb_host_resample_linear(x.ctypes.data_as(f32p), n, sr, 16000, out.ctypes.data_as(f32p), m)
     assert np.array_equal(out[:m], ref)
+
+
+# ---------------- f64 formatting of the output files (serde_json / ryu) ----------------
+def fmt(L, v):
+    L.wb_host_format_f64.argtypes = [C.c_double, C.c_char_p, C.c_int64]
+    L.wb_host_format_f64.restype = C.c_int64
+    buf = C.create_string_buffer(64)
+    n = L.wb_host_format_f64(v, buf, 64)
+    assert n == len(buf.value)
+    return buf.value.decode()
+
+
+# every float the reference's Rust binary wrote into its committed result files
+# (/root/reference/results.old/**/without_hf_pipeline_rust*/*.json), as printed by serde_json
+RUST_PRINTED = ['7.2111', '9.1312', '14.8844', '17.0939', '301.574', '0.023911', '0.030278', '0.049356', '0.056682', '0.2028574',
+                '0.42281892', '0.68677424', '8.65831095', '0.000482736', '0.000507354', '0.000559743', '0.000967648', '0.048492999',
+                '0.053896242', '0.271739968', '0.412314905', '0.647183284', '6.741848167', '9.131170268', '14.031795815',
+                '16.130229141', '17.093930471', '14.884440201999999', '7.2110552420000005', '0.04935592882663761',
+                '0.05668246868839603', '0.023911435328369368', '0.030278423893346063']
+# ryu's documented layout switches
+RYU_LAYOUT = [(1.0, "1.0"), (0.0, "0.0"), (-0.0, "-0.0"), (1e16, "1e16"), (1e15, "1000000000000000.0"),
+              (123456789012345680.0, "1.2345678901234568e17"), (0.1 + 0.2, "0.30000000000000004"), (1e-5, "0.00001"), (1e-6, "1e-6"),
+              (4.82e-6, "4.82e-6"), (0.0000482, "0.0000482"), (5e-324, "5e-324"), (1.7976931348623157e308, "1.7976931348623157e308"),
+              (-2.5, "-2.5"), (100.0, "100.0"), (1.5e-7, "1.5e-7"),
+              (2.0 ** -24, "5.960464477539063e-8"),       # exact decimal tie: the correctly ROUNDED 16 digits do not read back
+              (9007199254740993.0, "9007199254740992.0"), (0.3, "0.3"), (2.0 ** 70, "1.1805916207174113e21")]
+
+
+def test_f64_formatting_reproduces_what_the_rust_binary_printed(L):
+    for t in RUST_PRINTED:
+        assert fmt(L, float(t)) == t
+    for v, t in RYU_LAYOUT:
+        assert fmt(L, v) == t, (v, t)
+    assert fmt(L, float("nan")) == "null" and fmt(L, float("inf")) == "null"
+    import glob, os, re
+    files = glob.glob("/root/reference/results.old/**/without_hf_pipeline_rust*/*.json", recursive=True)
+    for f in files:                                   # live re-check when the reference is mounted (this container)
+        for m in re.finditer(r'(?<![\\w"])-?\\d+\\.\\d+(?:e-?\\d+)?', open(f).read()):
+            assert fmt(L, float(m.group(0))) == m.group(0)
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.floats(allow_nan=False, allow_infinity=False, width=64))
+def test_f64_formatting_round_trips_with_shortest_digits(L, v):
+    s = fmt(L, v)
+    assert float(s) == v and (v != 0 or s in ("0.0", "-0.0"))
+    digits = lambda t: t.lstrip("-").split("e")[0].replace(".", "").strip("0")
+    assert digits(s) == digits(repr(v))               # same shortest digit string as Python's repr (Gay / ryu agree)
+    assert ("e" in s) or ("." in s)

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -186,20 +187,42 @@ inline std::string escape(const std::string& s) {
 inline std::string fmt_f64(double v) {
     if (std::isnan(v) || std::isinf(v)) return "null";       // serde_json writes null
     if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
-    char buf[48];
-    int prec = 0;
-    for (; prec <= 16; ++prec) {
-        snprintf(buf, sizeof(buf), "%.*e", prec, v);
-        if (std::strtod(buf, nullptr) == v) break;
-    }
-    std::string t(buf);
-    const bool neg = t[0] == '-';
-    if (neg) t.erase(0, 1);
-    const size_t epos = t.find('e');
+    // Shortest digit string that reads back as v, and among those the one closest to v (ties -> even): what ryu /
+    // Grisu / David Gay's algorithm all define.  The correctly rounded n-digit decimal is NOT always it: at an exact
+    // decimal tie (v = 2^-24 = 5.9604644775390625e-8) round-half-even gives ...062, which reads back as a different
+    // double, while ...063 round-trips.  So both neighbours of the exact expansion are tried at every length.
+    const bool neg = std::signbit(v);
+    const double a = std::fabs(v);
+    char big[832];
+    snprintf(big, sizeof(big), "%.780e", a);                 // glibc prints the exact binary value (<= 767 significant digits)
+    std::string exact;
+    const char* ep = std::strchr(big, 'e');
+    for (const char* q = big; q < ep; ++q) if (*q != '.') exact += *q;
+    int e10 = std::atoi(ep + 1);
     std::string digits;
-    for (size_t i = 0; i < epos; ++i) if (t[i] != '.') digits += t[i];
+    auto reads_back = [&](const std::string& d, int e) {
+        const std::string t = d.substr(0, 1) + "." + d.substr(1) + "e" + std::to_string(e);
+        return std::strtod(t.c_str(), nullptr) == a;
+    };
+    for (size_t n = 1; n <= 17 && digits.empty(); ++n) {
+        std::string down = exact.substr(0, n), up = down;
+        int e_up = e10;
+        int i = (int)n - 1;
+        while (i >= 0 && up[(size_t)i] == '9') up[(size_t)i--] = '0';
+        if (i >= 0) ++up[(size_t)i]; else { up = "1" + up.substr(0, n - 1); ++e_up; }
+        const bool ok_d = reads_back(down, e10), ok_u = reads_back(up, e_up);
+        if (!ok_d && !ok_u) continue;
+        bool take_up = ok_u && !ok_d;
+        if (ok_d && ok_u) {                                  // closer to the exact expansion; tie -> even last digit
+            const std::string rest = exact.substr(n);
+            const std::string half = "5" + std::string(rest.size() - 1, '0');
+            take_up = rest > half || (rest == half && ((down[n - 1] - '0') & 1));
+        }
+        digits = take_up ? up : down;
+        if (take_up) e10 = e_up;
+    }
+    if (digits.empty()) { digits = exact.substr(0, 17); }
     while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
-    const int e10 = std::atoi(t.c_str() + epos + 1);
     const int len = (int)digits.size();
     const int k = e10 - (len - 1);          // value = digits * 10^k
     const int kk = len + k;                 // position of the decimal point

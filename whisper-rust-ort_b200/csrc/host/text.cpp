@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../common.h"
+#include "json.h"
 #include "utf8.h"
 
 namespace wbtext {
@@ -155,6 +156,16 @@ int wb_host_stat_block(const double* xs, int n, double* o) {                    
     o[4] = v.empty() ? NAN : v.back();
     o[5] = v.empty() ? NAN : sum / (double)v.size();
     return WB_OK;
+}
+
+int64_t wb_host_format_f64(double v, char* out, int64_t cap) {
+    const std::string s = wbjson::fmt_f64(v);
+    if (out && cap > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        std::memcpy(out, s.data(), n);
+        out[n] = '\0';
+    }
+    return (int64_t)s.size();
 }
 
 }  // extern "C"
