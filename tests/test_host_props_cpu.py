@@ -124,3 +124,44 @@ def test_f64_formatting_round_trips_with_shortest_digits(L, v):
     digits = lambda t: t.lstrip("-").split("e")[0].replace(".", "").strip("0")
     assert digits(s) == digits(repr(v))               # same shortest digit string as Python's repr (Gay / ryu agree)
     assert ("e" in s) or ("." in s)
+
+
+# ---------------- byte-level BPE decode: bytes -> String::from_utf8_lossy ----------------
+@pytest.fixture(scope="module")
+def byte_tok(L, tmp_path_factory):
+    """A tokenizer.json whose vocabulary is the 256 single-byte tokens (ids 0..255) plus a few specials."""
+    import json
+    b2u = hr.bytes_to_unicode()
+    vocab = {b2u[b]: b for b in range(256)}
+    added = [{"id": 300, "content": "<|endoftext|>", "special": True}, {"id": 301, "content": "<|0.00|>", "special": False},
+             {"id": 302, "content": "café au lait", "special": False}]
+    p = tmp_path_factory.mktemp("bytetok") / "tokenizer.json"
+    p.write_text(json.dumps({"model": {"type": "BPE", "vocab": vocab}, "added_tokens": added, "decoder": {"type": "ByteLevel"}}), encoding="utf-8")
+    L.wb_tokenizer_load.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+    t = C.c_void_p()
+    assert L.wb_tokenizer_load(C.byref(t), str(p).encode()) == 0, L.wb_last_error()
+    yield t
+    L.wb_tokenizer_free(t)
+
+
+def _decode(L, t, ids):
+    arr = (C.c_int64 * max(len(ids), 1))(*ids)
+    n = L.wb_host_decode_tokens(t, arr, len(ids), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    L.wb_host_decode_tokens(t, arr, len(ids), buf, n + 1)
+    return buf.raw[:n]
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.binary(min_size=0, max_size=40))
+def test_decode_of_arbitrary_bytes_is_from_utf8_lossy(L, byte_tok, data):
+    got = _decode(L, byte_tok, list(data))
+    assert got == data.decode("utf-8", errors="replace").encode("utf-8")       # same maximal-subpart policy as Rust
+
+
+def test_decode_mixes_specials_added_tokens_and_partial_sequences(L, byte_tok):
+    e_acute = list("é".encode())                                               # 0xC3 0xA9 as two single-byte tokens
+    assert _decode(L, byte_tok, [0x41, 300, *e_acute, 301]).decode() == "Aé<|0.00|>"       # special skipped, added kept
+    assert _decode(L, byte_tok, [e_acute[0], 301]).decode() == "�<|0.00|>"            # dangling lead byte
+    # an added token with a character outside the byte-level alphabet (the space) is taken as raw text, like the crate
+    assert _decode(L, byte_tok, [302]).decode() == "café au lait"

@@ -43,7 +43,10 @@ std::string decode_ids(const wb_tokenizer& t, const int64_t* ids, int n, bool sk
         if (skip_special && t.is_special[id]) continue;
         const std::string& tok = t.id_to_token[id];
         if (tok.empty()) continue;
-        if (!t.byte_level || t.is_added[id]) { bytes += tok; continue; }
+        // every surviving token goes through the ByteLevel decoder, added (non-special) ones included, exactly as
+        // tokenizers' decode_chain does: a token whose characters are all byte-level characters becomes those bytes,
+        // any other token is taken as its raw UTF-8 text
+        if (!t.byte_level) { bytes += tok; continue; }
         std::string piece;
         bool ok = true;
         size_t j = 0;
@@ -54,17 +57,7 @@ std::string decode_ids(const wb_tokenizer& t, const int64_t* ids, int n, bool sk
         }
         bytes += ok ? piece : tok;      // ByteLevel decoder falls back to the raw token text
     }
-    // String::from_utf8_lossy: invalid sequences become U+FFFD
-    std::string out;
-    size_t i = 0;
-    while (i < bytes.size()) {
-        size_t j = i;
-        uint32_t cp = wbutf8::decode(bytes, j);
-        if (cp == 0xFFFD && !(j - i == 3 && (unsigned char)bytes[i] == 0xEF)) out += "\xEF\xBF\xBD";
-        else out.append(bytes, i, j - i);
-        i = j;
-    }
-    return out;
+    return wbutf8::from_utf8_lossy(bytes);     // invalid sequences become U+FFFD, as in the tokenizers crate
 }
 
 }  // namespace

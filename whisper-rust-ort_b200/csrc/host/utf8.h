@@ -32,6 +32,46 @@ inline uint32_t decode(const std::string& s, size_t& i) {
     return 0xFFFD;
 }
 
+// String::from_utf8_lossy: well-formed sequences (Unicode Table 3-7: no overlongs, no surrogates, nothing above
+// U+10FFFF) are copied; every ill-formed run becomes ONE U+FFFD per maximal prefix of a well-formed sequence
+// (at least one byte) -- the policy Rust's Utf8Chunks and CPython's errors="replace" share.
+inline std::string from_utf8_lossy(const std::string& b) {
+    std::string out;
+    out.reserve(b.size());
+    size_t i = 0;
+    const size_t n = b.size();
+    auto at = [&](size_t k) -> int { return k < n ? (unsigned char)b[k] : -1; };
+    auto in = [](int v, int lo, int hi) { return v >= lo && v <= hi; };
+    while (i < n) {
+        const int c = at(i);
+        if (c < 0x80) { out += (char)c; ++i; continue; }
+        int need = 0, lo = 0x80, hi = 0xBF;                 // range of the SECOND byte depends on the lead byte
+        if (in(c, 0xC2, 0xDF)) need = 1;
+        else if (c == 0xE0) { need = 2; lo = 0xA0; }
+        else if (in(c, 0xE1, 0xEC) || in(c, 0xEE, 0xEF)) need = 2;
+        else if (c == 0xED) { need = 2; hi = 0x9F; }
+        else if (c == 0xF0) { need = 3; lo = 0x90; }
+        else if (in(c, 0xF1, 0xF3)) need = 3;
+        else if (c == 0xF4) { need = 3; hi = 0x8F; }
+        size_t len = 1;                                     // bytes of the maximal well-formed prefix
+        bool ok = need > 0;
+        if (ok) {
+            if (in(at(i + 1), lo, hi)) {
+                len = 2;
+                for (int k = 2; k <= need; ++k) {
+                    if (in(at(i + (size_t)k), 0x80, 0xBF)) len = (size_t)k + 1; else { ok = false; break; }
+                }
+            } else {
+                ok = false;
+            }
+        }
+        if (ok) out.append(b, i, (size_t)need + 1);
+        else out += "\xEF\xBF\xBD";
+        i += ok ? (size_t)need + 1 : len;
+    }
+    return out;
+}
+
 inline void encode(std::string& out, uint32_t cp) {
     if (cp < 0x80) out += (char)cp;
     else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
