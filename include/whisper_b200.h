@@ -167,6 +167,9 @@ int wb_host_chunk_starts(int64_t n_samples, int64_t chunk_len, int64_t step, int
 /* stitch_texts / word_overlap (main.rs:659-696). Returns needed length (excluding NUL). */
 int wb_host_word_overlap(const char* a, const char* b, int max_words);
 int64_t wb_host_stitch_texts(const char* const* chunks, int n, char* out, int64_t cap);
+/* Rust's str::to_lowercase as word_overlap applies it to every word (main.rs:687-688): full Unicode lowercase
+ * mapping incl. one-to-many images and the Final_Sigma rule.  Returns the needed length (excluding NUL). */
+int64_t wb_host_to_lowercase(const char* s, char* out, int64_t cap);
 /* percentile / stat_block (main.rs:1021-1048): out6 = {min, median, p90, p95, max, mean}. */
 double wb_host_percentile(const double* xs, int n, double p);
 int wb_host_stat_block(const double* xs, int n, double* out6);

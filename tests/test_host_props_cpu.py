@@ -165,3 +165,51 @@ def test_decode_mixes_specials_added_tokens_and_partial_sequences(L, byte_tok):
     assert _decode(L, byte_tok, [e_acute[0], 301]).decode() == "�<|0.00|>"            # dangling lead byte
     # an added token with a character outside the byte-level alphabet (the space) is taken as raw text, like the crate
     assert _decode(L, byte_tok, [302]).decode() == "café au lait"
+
+
+# ---------------- str::to_lowercase (full Unicode mapping + Final_Sigma) ----------------
+def lower(L, s):
+    L.wb_host_to_lowercase.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    L.wb_host_to_lowercase.restype = C.c_int64
+    b = s.encode("utf-8")
+    n = L.wb_host_to_lowercase(b, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    L.wb_host_to_lowercase(b, buf, n + 1)
+    return buf.raw[:n].decode("utf-8")
+
+
+def test_lowercase_of_every_scalar_value_matches_the_unicode_database(L):
+    """CPython's str.lower() implements the algorithm Rust's str::to_lowercase does (same tables, same Final_Sigma
+    rule), so it is the oracle here; the header is generated from it by tools/gen_unicode_tables.py."""
+    chunk = []
+    for c in range(1, 0x110000):
+        if 0xD800 <= c <= 0xDFFF:
+            continue
+        chunk.append(chr(c))
+        if len(chunk) == 4096:
+            s = " ".join(chunk)                        # spaces: no Final_Sigma context between neighbours
+            assert lower(L, s) == " ".join(ch.lower() for ch in chunk)
+            chunk = []
+    s = " ".join(chunk)
+    assert lower(L, s) == " ".join(ch.lower() for ch in chunk)
+
+
+SIGMA_WORDS = ["ΟΔΥΣΣΕΥΣ", "ΣΟΦΟΣ", "Σ", "ΑΣ", "ΑΣ.", "ΑΣ'Α", "ΑΣ́", "ΆΣ", "ΣΑΣ", "aΣ", "Σa", "1Σ", "ΑΣ1", "ΑΣ·Β", "İSTANBUL", "ǅUNGLA",
+               "ẞ", "ΆΈΉ", "ԱԲԳ", "ᲐᲑᲒ", "Ｈｅｌｌｏ", "ǄǇ", "Ⅷ", "Ⓐ", "𐐀𐐁", "Straße", "ÀÉÎÕÜ"]
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.one_of(st.sampled_from(SIGMA_WORDS), st.text(alphabet=st.characters(blacklist_categories=("Cs",)), min_size=0, max_size=8)),
+                min_size=0, max_size=6))
+def test_lowercase_of_random_text_matches_python(L, parts):
+    s = "".join(parts)
+    if "\x00" in s:
+        return                                          # C strings end at NUL
+    assert lower(L, s) == s.lower()
+
+
+def test_word_overlap_is_case_insensitive_in_every_script(L):
+    a, b = "είπε ο ΟΔΥΣΣΕΥΣ ΣΤΗΝ Ιθάκη", "οδυσσευς στην ιθάκη και μετά"
+    assert L.wb_host_word_overlap(a.encode(), b.encode(), 16) == hr.word_overlap(a, b, 16) == 3
+    a, b = "geldik İSTANBUL ŞEHRİ", "i̇stanbul şehri̇ çok güzel"
+    assert L.wb_host_word_overlap(a.encode(), b.encode(), 16) == hr.word_overlap(a, b, 16) == 2

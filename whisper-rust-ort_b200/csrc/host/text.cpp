@@ -12,6 +12,7 @@
 
 #include "../common.h"
 #include "json.h"
+#include "unicode_tables.h"
 #include "utf8.h"
 
 namespace wbtext {
@@ -52,10 +53,61 @@ std::string trim(const std::string& s) {
     return s.substr(b, e - b);
 }
 
+namespace {
+bool in_ranges(const uint32_t (*r)[2], int n, uint32_t c) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (c < r[mid][0]) hi = mid - 1;
+        else if (c > r[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+bool is_cased(uint32_t c) { return in_ranges(wbuni::CASED, wbuni::N_CASED, c); }
+bool is_case_ignorable(uint32_t c) { return in_ranges(wbuni::CASE_IGNORABLE, wbuni::N_CASE_IGNORABLE, c); }
+const wbuni::LowerEntry* lower_entry(uint32_t c) {
+    int lo = 0, hi = wbuni::N_LOWER - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (c < wbuni::LOWER[mid].cp) hi = mid - 1;
+        else if (c > wbuni::LOWER[mid].cp) lo = mid + 1;
+        else return &wbuni::LOWER[mid];
+    }
+    return nullptr;
+}
+}  // namespace
+
+// Rust's str::to_lowercase (alloc::str): the full Unicode mapping per scalar value (one char may become up to three,
+// U+0130 -> "i" + U+0307) and the one context rule, Final_Sigma: U+03A3 becomes U+03C2 when it is preceded by a cased
+// letter (skipping case-ignorable characters) and not followed by one.  Tables: unicode_tables.h (generated).
 std::string to_lowercase(const std::string& s) {
+    std::vector<uint32_t> cps;
+    for (size_t i = 0; i < s.size();) cps.push_back(wbutf8::decode(s, i));
     std::string out;
-    size_t i = 0;
-    while (i < s.size()) wbutf8::encode(out, wbutf8::to_lower(wbutf8::decode(s, i)));
+    for (size_t i = 0; i < cps.size(); ++i) {
+        const uint32_t c = cps[i];
+        if (c == 0x3A3) {
+            bool before = false, after = false;
+            for (size_t k = i; k-- > 0;) {
+                if (is_case_ignorable(cps[k])) continue;
+                before = is_cased(cps[k]);
+                break;
+            }
+            for (size_t k = i + 1; k < cps.size(); ++k) {
+                if (is_case_ignorable(cps[k])) continue;
+                after = is_cased(cps[k]);
+                break;
+            }
+            wbutf8::encode(out, (before && !after) ? 0x3C2u : 0x3C3u);
+            continue;
+        }
+        if (const wbuni::LowerEntry* e = lower_entry(c)) {
+            for (int k = 0; k < 3 && e->to[k]; ++k) wbutf8::encode(out, e->to[k]);
+        } else {
+            wbutf8::encode(out, c);
+        }
+    }
     return out;
 }
 
@@ -156,6 +208,16 @@ int wb_host_stat_block(const double* xs, int n, double* o) {                    
     o[4] = v.empty() ? NAN : v.back();
     o[5] = v.empty() ? NAN : sum / (double)v.size();
     return WB_OK;
+}
+
+int64_t wb_host_to_lowercase(const char* s, char* out, int64_t cap) {
+    const std::string r = wbtext::to_lowercase(s ? s : "");
+    if (out && cap > 0) {
+        const size_t n = std::min<size_t>(r.size(), (size_t)cap - 1);
+        std::memcpy(out, r.data(), n);
+        out[n] = '\0';
+    }
+    return (int64_t)r.size();
 }
 
 int64_t wb_host_format_f64(double v, char* out, int64_t cap) {

@@ -1,6 +1,5 @@
-// utf8.h — the few Unicode operations the reference's Rust std calls imply (char iteration,
-// White_Space, simple lowercase) without ICU.  Lowercasing covers ASCII, Latin-1, Latin Extended-A,
-// Greek and Cyrillic — the scripts Whisper emits with case; other code points map to themselves.
+// utf8.h — the few Unicode operations the reference's Rust std calls imply (char iteration, White_Space,
+// from_utf8_lossy) without ICU.  Lowercasing lives in text.cpp on top of the generated unicode_tables.h.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -82,21 +81,6 @@ inline void encode(std::string& out, uint32_t cp) {
 inline bool is_whitespace(uint32_t c) {      // Unicode White_Space (what Rust's char::is_whitespace tests)
     return (c >= 0x09 && c <= 0x0D) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 ||
            (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
-}
-
-inline uint32_t to_lower(uint32_t c) {
-    if (c >= 'A' && c <= 'Z') return c + 32;
-    if (c < 0x80) return c;
-    if ((c >= 0xC0 && c <= 0xDE) && c != 0xD7) return c + 32;                 // Latin-1
-    if (c >= 0x100 && c <= 0x137) return (c & 1) ? c : c + 1;                   // Latin Extended-A pairs
-    if (c >= 0x139 && c <= 0x148) return (c & 1) ? c + 1 : c;
-    if (c >= 0x14A && c <= 0x177) return (c & 1) ? c : c + 1;
-    if (c == 0x178) return 0xFF;
-    if (c >= 0x179 && c <= 0x17E) return (c & 1) ? c + 1 : c;
-    if (c >= 0x391 && c <= 0x3A9 && c != 0x3A2) return c + 32;                  // Greek
-    if (c >= 0x410 && c <= 0x42F) return c + 32;                                // Cyrillic
-    if (c >= 0x400 && c <= 0x40F) return c + 80;
-    return c;
 }
 
 }  // namespace wbutf8
