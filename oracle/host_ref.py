@@ -45,10 +45,40 @@ def decode_wav_samples(raw: np.ndarray, fmt: str, channels: int) -> np.ndarray:
     return acc / np.float32(channels)
 
 
+# Rust's char::is_whitespace = the Unicode White_Space property.  Python's str.split()/strip() also treat
+# U+001C..U+001F as separators, which Rust does not, so the Rust set is spelled out.
+RUST_WHITESPACE = set(range(0x09, 0x0E)) | {0x20, 0x85, 0xA0, 0x1680} | set(range(0x2000, 0x200B)) | {0x2028, 0x2029, 0x202F, 0x205F, 0x3000}
+
+
+def split_whitespace(s: str) -> list[str]:
+    """str::split_whitespace."""
+    out, cur = [], ""
+    for ch in s:
+        if ord(ch) in RUST_WHITESPACE:
+            if cur:
+                out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur:
+        out.append(cur)
+    return out
+
+
+def trim(s: str) -> str:
+    """str::trim."""
+    b, e = 0, len(s)
+    while b < e and ord(s[b]) in RUST_WHITESPACE:
+        b += 1
+    while e > b and ord(s[e - 1]) in RUST_WHITESPACE:
+        e -= 1
+    return s[b:e]
+
+
 def word_overlap(a: str, b: str, max_words: int) -> int:
     """main.rs:686-696."""
-    aw = [w.lower() for w in a.split()]
-    bw = [w.lower() for w in b.split()]
+    aw = [w.lower() for w in split_whitespace(a)]
+    bw = [w.lower() for w in split_whitespace(b)]
     mx = min(max_words, len(aw), len(bw))
     for k in range(mx, 0, -1):
         if aw[len(aw) - k:] == bw[:k]:
@@ -60,7 +90,7 @@ def stitch_texts(chunks: list[str]) -> str:
     """main.rs:659-684."""
     out = ""
     for chunk in chunks:
-        t = chunk.strip()
+        t = trim(chunk)
         if not t:
             continue
         if not out:
@@ -68,7 +98,7 @@ def stitch_texts(chunks: list[str]) -> str:
             continue
         ov = word_overlap(out, t, 16)
         if ov > 0:
-            rem = " ".join(t.split()[ov:])
+            rem = " ".join(split_whitespace(t)[ov:])
             if rem:
                 out += " " + rem
         else:

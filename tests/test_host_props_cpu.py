@@ -10,12 +10,14 @@ from hypothesis import given, settings, strategies as st
 import host_ref as hr
 from test_host_cpu import L, stitch            # noqa: F401  (fixture + helper)
 
-WORDS = ["the", "The", "cat", "sat", "on", "mat", "über", "naïve", "日本", "a", "A", "and", "then", "went", "home", "x1", "..."]
+WORDS = ["the", "The", "cat", "sat", "on", "mat", "über", "naïve", "日本", "a", "A", "and", "then", "went", "home", "x1", "...",
+         "ΣΟΦΟΣ", "σοφος", "İZ", "i̇z", "a\x1fb", "a\x1cB", "no\u200bbreak", "Ǆ", "ǆ"]
+SEPS = [" ", "  ", "\t", "\n", "\u00a0", "\u2003", "\u3000", "\x0b", "\x85", "\u2028"]            # all White_Space
 words = st.lists(st.sampled_from(WORDS), min_size=0, max_size=24)
 
 
 def _join(ws, rng_spaces):
-    return "".join(w + " " * s for w, s in zip(ws, rng_spaces)) if ws else ""
+    return "".join(w + SEPS[s % len(SEPS)] for w, s in zip(ws, rng_spaces)) if ws else ""
 
 
 @settings(max_examples=150, deadline=None)
@@ -27,7 +29,7 @@ def test_stitching_matches_oracle_on_random_word_lists(L, chunks_w, seed):
         if i and chunks_w[i - 1] and rng.random() < 0.6:          # make a real overlap with the previous chunk
             k = int(rng.integers(1, min(len(chunks_w[i - 1]), 18) + 1))
             ws = chunks_w[i - 1][-k:] + ws
-        chunks.append(_join(ws, rng.integers(1, 3, len(ws))))
+        chunks.append(_join(ws, rng.integers(0, 1000, len(ws))))
     assert stitch(L, chunks) == hr.stitch_texts(chunks)
     for a, b in zip(chunks, chunks[1:]):
         for mw in (1, 4, 16):
