@@ -177,6 +177,10 @@ int wb_host_stat_block(const double* xs, int n, double* out6);
  * "14.884440201999999", "1.0", "0.000482736", "4.82e-6", "1e16", non-finite -> "null"; main.rs:1232-1259).
  * Returns the needed length (excluding NUL), writes up to cap bytes. */
 int64_t wb_host_format_f64(double v, char* out, int64_t cap);
+/* How the output files print a string: a serde_json string literal (main.rs:1232) and a csv-crate field with
+ * QuoteStyle::Necessary (main.rs:1216-1229).  Same return convention. */
+int64_t wb_host_json_string(const char* s, char* out, int64_t cap);
+int64_t wb_host_csv_field(const char* s, char* out, int64_t cap);
 
 /* tokenizer.json reader + byte-level BPE id->text decoder (replaces the `tokenizers` crate uses:
  * Tokenizer::from_file main.rs:580, token_to_id :531, decode(ids, skip_special=true) :640). */

@@ -215,3 +215,39 @@ def test_word_overlap_is_case_insensitive_in_every_script(L):
     assert L.wb_host_word_overlap(a.encode(), b.encode(), 16) == hr.word_overlap(a, b, 16) == 3
     a, b = "geldik İSTANBUL ŞEHRİ", "i̇stanbul şehri̇ çok güzel"
     assert L.wb_host_word_overlap(a.encode(), b.encode(), 16) == hr.word_overlap(a, b, 16) == 2
+
+
+# ---------------- string output: serde_json literals and csv-crate fields ----------------
+def _call_str(L, fn, s):
+    f = getattr(L, fn)
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    f.restype = C.c_int64
+    b = s.encode("utf-8")
+    n = f(b, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    f(b, buf, n + 1)
+    return buf.raw[:n].decode("utf-8")
+
+
+TEXT = st.text(alphabet=st.one_of(st.sampled_from(list(' ,";\'\\/\t\n\r\x08\x0c\x01\x1f\x7fé日𐐀')), st.characters(blacklist_categories=("Cs",), min_codepoint=1)),
+               min_size=0, max_size=30)
+
+
+@settings(max_examples=300, deadline=None)
+@given(TEXT)
+def test_json_string_matches_serde_json_escaping(L, s):
+    import json
+    got = _call_str(L, "wb_host_json_string", s)
+    assert got == json.dumps(s, ensure_ascii=False)          # \\" \\\\ \\b \\f \\n \\r \\t, \\u00xx below 0x20, everything else raw
+    assert json.loads(got) == s
+
+
+@settings(max_examples=300, deadline=None)
+@given(TEXT)
+def test_csv_field_matches_minimal_quoting(L, s):
+    import csv, io
+    buf = io.StringIO()
+    csv.writer(buf, quoting=csv.QUOTE_MINIMAL, lineterminator="\n").writerow(["x", s, "y"])
+    want = buf.getvalue()[2:-3]                               # strip 'x,' and ',y\\n'
+    assert _call_str(L, "wb_host_csv_field", s) == want
+    assert next(csv.reader(io.StringIO("x," + want + ",y\n")))[1] == s.replace("\r\n", "\r\n")

@@ -28,6 +28,7 @@
 
 namespace wbtext {
 std::string stitch_texts(const std::vector<std::string>& chunks);
+std::string csv_field(const std::string& s);
 }
 
 namespace {
@@ -509,14 +510,7 @@ std::string stat_json(const std::vector<double>& xs, int indent) {              
            "\"p90\": " + wbjson::fmt_f64(o[2]) + ",\n" + in + "\"p95\": " + wbjson::fmt_f64(o[3]) + "\n" + end + "}";
 }
 
-std::string csv_field(const std::string& s) {      // csv crate, QuoteStyle::Necessary
-    bool q = s.empty() ? false : false;
-    for (char c : s) if (c == ',' || c == '"' || c == '\n' || c == '\r') { q = true; break; }
-    if (!q) return s;
-    std::string o = "\"";
-    for (char c : s) { if (c == '"') o += '"'; o += c; }
-    return o + "\"";
-}
+std::string csv_field(const std::string& s) { return wbtext::csv_field(s); }
 
 std::string fmt_fixed(double v, int prec) { char b[64]; snprintf(b, sizeof(b), "%.*f", prec, v); return b; }
 std::string lower(std::string s) { for (auto& c : s) c = (char)std::tolower((unsigned char)c); return s; }

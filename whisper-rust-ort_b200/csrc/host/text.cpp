@@ -111,6 +111,17 @@ std::string to_lowercase(const std::string& s) {
     return out;
 }
 
+// csv crate, QuoteStyle::Necessary (main.rs:1216-1229): a field is quoted only when it holds the delimiter, a quote,
+// CR or LF; quotes inside are doubled.
+std::string csv_field(const std::string& s) {
+    bool q = false;
+    for (char c : s) if (c == ',' || c == '"' || c == '\n' || c == '\r') { q = true; break; }
+    if (!q) return s;
+    std::string o = "\"";
+    for (char c : s) { if (c == '"') o += '"'; o += c; }
+    return o + "\"";
+}
+
 int word_overlap(const std::string& a, const std::string& b, int max_words) {      // main.rs:686-696
     std::vector<std::string> aw = split_whitespace(a), bw = split_whitespace(b);
     for (auto& w : aw) w = to_lowercase(w);
@@ -209,6 +220,17 @@ int wb_host_stat_block(const double* xs, int n, double* o) {                    
     o[5] = v.empty() ? NAN : sum / (double)v.size();
     return WB_OK;
 }
+
+static int64_t copy_out(const std::string& r, char* out, int64_t cap) {
+    if (out && cap > 0) {
+        const size_t n = std::min<size_t>(r.size(), (size_t)cap - 1);
+        std::memcpy(out, r.data(), n);
+        out[n] = '\0';
+    }
+    return (int64_t)r.size();
+}
+int64_t wb_host_json_string(const char* s, char* out, int64_t cap) { return copy_out(wbjson::escape(s ? s : ""), out, cap); }
+int64_t wb_host_csv_field(const char* s, char* out, int64_t cap) { return copy_out(wbtext::csv_field(s ? s : ""), out, cap); }
 
 int64_t wb_host_to_lowercase(const char* s, char* out, int64_t cap) {
     const std::string r = wbtext::to_lowercase(s ? s : "");
