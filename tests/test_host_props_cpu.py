@@ -251,3 +251,46 @@ def test_csv_field_matches_minimal_quoting(L, s):
     want = buf.getvalue()[2:-3]                               # strip 'x,' and ',y\\n'
     assert _call_str(L, "wb_host_csv_field", s) == want
     assert next(csv.reader(io.StringIO("x," + want + ",y\n")))[1] == s.replace("\r\n", "\r\n")
+
+
+# ---------------- RIFF/WAVE container variations ----------------
+def _riff(chunks):
+    body = b"WAVE"
+    for cid, payload, declared in chunks:
+        body += cid + np.uint32(len(payload) if declared is None else declared).tobytes() + payload
+        if len(payload) & 1:
+            body += b"\0"                                    # RIFF chunks are word aligned
+    return b"RIFF" + np.uint32(len(body)).tobytes() + body
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.sampled_from(["u8", "s16", "f32"]), st.integers(1, 3), st.integers(0, 300), st.sampled_from([16, 18, 40]),
+       st.lists(st.tuples(st.sampled_from([b"LIST", b"fact", b"bext", b"junk"]), st.binary(min_size=0, max_size=33)), max_size=3),
+       st.sampled_from(["exact", "zero_then_eof", "too_long"]), st.integers(0, 2**31 - 1))
+def test_wav_container_variations(L, tmp_path_factory, fmt, channels, frames, fmt_len, extra, size_kind, seed):
+    """fmt chunks of 16/18/40 bytes (WAVE_FORMAT_EXTENSIBLE), foreign chunks with odd sizes before the data, and the
+    bogus data sizes streaming writers leave behind: the samples are those of the plain file."""
+    from test_host_cpu import load_audio
+    import struct
+    rng = np.random.default_rng(seed)
+    if fmt == "u8":
+        raw = rng.integers(0, 256, frames * channels).astype(np.uint8); tag, bits = 1, 8
+    elif fmt == "s16":
+        raw = rng.integers(-32768, 32768, frames * channels).astype("<i2"); tag, bits = 1, 16
+    else:
+        raw = rng.uniform(-1, 1, frames * channels).astype("<f4"); tag, bits = 3, 32
+    block = channels * bits // 8
+    f = struct.pack("<HHIIHH", 0xFFFE if fmt_len == 40 else tag, channels, 16000, 16000 * block, block, bits)
+    if fmt_len == 18:
+        f += struct.pack("<H", 0)
+    elif fmt_len == 40:
+        f += struct.pack("<HHI", 22, bits, 0) + struct.pack("<H", tag) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+    data = raw.tobytes()
+    declared = {"exact": None, "zero_then_eof": None, "too_long": len(data) + 1000}[size_kind]
+    chunks = [(b"fmt ", f, None)] + [(cid, payload, None) for cid, payload in extra] + [(b"data", data, declared)]
+    p = tmp_path_factory.mktemp("wav") / "x.wav"
+    p.write_bytes(_riff(chunks))
+    got, dur = load_audio(L, p)
+    want = hr.decode_wav_samples(np.frombuffer(data, dtype=raw.dtype), fmt, channels)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert dur == len(want) / 16000.0
