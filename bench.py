@@ -155,6 +155,16 @@ class ClockSampler:
 
 
 # ---------------- CPU oracle port (cpu_baseline / reference arm) ----------------
+def probe_real_references():
+    """prefer the real CPU implementations if an image ever ships them.  None is installable offline today
+    (Rust toolchain, onnxruntime, faster-whisper), so the arm stays the oracle port; the probe result is reported."""
+    import importlib.util
+    import shutil
+    return {"cargo": shutil.which("cargo") is not None,
+            "onnxruntime": importlib.util.find_spec("onnxruntime") is not None,
+            "faster_whisper": importlib.util.find_spec("faster_whisper") is not None}
+
+
 def cpu_port_pass(model, clips, sup, bsup, threads):
     """One pass of the path on the CPU: C log-mel (oracle/mel_ref.c) + numpy Whisper (oracle/whisper_ref.py)."""
     import mel_oracle as mo
@@ -193,7 +203,8 @@ def run_reference(args, rank):
             "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "real_reference_toolchains_found": probe_real_references()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference binary (Rust+ONNX Runtime) not buildable offline; published EPYC-9654 4-core figure: 20.3x RT (BASELINE.md)"}
     print(json.dumps(line), flush=True)
@@ -344,7 +355,8 @@ def run_ours(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": CLIP_S / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"1 clip x 30 s, {MAX_NEW} new tokens, C log-mel + numpy Whisper fp32 ({dt:.1f} s)",
-                                    "tokens_match_gpu": bool(ref[0] == toks[0][0]) if args.precision == "fp32" else None}
+                                    "tokens_match_gpu": bool(ref[0] == toks[0][0]) if args.precision == "fp32" else None,
+                                    "real_reference_toolchains_found": probe_real_references()}
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()
