@@ -10,8 +10,11 @@
  *
  * Conventions: every function returning `int` returns WB_OK (0) or a negative WB_E* code and
  * stores a message retrievable with wb_last_error() (thread-local).  Host buffers are caller
- * owned.  A wb_ctx belongs to one GPU and is NOT thread-safe (the reference shares `&Session`
- * across rayon threads, main.rs:890-919; here that parallelism is the batch dimension).
+ * owned.  A wb_ctx belongs to one GPU and is NOT thread-safe: any host thread may call it, one call at a
+ * time (the reference shares `&Session` across rayon threads, main.rs:890-919; here that parallelism is the
+ * batch dimension).  Several contexts may be created on one GPU and driven concurrently from different
+ * threads (one batch in flight each); contexts of a process with the same device, weight source and
+ * architecture share one uploaded copy of the weights.
  * There is no CPU fallback: without a CUDA device every compute call fails with WB_ECUDA.
  */
 #ifndef WHISPER_B200_H
