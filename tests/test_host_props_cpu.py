@@ -294,3 +294,30 @@ def test_wav_container_variations(L, tmp_path_factory, fmt, channels, frames, fm
     want = hr.decode_wav_samples(np.frombuffer(data, dtype=raw.dtype), fmt, channels)
     assert got.shape == want.shape and np.array_equal(got, want)
     assert dur == len(want) / 16000.0
+
+
+# ---------------- tokenizer.json parsing: JSON string escapes, surrogate pairs, odd layouts ----------------
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.text(alphabet=st.characters(blacklist_categories=("Cs",), min_codepoint=1), min_size=1, max_size=8), min_size=1, max_size=12,
+                unique=True), st.booleans(), st.sampled_from([None, 0, 2]))
+def test_tokenizer_json_keys_survive_any_json_spelling(L, tmp_path_factory, keys, ascii_only, indent):
+    """The same vocabulary written with \\uXXXX escapes (incl. surrogate pairs for astral characters) or raw UTF-8, compact
+    or indented: every key must be found under its real spelling (wbjson::parse vs Python's json)."""
+    import json
+    L.wb_tokenizer_load.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+    L.wb_tokenizer_token_to_id.argtypes = [C.c_void_p, C.c_char_p]
+    L.wb_tokenizer_token_to_id.restype = C.c_int64
+    vocab = {k: i for i, k in enumerate(keys)}
+    doc = {"version": "1.0", "truncation": None, "padding": None, "unknown": [1, 2.5e3, -0.0, True, {"a": []}],
+           "added_tokens": [{"id": len(keys), "content": "<|endoftext|>", "special": True, "lstrip": False}],
+           "decoder": {"type": "ByteLevel", "add_prefix_space": True}, "model": {"type": "BPE", "dropout": None, "vocab": vocab, "merges": ["a b"]}}
+    p = tmp_path_factory.mktemp("tokjson") / "tokenizer.json"
+    p.write_text(json.dumps(doc, ensure_ascii=ascii_only, indent=indent), encoding="utf-8")
+    t = C.c_void_p()
+    assert L.wb_tokenizer_load(C.byref(t), str(p).encode()) == 0, L.wb_last_error()
+    try:
+        for k, i in vocab.items():
+            assert L.wb_tokenizer_token_to_id(t, k.encode("utf-8")) == i, k
+        assert L.wb_tokenizer_token_to_id(t, b"<|endoftext|>") == len(keys)
+    finally:
+        L.wb_tokenizer_free(t)
