@@ -117,9 +117,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int, enabled: bool = True):
+    def __init__(self, index: int, enabled: bool = True, interval: float = 0.2):
         # rank 0 only: nvidia-smi takes driver locks, and 8 ranks polling it stall each other's launches
-        self.index, self.rows, self.stop, self.enabled = index, [], threading.Event(), enabled
+        self.index, self.rows, self.stop, self.enabled, self.interval = index, [], threading.Event(), enabled, interval
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -131,7 +131,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(self.interval)
 
     def __enter__(self):
         if self.enabled:
@@ -272,7 +272,7 @@ def run_ours(args, rank, world, local_rank):
         toks[i] = ctxs[i].transcribe_resident(B, PROMPT, MAX_NEW, EOT, sup, bsup)
     run_workers(resident_step, args.warmup * S)
     barrier()
-    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0), interval=0.05 if world == 1 else 0.2) as clk:
         m.mark(0)
         t0 = time.perf_counter()
         lat_res = run_workers(resident_step, args.steps)
