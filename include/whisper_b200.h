@@ -159,7 +159,8 @@ int wb_selftest_fft400(const float* re, const float* im, float* out_re, float* o
 int wb_selftest_attn(wb_ctx* ctx, int B, float* max_diff_out, float* max_abs_out);
 
 /* ---- host-side pieces of the path (C++ in csrc/host/, exported for the CLI and tests) ---- */
-/* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8/s16/s24/s32/f32, channel
+/* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8 / s16 / f32 / A-law / mu-law (what symphonia hands the
+ * reference as U8, S16 or F32 buffers; s24 / s32 / f64 / ADPCM / FLAC fail with its "Unsupported decoded sample format"), channel
  * mean downmix, linear resample to 16 kHz.  *pcm_out is malloc'd; release with wb_host_free. */
 int wb_host_load_audio_16k_mono(const char* path, float** pcm_out, int64_t* n_out, double* dur_out);
 int64_t wb_host_resample_linear(const float* x, int64_t n, uint32_t sr_in, uint32_t sr_out,

@@ -45,6 +45,156 @@ def decode_wav_samples(raw: np.ndarray, fmt: str, channels: int) -> np.ndarray:
     return acc / np.float32(channels)
 
 
+_ALAW = None
+
+
+def _g711_tables():
+    """ITU-T G.711 expansion tables (what symphonia-codec-pcm applies to PCM_ALAW / PCM_MULAW packets -> S16)."""
+    global _ALAW
+    if _ALAW is None:
+        al, mu = np.zeros(256, np.int16), np.zeros(256, np.int16)
+        for v in range(256):
+            a = v ^ 0x55
+            t, seg = (a & 0x0F) << 4, (a & 0x70) >> 4
+            t = t + 8 if seg == 0 else t + 0x108 if seg == 1 else (t + 0x108) << (seg - 1)
+            al[v] = t if a & 0x80 else -t
+            u = (~v) & 0xFF
+            t = (((u & 0x0F) << 3) + 0x84) << ((u & 0x70) >> 4)
+            mu[v] = (0x84 - t) if u & 0x80 else (t - 0x84)
+        _ALAW = (al, mu)
+    return _ALAW
+
+
+class WavError(ValueError):
+    pass
+
+
+def read_wav_symphonia(blob: bytes):
+    """What load_audio_16k_mono (main.rs:228-316) gets out of symphonia 0.5.5's RIFF/WAVE reader + PCM decoder, before
+    resampling: -> (mono f32 samples, sample_rate).  symphonia-format-riff is a Cargo.lock dependency that is not under
+    /root/reference; this restates its published algorithm (ChunksReader::next, WavReader::try_new, next_packet):
+    the RIFF length bounds the chunk walk, a chunk longer than the rest of its parent is an error unless both lengths
+    are 0xFFFFFFFF, chunks are word aligned, the walk stops at the first data chunk, packets are <= 1152 blocks cut
+    from the DECLARED data length and a packet running past EOF is dropped whole (IoError -> `break`, main.rs:258-262)."""
+    import struct
+    if len(blob) < 12:
+        raise WavError("short read")
+    if blob[:4] == b"fLaC":
+        raise WavError("Unsupported decoded sample format")          # FLAC decodes to S32 -> main.rs:303
+    if blob[:4] != b"RIFF":
+        raise WavError("unsupported audio container")
+    if blob[8:12] != b"WAVE":
+        raise WavError("wav: riff form is not wave")
+    riff_len = struct.unpack_from("<I", blob, 4)[0]
+    consumed, pos, fmt = 0, 12, None
+    while True:
+        if consumed & 1:
+            if pos >= len(blob):
+                raise WavError("end of stream")
+            pos += 1
+            consumed += 1
+        if consumed + 8 > riff_len:
+            raise WavError("wav: missing data chunk")
+        if pos + 8 > len(blob):
+            raise WavError("end of stream")
+        cid, ln = blob[pos:pos + 4], struct.unpack_from("<I", blob, pos + 4)[0]
+        pos += 8
+        consumed += 8
+        if riff_len - consumed < ln and not (riff_len == ln == 0xFFFFFFFF):
+            raise WavError("riff: chunk length exceeds parent (list) chunk length")
+        consumed = min(consumed + ln, 0xFFFFFFFF)
+        if cid == b"fmt ":
+            if ln < 16:
+                raise WavError("wav: malformed fmt chunk")
+            if pos + ln > len(blob):
+                raise WavError("end of stream")
+            tag, ch, sr, _, align, bits = struct.unpack_from("<HHIIHH", blob, pos)
+            def lr(what):
+                if ch not in (1, 2):
+                    raise WavError(f"wav: channel layout is not stereo or mono for {what}")
+            if tag == 1:
+                if ln not in (16, 18, 40):
+                    raise WavError("wav: malformed fmt_pcm chunk")
+                if bits not in (8, 16, 24, 32):
+                    raise WavError("wav: bits per sample for fmt_pcm must be 8, 16, 24 or 32 bits")
+                lr("fmt_pcm")
+                codec = {8: "u8", 16: "s16"}.get(bits, "other")
+            elif tag == 3:
+                if ln not in (16, 18):
+                    raise WavError("wav: malformed fmt_ieee chunk")
+                if ln == 18 and struct.unpack_from("<H", blob, pos + 16)[0] != 0:
+                    raise WavError("wav: extension length not 0 for fmt_ieee chunk")
+                if bits not in (32, 64):
+                    raise WavError("wav: bits per sample for fmt_ieee must be 32 or 64 bits")
+                lr("fmt_ieee")
+                codec = "f32" if bits == 32 else "other"
+            elif tag == 0xFFFE:
+                if ln != 40:
+                    raise WavError("wav: malformed fmt_ext chunk")
+                ext, valid, mask = struct.unpack_from("<HHI", blob, pos + 16)
+                if ext != 22:
+                    raise WavError("wav: extension length not 22 for fmt_ext chunk")
+                if bits & 7:
+                    raise WavError("wav: bits per sample for fmt_ext must be a multiple of 8")
+                if valid > bits:
+                    raise WavError("wav: bits per sample exceeds coded bits per sample for fmt_ext")
+                if bin(mask).count("1") != ch:
+                    raise WavError("wav: channel mask mismatch for fmt_ext")
+                if mask >> 26:
+                    raise WavError("wav: too many channel masks")
+                if blob[pos + 26:pos + 40] != bytes.fromhex("000000001000800000aa00389b71"):
+                    raise WavError("wav: unsupported fmt_ext sub-type")
+                sub = struct.unpack_from("<H", blob, pos + 24)[0]
+                if sub == 1 and bits in (8, 16, 24, 32):
+                    codec = {8: "u8", 16: "s16"}.get(bits, "other")
+                elif sub == 3 and bits in (32, 64):
+                    codec = "f32" if bits == 32 else "other"
+                else:
+                    raise WavError("wav: unsupported fmt_ext sub-type")
+            elif tag in (6, 7):
+                if ln != 18:
+                    raise WavError("wav: malformed fmt_alaw/fmt_mulaw chunk")
+                if bits != 8:
+                    raise WavError("wav: bits per sample for fmt_alaw/fmt_mulaw must be 8 bits")
+                lr("fmt_alaw" if tag == 6 else "fmt_mulaw")
+                codec = "alaw" if tag == 6 else "mulaw"
+            elif tag in (2, 0x11):
+                codec = "other"                                      # ADPCM decodes to S32 -> main.rs:303
+            else:
+                raise WavError("wav: unsupported wave format")
+            fmt = (codec, ch, sr, align, bits)
+        elif cid == b"data":
+            break
+        pos += ln
+        if pos > len(blob):
+            raise WavError("end of stream")
+    if fmt is None:
+        raise WavError("No default track")
+    codec, ch, sr, align, bits = fmt
+    if sr == 0:
+        raise WavError("Unknown sample rate")
+    if ch == 0:
+        raise WavError("Unknown channels")
+    if codec == "other":
+        raise WavError("Unsupported decoded sample format")
+    if align == 0:
+        raise WavError("riff: block size is 0")
+    if align != ch * bits // 8:
+        raise WavError("wav: block_align does not match")
+    avail, blocks, frames = len(blob) - pos, ln // align, 0
+    while frames < blocks:
+        n = min(1152, blocks - frames)
+        if (frames + n) * align > avail:
+            break
+        frames += n
+    raw = blob[pos:pos + frames * align]
+    if codec in ("alaw", "mulaw"):
+        tab = _g711_tables()[0 if codec == "alaw" else 1]
+        return decode_wav_samples(tab[np.frombuffer(raw, np.uint8)], "s16", ch), sr
+    dt = {"u8": np.uint8, "s16": "<i2", "f32": "<f4"}[codec]
+    return decode_wav_samples(np.frombuffer(raw, dtype=dt), codec, ch), sr
+
+
 # Rust's char::is_whitespace = the Unicode White_Space property.  Python's str.split()/strip() also treat
 # U+001C..U+001F as separators, which Rust does not, so the Rust set is spelled out.
 RUST_WHITESPACE = set(range(0x09, 0x0E)) | {0x20, 0x85, 0xA0, 0x1680} | set(range(0x2000, 0x200B)) | {0x2028, 0x2029, 0x202F, 0x205F, 0x3000}

@@ -170,7 +170,7 @@ def decode(L, tok, ids):
     n = L.wb_host_decode_tokens(tok, a, len(ids), None, 0)
     buf = C.create_string_buffer(n + 1)
     L.wb_host_decode_tokens(tok, a, len(ids), buf, n + 1)
-    return buf.value.decode()
+    return buf.raw[:n].decode()              # the text may hold U+0000 (byte-level 'Ā'): length-delimited, not NUL-delimited
 
 
 def test_tokenizer_decode_and_special_tokens(L, tok_json):

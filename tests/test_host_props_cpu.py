@@ -8,7 +8,7 @@ import pytest
 from hypothesis import given, settings, strategies as st
 
 import host_ref as hr
-from test_host_cpu import L, stitch            # noqa: F401  (fixture + helper)
+from test_host_cpu import L, load_audio, stitch            # noqa: F401  (fixture + helpers)
 
 WORDS = ["the", "The", "cat", "sat", "on", "mat", "über", "naïve", "日本", "a", "A", "and", "then", "went", "home", "x1", "...",
          "ΣΟΦΟΣ", "σοφος", "İZ", "i̇z", "a\x1fb", "a\x1cB", "no\u200bbreak", "Ǆ", "ǆ"]
@@ -254,46 +254,114 @@ def test_csv_field_matches_minimal_quoting(L, s):
 
 
 # ---------------- RIFF/WAVE container variations ----------------
-def _riff(chunks):
+GUID_TAIL = bytes.fromhex("000000001000800000aa00389b71")
+
+
+def _riff(chunks, riff_len=None, tail=b""):
     body = b"WAVE"
     for cid, payload, declared in chunks:
         body += cid + np.uint32(len(payload) if declared is None else declared).tobytes() + payload
         if len(payload) & 1:
             body += b"\0"                                    # RIFF chunks are word aligned
-    return b"RIFF" + np.uint32(len(body)).tobytes() + body
+    body += tail
+    return b"RIFF" + np.uint32(len(body) if riff_len is None else riff_len).tobytes() + body
 
 
-@settings(max_examples=120, deadline=None)
-@given(st.sampled_from(["u8", "s16", "f32"]), st.integers(1, 3), st.integers(0, 300), st.sampled_from([16, 18, 40]),
+@settings(max_examples=200, deadline=None)
+@given(st.sampled_from(["u8", "s16", "f32", "alaw", "mulaw"]), st.integers(1, 3), st.integers(0, 2600), st.sampled_from([16, 18, 40]),
        st.lists(st.tuples(st.sampled_from([b"LIST", b"fact", b"bext", b"junk"]), st.binary(min_size=0, max_size=33)), max_size=3),
-       st.sampled_from(["exact", "zero_then_eof", "too_long"]), st.integers(0, 2**31 - 1))
-def test_wav_container_variations(L, tmp_path_factory, fmt, channels, frames, fmt_len, extra, size_kind, seed):
-    """fmt chunks of 16/18/40 bytes (WAVE_FORMAT_EXTENSIBLE), foreign chunks with odd sizes before the data, and the
-    bogus data sizes streaming writers leave behind: the samples are those of the plain file."""
-    from test_host_cpu import load_audio
+       st.sampled_from(["exact", "streamed", "too_long", "short_riff", "mask0"]), st.binary(max_size=40), st.integers(0, 2**31 - 1))
+def test_wav_container_variations(L, tmp_path_factory, fmt, channels, frames, fmt_len, extra, size_kind, tail, seed):
+    """The RIFF/WAVE reader against the restatement of symphonia-format-riff 0.5.5 (oracle/host_ref.py::read_wav_symphonia):
+    fmt chunks of 16/18/40 bytes, foreign chunks with odd sizes before the data, odd-length data + pad byte, more than two
+    channels (extensible only), A-law/mu-law, and the sizes streaming writers leave behind: `streamed` = RIFF and data
+    length both 0xFFFFFFFF (accepted; whole 1152-frame packets only, the partial packet at EOF is dropped), `too_long` =
+    data length beyond its parent (the reference fails), `short_riff` = RIFF length that hides the data chunk."""
     import struct
     rng = np.random.default_rng(seed)
     if fmt == "u8":
         raw = rng.integers(0, 256, frames * channels).astype(np.uint8); tag, bits = 1, 8
     elif fmt == "s16":
         raw = rng.integers(-32768, 32768, frames * channels).astype("<i2"); tag, bits = 1, 16
-    else:
+    elif fmt == "f32":
         raw = rng.uniform(-1, 1, frames * channels).astype("<f4"); tag, bits = 3, 32
+    else:
+        raw = rng.integers(0, 256, frames * channels).astype(np.uint8); tag, bits = (6 if fmt == "alaw" else 7), 8
     block = channels * bits // 8
+    mask = 0 if size_kind == "mask0" else (1 << channels) - 1
     f = struct.pack("<HHIIHH", 0xFFFE if fmt_len == 40 else tag, channels, 16000, 16000 * block, block, bits)
     if fmt_len == 18:
         f += struct.pack("<H", 0)
     elif fmt_len == 40:
-        f += struct.pack("<HHI", 22, bits, 0) + struct.pack("<H", tag) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+        f += struct.pack("<HHI", 22, bits, mask) + struct.pack("<H", tag) + GUID_TAIL
     data = raw.tobytes()
-    declared = {"exact": None, "zero_then_eof": None, "too_long": len(data) + 1000}[size_kind]
-    chunks = [(b"fmt ", f, None)] + [(cid, payload, None) for cid, payload in extra] + [(b"data", data, declared)]
+    chunks = [(b"fmt ", f, None)] + [(cid, payload, None) for cid, payload in extra]
+    if size_kind == "streamed":
+        blob = _riff(chunks + [(b"data", data, 0xFFFFFFFF)], riff_len=0xFFFFFFFF, tail=tail)
+    elif size_kind == "too_long":
+        blob = _riff(chunks + [(b"data", data, len(data) + 1000)])
+    elif size_kind == "short_riff":
+        blob = _riff(chunks + [(b"data", data, None)], riff_len=4 + 8 + len(f) - 2)
+    else:
+        blob = _riff(chunks + [(b"data", data, None)], tail=tail)
     p = tmp_path_factory.mktemp("wav") / "x.wav"
-    p.write_bytes(_riff(chunks))
+    p.write_bytes(blob)
+    try:
+        want, sr = hr.read_wav_symphonia(blob)
+    except hr.WavError as e:
+        with pytest.raises(RuntimeError) as ei:
+            load_audio(L, p)
+        assert str(e).split(" for ")[0][:40] in str(ei.value)
+        return
+    assert sr == 16000
     got, dur = load_audio(L, p)
-    want = hr.decode_wav_samples(np.frombuffer(data, dtype=raw.dtype), fmt, channels)
     assert got.shape == want.shape and np.array_equal(got, want)
     assert dur == len(want) / 16000.0
+    # what the contract says, spelled out independently of the restatement
+    if size_kind in ("exact",):
+        assert len(want) == frames
+    if size_kind == "streamed":
+        assert len(want) == (len(data) + (len(data) & 1) + len(tail)) // block // 1152 * 1152
+
+
+def test_wav_contract_examples(L, tmp_path):
+    """Known answers of the settled contract: an odd-length u8 data chunk keeps its pad byte out of
+    the samples; an over-declared data chunk inside a correctly sized RIFF is the reference's decode error; plain PCM
+    with 3 channels is rejected, the same samples as WAVE_FORMAT_EXTENSIBLE are accepted; G.711 goes through."""
+    import struct, audioop
+    def fmt_chunk(tag, ch, bits, ext=None):
+        block = ch * bits // 8
+        body = struct.pack("<HHIIHH", tag if ext is None else 0xFFFE, ch, 16000, 16000 * block, block, bits)
+        if ext is not None:
+            body += struct.pack("<HHI", 22, bits, ext) + struct.pack("<H", tag) + GUID_TAIL
+        return (b"fmt ", body, None)
+    def load(blob):
+        p = tmp_path / "t.wav"
+        p.write_bytes(blob)
+        return load_audio(L, p)[0]
+    one = np.array([200], np.uint8).tobytes()
+    assert load(_riff([fmt_chunk(1, 1, 8), (b"data", one, None)])).tolist() == [(200 - 128) / 128]
+    with pytest.raises(RuntimeError, match="chunk length exceeds parent"):
+        load(_riff([fmt_chunk(1, 1, 8), (b"data", one, 1001)]))
+    with pytest.raises(RuntimeError, match="missing data chunk"):
+        load(_riff([fmt_chunk(1, 1, 8)]))
+    s3 = np.arange(6, dtype="<i2").tobytes()
+    with pytest.raises(RuntimeError, match="not stereo or mono"):
+        load(_riff([fmt_chunk(1, 3, 16), (b"data", s3, None)]))
+    assert load(_riff([fmt_chunk(1, 3, 16, ext=0b111), (b"data", s3, None)])).tolist() == [np.float32(1 / 32768), np.float32(4 / 32768)]
+    with pytest.raises(RuntimeError, match="channel mask mismatch"):
+        load(_riff([fmt_chunk(1, 3, 16, ext=0b011), (b"data", s3, None)]))
+    # streamed sizes: 2500 frames present -> two whole packets survive
+    x = np.arange(2500, dtype="<i2")
+    got = load(_riff([fmt_chunk(1, 1, 16), (b"data", x.tobytes(), 0xFFFFFFFF)], riff_len=0xFFFFFFFF))
+    assert np.array_equal(got, x[:2304].astype(np.float32) / np.float32(32768))
+    # G.711 against Python's audioop (an independent implementation of the ITU tables)
+    codes = np.arange(256, dtype=np.uint8).tobytes()
+    for tag, conv in ((6, audioop.alaw2lin), (7, audioop.ulaw2lin)):
+        body = struct.pack("<HHIIHHH", tag, 1, 16000, 16000, 1, 8, 0)
+        got = load(_riff([(b"fmt ", body, None), (b"data", codes, None)]))
+        want = np.frombuffer(conv(codes, 2), "<i2").astype(np.float32) / np.float32(32768)
+        assert np.array_equal(got, want)
 
 
 # ---------------- tokenizer.json parsing: JSON string escapes, surrogate pairs, odd layouts ----------------

@@ -33,42 +33,48 @@ void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_fil
     WB_REQUIRE(ctx->cfg.n_mels == 80, WB_EINVAL, "log-mel kernel implements the reference's 80-bin frontend only");
     if (chunk_len <= 0) chunk_len = WB_CHUNK_SAMPLES;
     if (step <= 0) step = 400000;
-    MelState& s = ctx->mel;
-    s.raw_valid = false;
-    s.n_files = n_files;
-    s.h_file_off.assign(offsets, offsets + n_files + 1);
-    s.h_frame_off.assign(n_files + 1, 0);
-    s.h_tile_off.assign(n_files + 1, 0);
-    s.h_chunks.clear();
-    s.h_chunk_pos.clear();
+    WB_REQUIRE(offsets[0] == 0, WB_EINVAL, "offsets[0] must be 0");
+    // build and validate into locals; the context's MelState changes only once everything checked out (a rejected
+    // upload must not leave metadata that disagrees with the device buffers of the previous one)
+    std::vector<int64_t> h_frame_off(n_files + 1, 0), h_chunk_pos;
+    std::vector<int> h_tile_off(n_files + 1, 0);
+    std::vector<MelChunk> h_chunks;
     for (int i = 0; i < n_files; ++i) {
         const int64_t n = offsets[i + 1] - offsets[i];
         WB_REQUIRE(n > 0, WB_EINVAL, "Empty audio (file %d)", i);                      // main.rs:414-416
         const int64_t nf = mel_n_frames(n);
-        s.h_frame_off[i + 1] = s.h_frame_off[i] + nf;
-        s.h_tile_off[i + 1] = s.h_tile_off[i] + (int)ceil_div64(nf, 32);
+        h_frame_off[i + 1] = h_frame_off[i] + nf;
+        h_tile_off[i + 1] = h_tile_off[i] + (int)ceil_div64(nf, 32);
         int64_t pos = 0;                                                               // main.rs:875-882
         while (pos < n) {
             const int64_t end = pos + chunk_len < n ? pos + chunk_len : n;
-            s.h_chunks.push_back(MelChunk{i, (int)(pos / 160)});
-            s.h_chunk_pos.push_back(pos);
+            h_chunks.push_back(MelChunk{i, (int)(pos / 160)});
+            h_chunk_pos.push_back(pos);
             if (end == n) break;
             pos += step;
         }
     }
-    s.n_chunks = (int)s.h_chunks.size();
+    WB_REQUIRE((int)h_chunks.size() <= ctx->cfg.max_chunks, WB_ECAP, "%d chunks exceed max_chunks %d", (int)h_chunks.size(), ctx->cfg.max_chunks);
+    MelState& s = ctx->mel;
+    s.raw_valid = false;
+    s.n_files = 0;                                   // stays 0 (= nothing resident) if an allocation or copy below fails
+    s.n_chunks = 0;
+    s.h_file_off.assign(offsets, offsets + n_files + 1);
+    s.h_frame_off.swap(h_frame_off);
+    s.h_tile_off.swap(h_tile_off);
+    s.h_chunks.swap(h_chunks);
+    s.h_chunk_pos.swap(h_chunk_pos);
+    const int n_chunks = (int)s.h_chunks.size();
     s.total_frames = s.h_frame_off[n_files];
     s.total_tiles = s.h_tile_off[n_files];
-    WB_REQUIRE(s.n_chunks <= ctx->cfg.max_chunks, WB_ECAP, "%d chunks exceed max_chunks %d", s.n_chunks, ctx->cfg.max_chunks);
     const int64_t total = offsets[n_files] - offsets[0];
-    WB_REQUIRE(offsets[0] == 0, WB_EINVAL, "offsets[0] must be 0");
     s.pcm.reserve((size_t)total);
     s.file_off.reserve(n_files + 1);
     s.frame_off.reserve(n_files + 1);
     s.tile_off.reserve(n_files + 1);
     s.fmax.reserve(n_files);
     s.raw.reserve((size_t)s.total_frames * 80);
-    s.chunks.reserve(s.n_chunks);
+    s.chunks.reserve(n_chunks);
     cudaStream_t st = ctx->stream;
     CudaEvent e0, e1;
     CUDA_CHECK(cudaEventRecord(e0.e, st));
@@ -76,10 +82,12 @@ void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_fil
     CUDA_CHECK(cudaMemcpyAsync(s.file_off.p, s.h_file_off.data(), sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(s.frame_off.p, s.h_frame_off.data(), sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(s.tile_off.p, s.h_tile_off.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(s.chunks.p, s.h_chunks.data(), sizeof(MelChunk) * s.n_chunks, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(s.chunks.p, s.h_chunks.data(), sizeof(MelChunk) * n_chunks, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(e1.e, st));
     CUDA_CHECK(wb_stream_sync(st));
     CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.h2d_ms, e0.e, e1.e));
+    s.n_files = n_files;                             // committed: the device buffers now match the metadata
+    s.n_chunks = n_chunks;
     if (n_chunks_out) *n_chunks_out = s.n_chunks;
 }
 
@@ -195,6 +203,10 @@ int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* wei
             t_last = now;
         };
         lap("cuda init");
+        // >48 KB dynamic shared memory opt-ins are per device: set them for THIS context's device
+        mel_set_attrs();
+        gemm_tc_set_attrs();
+        attn_tc_set_attrs();
         mel_build_tables(ctx->mel_tables);
         CUDA_CHECK(cudaMalloc(&ctx->mel_tables_dev, sizeof(MelTables)));
         CUDA_CHECK(cudaMemcpy(ctx->mel_tables_dev, &ctx->mel_tables, sizeof(MelTables), cudaMemcpyHostToDevice));

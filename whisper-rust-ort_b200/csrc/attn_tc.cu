@@ -334,6 +334,10 @@ bool attn_tc_enabled() {
     return enabled != 0;
 }
 
+void attn_tc_set_attrs() {           // per context / device, from wb_create (see mel_set_attrs)
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+}
+
 // qkv: [B][T][3d] bf16 (q | k | v), out: [B][T][d] bf16.
 void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H) {
     static EncodeTiledFn fn = nullptr;
@@ -343,7 +347,6 @@ void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H
         CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
         WB_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, WB_ECUDA, "cuTensorMapEncodeTiled not available");
         fn = reinterpret_cast<EncodeTiledFn>(p);
-        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
     }
     WB_REQUIRE(d == H * HD, WB_EINVAL, "attention kernel needs head_dim 64");
     CUtensorMap tm;

@@ -142,6 +142,7 @@ struct wb_ctx {
 
 // mel.cu
 void mel_build_tables(MelTables& t);
+void mel_set_attrs();
 int64_t mel_n_frames(int64_t n);
 void mel_launch_raw(wb_ctx* ctx);
 void mel_launch_chunks(wb_ctx* ctx, int chunk0, int n, void* out);
@@ -171,12 +172,14 @@ struct GemmArgs {
 };
 void gemm_simt(wb_ctx* ctx, const GemmArgs& a);
 // gemm_tc.cu — tcgen05/TMEM/TMA kernel (bf16 operands, K-major, N % 128 == 0)
+void gemm_tc_set_attrs();
 bool gemm_tc_eligible(const GemmArgs& a);
 void gemm_tc(wb_ctx* ctx, const GemmArgs& a);
 // dispatcher: tensor-core kernel when eligible, else SIMT
 void gemm(wb_ctx* ctx, const GemmArgs& a);
 
 // attn_tc.cu — tcgen05 flash attention (bf16 build)
+void attn_tc_set_attrs();
 bool attn_tc_enabled();
 void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H);
 // encoder.cu

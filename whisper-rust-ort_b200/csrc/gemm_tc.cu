@@ -390,13 +390,12 @@ bool gemm_tc_eligible(const GemmArgs& g) {
            (g.batch == 1 || (g.sAo % 8 == 0 && g.inner <= 1)) && (g.ld_rowadd % 4 == 0);
 }
 
+void gemm_tc_set_attrs() {           // per context / device, from wb_create (see mel_set_attrs)
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128>::SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<256>::SMEM));
+}
+
 void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
-    static bool attr = false;
-    if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128>::SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<256>::SMEM));
-        attr = true;
-    }
     static int wide = -1;                           // WB_TC_BN256=0: 128-wide tiles everywhere
     if (wide < 0) { const char* e = getenv("WB_TC_BN256"); wide = !(e && e[0] == '0'); }
     // wide tiles where there are enough of them: at N = 512 the 128x256 grid is 5.07 waves of 148 CTAs and the

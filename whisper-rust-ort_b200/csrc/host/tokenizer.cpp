@@ -15,10 +15,10 @@
 
 struct wb_tokenizer {
     std::vector<std::string> id_to_token;
-    std::vector<unsigned char> is_special, is_added;
+    std::vector<unsigned char> is_special, is_added, present;
     std::unordered_map<std::string, int64_t> token_to_id;
     int byte_of_char[512];          // GPT-2 bytes_to_unicode inverse; -1 = not a byte-level char
-    bool byte_level = true;
+    bool byte_level = true;         // "decoder": {"type": "ByteLevel"}; false = no decoder section (tokens joined by ' ')
 };
 
 namespace {
@@ -36,17 +36,23 @@ void build_byte_map(wb_tokenizer& t) {
 
 std::string decode_ids(const wb_tokenizer& t, const int64_t* ids, int n, bool skip_special) {
     std::string bytes;
+    bool first = true;
     for (int i = 0; i < n; ++i) {
         // main.rs:639: ids that do not fit u32 are dropped; unknown ids are skipped by the crate
         if (ids[i] < 0 || ids[i] >= (int64_t)t.id_to_token.size()) continue;
         const size_t id = (size_t)ids[i];
+        if (!t.present[id]) continue;             // a hole in the id space: id_to_token() is None
         if (skip_special && t.is_special[id]) continue;
         const std::string& tok = t.id_to_token[id];
-        if (tok.empty()) continue;
         // every surviving token goes through the ByteLevel decoder, added (non-special) ones included, exactly as
         // tokenizers' decode_chain does: a token whose characters are all byte-level characters becomes those bytes,
         // any other token is taken as its raw UTF-8 text
-        if (!t.byte_level) { bytes += tok; continue; }
+        if (!t.byte_level) {                     // Tokenizer::decode without a decoder: tokens.join(" ")
+            if (!first) bytes += ' ';
+            first = false;
+            bytes += tok;
+            continue;
+        }
         std::string piece;
         bool ok = true;
         size_t j = 0;
@@ -85,7 +91,9 @@ int wb_tokenizer_load(wb_tokenizer** out, const char* path) {
                 t->id_to_token.resize((size_t)id + 1);
                 t->is_special.resize((size_t)id + 1, 0);
                 t->is_added.resize((size_t)id + 1, 0);
+                t->present.resize((size_t)id + 1, 0);
             }
+            t->present[(size_t)id] = 1;
             t->id_to_token[(size_t)id] = tok;
             t->is_special[(size_t)id] = special;
             t->is_added[(size_t)id] = added;
@@ -96,7 +104,14 @@ int wb_tokenizer_load(wb_tokenizer** out, const char* path) {
         for (const auto& a : root["added_tokens"].arr())
             put((int64_t)a["id"].num(), a["content"].str(), a["special"].type == wbjson::Value::Bool && a["special"].b, true);
         const wbjson::Value& dec = root["decoder"];
-        t->byte_level = dec.is_null() || dec["type"].str() == "ByteLevel";
+        // the reference's model (openai/whisper-*) ships a ByteLevel decoder; a file without a decoder section decodes
+        // to the tokens joined by ' ' (tokenizers: Tokenizer::decode); other decoder types are not restated here
+        if (dec.is_null()) t->byte_level = false;
+        else {
+            WB_REQUIRE(dec["type"].str() == "ByteLevel", WB_EINVAL, "Failed to load tokenizer %s: decoder type '%s' is not supported (ByteLevel only)",
+                       path, dec["type"].str().c_str());
+            t->byte_level = true;
+        }
         WB_REQUIRE(!t->id_to_token.empty(), WB_EINVAL, "Failed to load tokenizer %s: empty vocabulary", path);
         *out = t;
         return WB_OK;

@@ -322,13 +322,14 @@ int64_t mel_n_frames(int64_t n) {
     return nf;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: called from wb_create for every context (after
+// cudaSetDevice), never behind a process-wide flag (a second GPU in the same process would miss the opt-in).
+void mel_set_attrs() {
+    CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MEL_SMEM));
+}
+
 void mel_launch_raw(wb_ctx* ctx) {
     MelState& s = ctx->mel;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MEL_SMEM));
-        attr_done = true;
-    }
     // -inf as int bits
     std::vector<int> init(s.n_files, (int)0xff800000u);
     CUDA_CHECK(cudaMemcpyAsync(s.fmax.p, init.data(), sizeof(int) * s.n_files, cudaMemcpyHostToDevice, ctx->stream));

@@ -62,8 +62,17 @@ def write_wav(path: str, pcm: np.ndarray, sr: int = SR, fmt: str = "s16", channe
     else:
         raise ValueError(fmt)
     block = channels * bits // 8
-    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE"
-    hdr += b"fmt " + struct.pack("<IHHIIHH", 16, tag, channels, sr, sr * block, block, bits)
+    if channels <= 2:
+        fmt_body = struct.pack("<HHIIHH", tag, channels, sr, sr * block, block, bits)
+    else:
+        # symphonia's fmt_pcm / fmt_ieee chunks are mono or stereo only: more channels need WAVE_FORMAT_EXTENSIBLE
+        # with one channel-mask bit per channel
+        fmt_body = (struct.pack("<HHIIHH", 0xFFFE, channels, sr, sr * block, block, bits) + struct.pack("<HHI", 22, bits, (1 << channels) - 1)
+                    + struct.pack("<H", tag) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71")
+    pad = b"\0" * (len(data) & 1)
+    hdr = b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt_body) + 8 + len(data) + len(pad)) + b"WAVE"
+    hdr += b"fmt " + struct.pack("<I", len(fmt_body)) + fmt_body
     hdr += b"data" + struct.pack("<I", len(data))
+    data += pad
     with open(path, "wb") as f:
         f.write(hdr + data)
