@@ -76,6 +76,37 @@ def test_bf16_teacher_forced_logits_and_argmax(wb, fast, oracle, golden_dir):
     assert np.all(got[clear] == forced[clear])
 
 
+def test_bf16_batch32_128_steps_teacher_forced_vs_oracle(wb, oracle, golden_dir):
+    """The headline configuration itself (bf16 build, batch 32, 128 new tokens: BASELINE.json configs[3]) against the fp32
+    oracle, not only against itself: 4 distinct clips, each 8 times in the batch of 32, the oracle's greedy ids
+    (main.rs:753-829) teacher-forced for all 128 steps.  Logits of every row and step within 5e-2 of the oracle's
+    (logit std ~0.45), arg-max identical wherever the oracle's top-1 margin is clear of bf16 noise, and the 8 copies of a
+    clip bit-identical wherever they sit in the batch."""
+    g = np.load(f"{golden_dir}/hf_whisper_base_seed0.npz")
+    m = wb.Whisper(wb.default_cfg("base", precision=wb.WB_PREC_BF16, max_batch=32, max_chunks=32))
+    uniq = wb.synth.batch(4, seed=5)
+    idx = np.arange(32) % 4
+    steps = 128
+    mel = np.stack([mo.log_mel(c) for c in uniq])
+    ref_t, ref_l = oracle.greedy(oracle.encode(mel), g["prompt"], steps, EOT, g["suppress"], g["begin_suppress"], return_logits=True)
+    ref_l = np.stack(ref_l, 1)                                      # [4][128][V]
+    forced = np.array([s[len(g["prompt"]):] for s in ref_t])
+    assert forced.shape == (4, steps)                               # random-init never emits EOT
+    m.encode(mel[idx])
+    toks, lg = m.greedy_decode(32, g["prompt"], steps, EOT, g["suppress"], g["begin_suppress"], forced=forced[idx], want_logits=True)
+    got = np.array([s[len(g["prompt"]):] for s in toks])
+    sup = np.isin(np.arange(ref_l.shape[-1]), g["suppress"])
+    top2 = np.sort(np.where(sup, -np.inf, ref_l), -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 0.1
+    assert clear.mean() > 0.3
+    for r in range(32):
+        k = idx[r]
+        assert np.abs(lg[r] - ref_l[k]).max() <= 5e-2, (r, float(np.abs(lg[r] - ref_l[k]).max()))
+        assert np.all(got[r][clear[k]] == forced[k][clear[k]])
+        assert np.array_equal(lg[r], lg[k])                         # same clip, other batch position: same bits
+    m.close()
+
+
 def test_bf16_fused_path_runs_and_is_deterministic(wb, fast):
     x = wb.synth.batch(3, seed=9)
     a, fa = fast.transcribe_batch(x, [50258, 50259, 50359, 50363], 12, EOT)

@@ -1,0 +1,108 @@
+"""One-off GPU measurements behind the numbers in DESIGN.md / profiles/ (not the bench contract; see bench.py).
+
+  python tools/gpu_probe.py decode [B] [new_tokens]   cluster-chained decoder layers vs the per-kernel path:
+                                                      token agreement, ms per decode, ms per step
+  python tools/gpu_probe.py inflight [S...]           throughput with S batches of 32 in flight
+  python tools/gpu_probe.py kernels                   cross_attn / vocab_proj / logmel replays (wb_bench_kernel)
+"""
+import json
+import os
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import wb200  # noqa: E402
+
+PROMPT, EOT = [50258, 50259, 50359, 50363], 50257
+
+
+def make(B, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return wb200.Whisper(wb200.default_cfg("base", precision=wb200.WB_PREC_BF16, max_batch=B, max_chunks=B))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def decode(argv):
+    B = int(argv[0]) if argv else 32
+    new = int(argv[1]) if len(argv) > 1 else 128
+    pcm = wb200.synth.fast_batch(B, seed=1)
+    out = {}
+    toks = {}
+    for name, env in (("cluster", {"WB_DEC_CLUSTER": "1"}), ("per_kernel", {"WB_DEC_CLUSTER": "0"})):
+        m = make(B, **env)
+        m.upload_pcm(pcm)
+        m.run_log_mel()
+        m.encode(None, 0, B, want_hidden=False)
+        best = 1e9
+        for _ in range(4):
+            t = m.greedy_decode(B, PROMPT, new, EOT)
+            tm = m.timing()
+            best = min(best, tm["decode_ms"])
+        toks[name] = t
+        out[name] = {"decode_ms": best, "ms_per_step": best / (len(PROMPT) + new - 1), "launches": tm["decode_launches"],
+                     "steps": tm["decode_steps"]}
+        m.close()
+    a, b = np.array(toks["cluster"]), np.array(toks["per_kernel"])
+    same = (a == b)
+    first_diff = [int(np.argmax(~r)) if not r.all() else -1 for r in same]
+    out["token_agreement"] = {"frac": float(same.mean()), "rows_identical": int(same.all(1).sum()), "rows": B,
+                              "first_diff_pos_per_row": first_diff}
+    out["head"] = {"cluster": toks["cluster"][0][:12], "per_kernel": toks["per_kernel"][0][:12]}
+    print(json.dumps(out, indent=1))
+
+
+def inflight(argv):
+    counts = [int(x) for x in argv] or [1, 2, 4]
+    B = 32
+    pcm = wb200.synth.fast_batch(B, seed=1)
+    out = {}
+    for S in counts:
+        ctxs = [make(B) for _ in range(S)]
+        for c in ctxs:
+            c.upload_pcm(pcm)
+        def work(i, n):
+            for _ in range(n):
+                ctxs[i].transcribe_resident(B, PROMPT, 128, EOT)
+        for phase, n in (("warm", 2), ("timed", 6)):
+            th = [threading.Thread(target=work, args=(i, n)) for i in range(S)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            dt = time.perf_counter() - t0
+        out[S] = {"audio_s_per_s": S * 6 * B * 30 / dt, "ms_per_batch": 1000 * dt / (S * 6), "stage_ms": ctxs[0].timing()}
+        for c in ctxs:
+            c.close()
+    print(json.dumps(out, indent=1))
+
+
+def kernels(argv):
+    B = 32
+    m = make(B)
+    m.upload_pcm(wb200.synth.fast_batch(B, seed=1))
+    m.run_log_mel()
+    m.encode(None, 0, B, want_hidden=False)
+    m.greedy_decode(B, PROMPT, int(argv[0]) if argv else 64, EOT)
+    out = {}
+    for k, it in (("cross_attn", 30), ("vocab_proj", 20), ("dec_vocab", 20), ("logmel", 10)):
+        ms, by = m.bench_kernel(k, B, it)
+        out[k] = {"ms": ms, "bytes": by, "GBps": by / ms / 1e6}
+    for b in ([int(x) for x in os.environ["WB_PROBE_B"].split(",")] if "WB_PROBE_B" in os.environ else (1, 4, 7, 14, 28, 32)):
+        ms, by = m.bench_kernel("dec_layers", b, 20)
+        out[f"dec_layers_B{b}"] = {"ms": ms, "bytes": by, "GBps": by / ms / 1e6}
+    print(json.dumps(out, indent=1))
+    m.close()
+
+
+if __name__ == "__main__":
+    {"decode": decode, "inflight": inflight, "kernels": kernels}[sys.argv[1]](sys.argv[2:])

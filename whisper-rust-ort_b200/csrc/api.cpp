@@ -240,16 +240,10 @@ void wb_destroy(wb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);          // own work only (see wb_create)
-    for (int k = 0; k < 3; ++k)
-        if (ctx->dec.side[k]) cudaStreamSynchronize(ctx->dec.side[k]);
+    dec_cluster_free(ctx);
     weights_free(ctx);
     for (auto& g : ctx->dec.graphs) cudaGraphExecDestroy(g.exec);
     if (ctx->dec.unfinished_host) cudaFreeHost(ctx->dec.unfinished_host);
-    for (int k = 0; k < 3; ++k) {
-        if (ctx->dec.side[k]) cudaStreamDestroy(ctx->dec.side[k]);
-        if (ctx->dec.ev_join[k]) cudaEventDestroy(ctx->dec.ev_join[k]);
-    }
-    if (ctx->dec.ev_fork) cudaEventDestroy(ctx->dec.ev_fork);
     if (ctx->mel_tables_dev) cudaFree(ctx->mel_tables_dev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

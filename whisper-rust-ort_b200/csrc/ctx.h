@@ -106,20 +106,18 @@ struct DecBufs {
     DevBuf<int> tokens;                // [B][T_total] generated+prompt ids (device)
     DevBuf<int> forced;                // [B][max_new] teacher forcing (optional)
     DevBuf<int> lens, finished, state; // state: [0]=position t, [1]=#unfinished
-    DevBuf<float> xscratch;            // cross-attention split-key partials [B][H][XSPLIT][64+2]
-    DevBuf<int> xcount;                // arrival counters [B][H]
     DevBuf<float> amax_buf;            // fused arg-max partials of the vocabulary projection
     float* amax_val = nullptr; int* amax_idx = nullptr; int* amax_state = nullptr; int amax_ctas = 0;
-    bool fuse_argmax = true, want_logits = false, fuse_chain = false;
+    bool fuse_argmax = true, want_logits = false;
     DevBuf<unsigned int> sup_base, sup_first;   // vocab bitmaps
     int T_max = 0;
+    int last_T_total = 0;              // prompt_len + max_new of the last decode (layout of `tokens`)
     // decode-segment CUDA graphs (prompt prefix, SEG generated tokens, remainder), cached by key
     std::vector<DecGraph> graphs;
     int* unfinished_host = nullptr;    // mapped: sequences still running, written at the end of a segment
     int* unfinished_dev = nullptr;
     bool pdl = false;                  // programmatic dependent launch for the decode chain
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // parallel sub-batch chains
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    struct DecCluster* cluster = nullptr;   // dec_cluster.cu: all layers of a step in one launch (bf16, whisper-base widths)
 };
 
 struct wb_ctx {
@@ -186,6 +184,17 @@ void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H
 int attention_simt(wb_ctx* ctx, const void* qkv, void* att, int B);
 void encoder_alloc(wb_ctx* ctx);
 void encoder_forward(wb_ctx* ctx, const void* mel_tm, int B);   // mel_tm: [B][3002][n_mels] compute dtype
+// dec_cluster.cu — embedding + all decoder layers of one step as ONE cluster-chained launch
+void dec_cluster_alloc(wb_ctx* ctx);
+void dec_cluster_free(wb_ctx* ctx);
+bool dec_cluster_enabled(const wb_ctx* ctx);
+bool dec_cluster_vocab_ok(const wb_ctx* ctx, int B);
+void dec_cluster_vocab(wb_ctx* ctx, cudaStream_t st, bool pdl, int* state, int B, float* logits, const int* forced, int max_new, int eot,
+                       int T_total, int* cur_tok);
+double dec_cluster_vocab_bytes(const wb_ctx* ctx);
+double dec_cluster_bytes(const wb_ctx* ctx, int B);
+void dec_cluster_print_prof(wb_ctx* ctx);
+void dec_cluster_layers(wb_ctx* ctx, cudaStream_t st, bool pdl, const int* state, const int* prompt_dev, const int* cur_tok, int B);
 // decoder.cu
 void decoder_alloc(wb_ctx* ctx);
 struct DecodeParams {

@@ -30,23 +30,16 @@ __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-static thread_local int g_cluster = 0;         // cluster size for the next launch_k (0 = none)
 template <typename... KArgs, typename... Args>
 void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     int na = 0;
     if (pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
-    }
-    if (g_cluster > 0) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = (unsigned)g_cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-        ++na;
-        g_cluster = 0;
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
@@ -298,17 +291,11 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
 }
 
 // ---- cross-attention over the cached encoder K/V: the dominant HBM stream of a step ----
-// grid (H, B, XSPLIT), 256 threads.  Single pass, flash-decoding style: every lane group (8 lanes
+// grid (H, B), 256 threads.  Single pass, flash-decoding style: every lane group (8 lanes
 // in f32, 4 in bf16: 32 bytes of a 64-wide row per lane) walks its keys with an online softmax,
 // loading the K and the V row of UN keys together (raw 128-bit registers, converted on use), so a
-// CTA exposes Tk / (groups * UN * XSPLIT) memory round trips instead of two passes over the keys.
-// Groups merge by shuffles, warps through shared memory, the XSPLIT key ranges of a (b,h) pair
-// through a global scratch + arrival counter: the last CTA to arrive writes the output.
-#ifndef WB_XSPLIT
-#define WB_XSPLIT 1
-#endif
-constexpr int XSPLIT = WB_XSPLIT;
-
+// CTA exposes Tk / (groups * UN) memory round trips instead of two passes over the keys.
+// Groups merge by shuffles, warps through shared memory.
 template <typename KT> struct RowRaw;
 template <> struct RowRaw<float> {
     static constexpr int DPL = 8;
@@ -333,16 +320,14 @@ template <> struct RowRaw<bf16> {
 
 template <typename KT, int NW>          // NW warps per CTA: 8, or 4 when H*B would not fit one wave of 8-warp CTAs
 __global__ void __launch_bounds__(NW * 32)
-cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out,
-                  float* __restrict__ scratch, int* __restrict__ counters, int d, int Tk) {
+cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out, int d, int Tk) {
     constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = NW * 32 / LPR, UN = 4;
     __shared__ float s_m[NW], s_l[NW];
     __shared__ float s_acc[NW][64];
-    __shared__ int s_last;
-    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, H = gridDim.x;
+    const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / LPR, li = tid % LPR;
-    const int per = (Tk + XSPLIT - 1) / XSPLIT, k_lo = sp * per, k_hi = min(Tk, k_lo + per);
+    const int k_lo = 0, k_hi = Tk;
     // lane li owns dims [li*DPL/2, +DPL/2) and [32 + li*DPL/2, +DPL/2): each 128-bit load instruction of a
     // lane group then covers whole 32-byte sectors of consecutive bytes of the row
     constexpr int HPL = DPL / 2;
@@ -435,37 +420,7 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
             lt = fmaf(s_l[w], wgt, lt);
         }
     }
-    if (XSPLIT == 1) {
-        if (tid < 64) out[(size_t)b * d + h * 64 + tid] = my / lt;
-        return;
-    }
-    // publish this key range, the last CTA of the (b,h) pair combines them
-    float* rec = scratch + ((size_t)(b * H + h) * XSPLIT + sp) * 66;
-    if (tid < 64) rec[tid] = my;
-    if (tid == 0) { rec[64] = mt; rec[65] = lt; }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int prev = atomicAdd(counters + b * H + h, 1);
-        s_last = (prev == XSPLIT - 1);
-        if (s_last) counters[b * H + h] = 0;           // ready for the next launch
-    }
-    __syncthreads();
-    if (s_last && tid < 64) {
-        __threadfence();
-        const float* r0 = scratch + (size_t)(b * H + h) * XSPLIT * 66;
-        float mm = -INFINITY;
-#pragma unroll
-        for (int s2 = 0; s2 < XSPLIT; ++s2) mm = fmaxf(mm, __ldcg(r0 + s2 * 66 + 64));
-        float a = 0.f, ll = 0.f;
-#pragma unroll
-        for (int s2 = 0; s2 < XSPLIT; ++s2) {
-            const float wgt = expf(__ldcg(r0 + s2 * 66 + 64) - mm);
-            a = fmaf(__ldcg(r0 + s2 * 66 + tid), wgt, a);
-            ll = fmaf(__ldcg(r0 + s2 * 66 + 65), wgt, ll);
-        }
-        out[(size_t)b * d + h * 64 + tid] = a / ll;
-    }
+    if (tid < 64) out[(size_t)b * d + h * 64 + tid] = my / lt;
 }
 
 // ---- decoder self-attention for the new token (causal = all cached keys 0..s) ----
@@ -689,37 +644,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // one cross-attention launch over B sequences
 template <typename WT>
-void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, float* scratch, int* counters,
-                       int H, int B, int d, int Tk) {
+void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, int H, int B, int d, int Tk) {
     // 8-warp CTAs hold 2 per SM (register file), 4-warp CTAs 4 per SM.  When the (b,h) pairs overflow one wave of
     // 8-warp CTAs but fit one wave of 4-warp CTAs, the smaller shape keeps every pair streaming at once instead of
     // leaving a few CTAs to run alone at the end (large-v3 widths at batch 16: 320 pairs on 148 SMs).
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int units = H * B * XSPLIT;
+    const int units = H * B;
     if (units > 2 * sms && units <= 4 * sms)
-        launch_k(cross_attn_kernel<WT, 4>, dim3(H, B, XSPLIT), dim3(128), 0, st, pdl, q, ckv, att, scratch, counters, d, Tk);
+        launch_k(cross_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, q, ckv, att, d, Tk);
     else
-        launch_k(cross_attn_kernel<WT, 8>, dim3(H, B, XSPLIT), dim3(256), 0, st, pdl, q, ckv, att, scratch, counters, d, Tk);
+        launch_k(cross_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, q, ckv, att, d, Tk);
 }
 
 constexpr int MM_THREADS = 256;
 
-// How a stage waits for its input: SYNC_PDL = the predecessor KERNEL (griddepcontrol), SYNC_CLUSTER =
-// the predecessor STAGE of the same kernel, run by the other CTAs of this thread-block cluster.
-enum { SYNC_PDL = 0, SYNC_CLUSTER = 1 };
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-template <int MODE> __device__ __forceinline__ void stage_sync() {
-    if (MODE == SYNC_PDL) pdl_sync(); else cluster_barrier();
-}
-
-// One skinny GEMM "stage" executed by CTA `cta` of `ncta` cooperating CTAs (a whole grid, or one
-// thread-block cluster).  Activations are exchanged through global memory (L2): loads use ld.cg so a
-// value written by another CTA before the barrier is never served from a stale L1 line.
-template <int RW, int KS, int NCH, int NP, int MODE>   // K = KS slices x NP passes x NCH chunks of 32
+// One skinny GEMM executed by CTA `cta` of the `ncta` CTAs of the grid.
+template <int RW, int KS, int NCH, int NP>   // K = KS slices x NP passes x NCH chunks of 32
 __device__ __forceinline__ void
 mma_stage(unsigned char* mm_smem, int cta, int ncta,
           const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
@@ -760,7 +701,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             }
         }
         if (!synced) {
-            stage_sync<MODE>();
+            pdl_sync();
             synced = true;
             if (amax_val) sup = (state[0] - (state[1] - 1) == 0) ? sup_first : sup_base;   // first generated token?
             // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
@@ -1005,7 +946,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             amax_idx[cta * 32 + tid] = bi;
         }
     }
-    if (!synced) stage_sync<MODE>();                // a CTA without tiles still takes part in the barrier
+    if (!synced) pdl_sync();                        // a CTA without tiles still releases its dependents
 }
 
 template <int RW, int KS, int NCH, int NP>
@@ -1016,48 +957,8 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                   const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
                   float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     extern __shared__ __align__(16) unsigned char mm_smem[];
-    mma_stage<RW, KS, NCH, NP, SYNC_PDL>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
+    mma_stage<RW, KS, NCH, NP>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
                                      state, sup_base, sup_first, amax_val, amax_idx);
-}
-
-// ---- cluster-chained decoder stages (bf16 build, d_model 512 / ffn 2048) ----
-// The GEMMs between two attention kernels form a chain with grid-wide dependencies (each needs the
-// full rows its predecessor produced).  Instead of one launch per GEMM, one thread-block cluster
-// of CL CTAs runs the whole chain: every CTA computes its share of a stage's output rows, the
-// hardware cluster barrier (release/acquire) replaces the kernel boundary, and the weights of the
-// next stage are already in flight when the barrier is reached.
-struct ChainStage {
-    const float* X; const bf16* W; const float* bias; const float* ln_w; const float* ln_b; const float* residual; float* Y;
-    int N, K, act;
-};
-struct ChainArgs {
-    ChainStage st[4];
-    int n_stages, B;
-};
-
-__device__ __forceinline__ int cluster_rank() { int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ int cluster_size() { int r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-
-template <int MODE>
-__device__ __forceinline__ void chain_stage(unsigned char* smem, int cta, int ncta, const ChainStage& s, int B) {
-    if (s.K == 512) {
-        if (s.N > 1024) mma_stage<4, 2, 8, 1, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
-        else mma_stage<2, 4, 4, 1, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
-    } else {    // K == 2048
-        mma_stage<2, 4, 16, 1, MODE>(smem, cta, ncta, s.X, B, s.K, s.W, s.N, s.bias, s.ln_w, s.ln_b, s.act, s.residual, s.Y, nullptr, nullptr, nullptr, nullptr, nullptr);
-    }
-}
-
-__global__ void __launch_bounds__(MM_THREADS, 1)
-dec_chain_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) unsigned char mm_smem[];
-    const int cta = cluster_rank(), ncta = cluster_size();
-    chain_stage<SYNC_PDL>(mm_smem, cta, ncta, a.st[0], a.B);
-#pragma unroll 1
-    for (int i = 1; i < a.n_stages; ++i) {
-        __syncthreads();                            // this CTA is done with the shared tile of the previous stage
-        chain_stage<SYNC_CLUSTER>(mm_smem, cta, ncta, a.st[i], a.B);
-    }
 }
 
 template <int RW, int KS, int NCH, int NP = 1>
@@ -1123,22 +1024,8 @@ void skinny_mma_set_attrs() {       // once per process, outside any stream capt
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
-constexpr int CHAIN_CLUSTER = 8;
-constexpr size_t CHAIN_SMEM = 32 * (2048 * 2 + 64) + sizeof(float) * 8 * 16 * 33;
-
-ChainStage chain_stage_of(const float* X, const LinearW& L, const LNW* ln, int act, const float* residual, float* Y) {
-    ChainStage c{};
-    c.X = X; c.W = reinterpret_cast<const bf16*>(L.w); c.bias = L.b; c.ln_w = ln ? ln->w : nullptr; c.ln_b = ln ? ln->b : nullptr;
-    c.residual = residual; c.Y = Y; c.N = L.out; c.K = L.in; c.act = act;
-    return c;
-}
-void launch_chain(wb_ctx* ctx, cudaStream_t st, const ChainArgs& a) {
-    g_cluster = CHAIN_CLUSTER;
-    launch_k(dec_chain_kernel, dim3(CHAIN_CLUSTER), dim3(MM_THREADS), CHAIN_SMEM, st, ctx->dec.pdl, a);
-}
 inline bool skinny_mma(wb_ctx*, const float*, int, int, const float*, int, const float*, const float*, const float*, int,
                        const float*, float*) { return false; }     // fp32 validation build stays on the SIMT kernel
 
@@ -1180,64 +1067,44 @@ void set_func_attrs() {
     CUDA_CHECK(cudaFuncSetAttribute(skinny_gemm_kernel<WT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
-// Enqueue one decode step.  with_logits: final LN + tied vocab projection + argmax.
+// Enqueue one decode step for sequences [0, B).  with_logits: final LN + tied vocab projection + argmax.
 template <typename WT>
-int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool with_logits, const int* prompt_dev,
+int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logits, const int* prompt_dev,
                  const int* forced_dev, int max_new, int eot, int T_total, bool first) {
-    // One decode step for sequences [b0, b0+B) on stream `st` with its own step counter `state`:
-    // sub-batches of a decode run as independent chains on parallel graph branches.
     const wb_model_cfg& c = ctx->cfg;
     const int d = c.d_model, H = c.n_heads, Tk = c.n_audio_ctx;
     DecBufs& D = ctx->dec;
     ModelW& w = ctx->w;
-    float* x = D.x.p + (size_t)b0 * d;
-    float* qkv = D.qkv.p + (size_t)b0 * 3 * d;
-    float* att = D.att.p + (size_t)b0 * d;
-    float* q = D.q.p + (size_t)b0 * d;
-    float* ffn = D.ffn.p + (size_t)b0 * c.ffn_dim;
-    float* logits = D.logits.p + (size_t)b0 * c.vocab;
-    int* cur_tok = D.tokens.p + (size_t)c.max_batch * T_total + b0;
+    float* x = D.x.p;
+    int* cur_tok = D.tokens.p + (size_t)c.max_batch * T_total;
     int n = 0;
-    cudaStream_t saved = ctx->stream;
-    ctx->stream = st;                                        // skinny() launches on ctx->stream
     const bool pdl = D.pdl;
-    // the first kernel of a chain follows memcpy nodes, not a kernel: plain launch
-    launch_k(embed_kernel<WT>, dim3(B), dim3(128), 0, st, pdl && !first, (const int*)state, prompt_dev, (const int*)cur_tok, (const WT*)w.embed, (const float*)w.dec_pos, x, d); ++n;
-    // bf16 build at whisper-base widths: the GEMM chains between the attention kernels run as
-    // cluster-chained stages (dec_chain_kernel): 4 launches per layer instead of 8.
-    const bool chain = sizeof(WT) == 2 && D.fuse_chain && skinny_mma_enabled() && B <= 32 && d == 512 && c.ffn_dim == 2048;
-    for (int l = 0; l < c.dec_layers; ++l) {
-        const DecLayerW& L = w.dec[l];
-        WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + ((size_t)l * c.max_batch + b0) * D.T_max * 2 * d;
-        const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + ((size_t)l * c.max_batch + b0) * Tk * 2 * d;
-        if (!chain || l == 0) { skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, qkv); ++n; }              // K3c
-        launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)qkv, skv, att, d, D.T_max); ++n;   // K3d
-        if (chain) {
-            ChainArgs a{};
-            a.B = B; a.n_stages = 2;
-            a.st[0] = chain_stage_of(att, L.o, nullptr, 0, x, x);                                             // K3f
-            a.st[1] = chain_stage_of(x, L.cq, &L.ln2, 0, nullptr, q);
-            launch_chain(ctx, st, a); ++n;
-        } else {
-            skinny<WT>(ctx, att, B, d, L.o, nullptr, 0, x, x); ++n;
-            skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, q); ++n;
+    if (sizeof(WT) == 2 && dec_cluster_enabled(ctx)) {
+        // bf16 build at whisper-base widths: embedding + all decoder layers in ONE launch (dec_cluster.cu).
+        // The first kernel of a graph follows memcpy nodes, not a kernel: plain launch.
+        dec_cluster_layers(ctx, st, pdl && !first, state, prompt_dev, cur_tok, B); ++n;
+    } else {
+        launch_k(embed_kernel<WT>, dim3(B), dim3(128), 0, st, pdl && !first, (const int*)state, prompt_dev, (const int*)cur_tok, (const WT*)w.embed, (const float*)w.dec_pos, x, d); ++n;
+        for (int l = 0; l < c.dec_layers; ++l) {
+            const DecLayerW& L = w.dec[l];
+            WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + (size_t)l * c.max_batch * D.T_max * 2 * d;
+            const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + (size_t)l * c.max_batch * Tk * 2 * d;
+            skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, D.qkv.p); ++n;                                             // K3c
+            launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max); ++n;   // K3d
+            skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, x, x); ++n;                                                      // K3f
+            skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
+            launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk); ++n;                          // K3e
+            skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, x, x); ++n;
+            skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                                               // K3g
+            skinny<WT>(ctx, D.ffn.p, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
         }
-        launch_cross_attn<WT>(st, pdl, (const float*)q, ckv, att,
-                              D.xscratch.p + (size_t)b0 * H * XSPLIT * 66, D.xcount.p + (size_t)b0 * H, H, B, d, Tk); ++n;   // K3e
-        if (chain) {
-            ChainArgs a{};
-            a.B = B;
-            a.st[0] = chain_stage_of(att, L.co, nullptr, 0, x, x);
-            a.st[1] = chain_stage_of(x, L.fc1, &L.ln3, 1, nullptr, ffn);                                      // K3g
-            a.st[2] = chain_stage_of(ffn, L.fc2, nullptr, 0, x, x);
-            a.n_stages = 3;
-            if (l + 1 < c.dec_layers) { a.st[3] = chain_stage_of(x, w.dec[l + 1].qkv, &w.dec[l + 1].ln1, 0, nullptr, qkv); a.n_stages = 4; }
-            launch_chain(ctx, st, a); ++n;
-        } else {
-            skinny<WT>(ctx, att, B, d, L.co, nullptr, 0, x, x); ++n;
-            skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, ffn); ++n;
-            skinny<WT>(ctx, ffn, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
-        }
+    }
+    if (with_logits && sizeof(WT) == 2 && dec_cluster_vocab_ok(ctx, B) && D.fuse_argmax) {
+        // bf16 build at whisper-base widths: final LN + vocabulary projection + arg-max + token bookkeeping + step advance
+        // in ONE launch (dec_cluster.cu): a decode step is two launches
+        dec_cluster_vocab(ctx, st, pdl, state, B, D.want_logits ? D.logits.p : nullptr, forced_dev, max_new, eot, T_total, cur_tok); ++n;
+        CUDA_CHECK(cudaGetLastError());
+        return n;
     }
     if (with_logits) {                                                                               // K3h
         LinearW dummy;
@@ -1245,24 +1112,21 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int b0, int B, int* state, bool w
         // unless the caller asked for logits); fp32 build: separate full arg-max over the logits.
         const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && c.vocab >= 8192 && (d == 512 || d == 128 || d == 1280);   // shapes with an mma vocab kernel
         D.amax_state = fuse ? state : nullptr;
-        const int slice = (int)((long long)b0 * 4 / c.max_batch);           // up to 4 concurrent sub-batch chains
-        D.amax_val = D.amax_buf.p + (size_t)slice * 64 * ctx->sm_count;      // per-chain slice: [ctas][32] val | idx
+        D.amax_val = D.amax_buf.p;                                           // [ctas][32] val | idx
         D.amax_idx = reinterpret_cast<int*>(D.amax_val + (size_t)32 * ctx->sm_count);
         D.amax_ctas = 0;
-        skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, (fuse && !D.want_logits) ? nullptr : logits, c.vocab, w.embed); ++n;
+        skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, (fuse && !D.want_logits) ? nullptr : D.logits.p, c.vocab, w.embed); ++n;
         D.amax_state = nullptr;
-        const int* fdev = forced_dev ? forced_dev + (size_t)b0 * max_new : (const int*)nullptr;
         if (fuse && D.amax_ctas > 0) {
             launch_k(argmax_merge_kernel, dim3(B), dim3(32), 0, st, pdl, (const int*)state, (const float*)D.amax_val, (const int*)D.amax_idx,
-                     D.amax_ctas, fdev, max_new, eot, T_total, D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
+                     D.amax_ctas, forced_dev, max_new, eot, T_total, D.tokens.p, D.lens.p, D.finished.p, cur_tok); ++n;
         } else {
-            launch_k(argmax_kernel, dim3(B), dim3(1024), 0, st, pdl, (const int*)state, (const float*)logits, c.vocab,
-                     (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p, fdev, max_new, eot, T_total,
-                     D.tokens.p + (size_t)b0 * T_total, D.lens.p + b0, D.finished.p + b0, cur_tok); ++n;
+            launch_k(argmax_kernel, dim3(B), dim3(1024), 0, st, pdl, (const int*)state, (const float*)D.logits.p, c.vocab,
+                     (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p, forced_dev, max_new, eot, T_total,
+                     D.tokens.p, D.lens.p, D.finished.p, cur_tok); ++n;
         }
     }
     launch_k(advance_kernel, dim3(1), dim3(1), 0, st, pdl, state); ++n;
-    ctx->stream = saved;
     CUDA_CHECK(cudaGetLastError());
     return n;
 }
@@ -1286,20 +1150,14 @@ void decoder_alloc(wb_ctx* ctx) {
     D.lens.reserve(B);
     D.finished.reserve(B);
     D.state.reserve(16);
-    D.xscratch.reserve(B * (size_t)c.n_heads * XSPLIT * 66);
-    D.xcount.reserve_zero(B * (size_t)c.n_heads);
-    D.amax_buf.reserve((size_t)4 * 64 * ctx->sm_count);
-    for (int k = 0; k < 3; ++k) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&D.side[k], cudaStreamNonBlocking));
-        CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_join[k], cudaEventDisableTiming));
-    }
-    CUDA_CHECK(cudaEventCreateWithFlags(&D.ev_fork, cudaEventDisableTiming));
+    D.amax_buf.reserve((size_t)64 * ctx->sm_count);
     CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&D.unfinished_host), sizeof(int), cudaHostAllocMapped));
     CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&D.unfinished_dev), D.unfinished_host, 0));
     const size_t words = ((size_t)c.vocab + 31) / 32;
     D.sup_base.reserve(words);
     D.sup_first.reserve(words);
     if (c.precision == WB_PREC_BF16) { set_func_attrs<bf16>(); skinny_mma_set_attrs(); } else set_func_attrs<float>();
+    dec_cluster_alloc(ctx);           // bf16 build at whisper-base widths: all layers of a step in one launch
 }
 
 void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
@@ -1307,6 +1165,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     DecBufs& D = ctx->dec;
     const int B = p.B, P = p.prompt_len, max_new = p.max_new < 1 ? 1 : p.max_new;   // main.rs:779,793
     const int T_total = P + max_new;
+    D.last_T_total = T_total;
     WB_REQUIRE(B >= 1 && B <= c.max_batch, WB_ECAP, "decode batch %d exceeds max_batch %d", B, c.max_batch);
     WB_REQUIRE(B <= ctx->enc.B_valid, WB_ESTATE, "decode batch %d but only %d sequences encoded", B, ctx->enc.B_valid);
     WB_REQUIRE(P >= 1 && T_total <= D.T_max, WB_ECAP, "prompt_len + max_new_tokens = %d exceeds n_text_ctx %d", T_total, D.T_max);
@@ -1330,7 +1189,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     CUDA_CHECK(cudaMemcpyAsync(D.tokens.p, tok.data(), sizeof(int) * tok.size(), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(D.sup_base.p, base.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(D.sup_first.p, first.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
-    std::vector<int> lens(B, P), st4 = {0, P, 0, 0, 0, P, 0, 0, 0, P, 0, 0, 0, P, 0, 0};
+    std::vector<int> lens(B, P), st4 = {0, P, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_CHECK(cudaMemcpyAsync(D.lens.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(D.finished.p, 0, sizeof(int) * B, st));
     CUDA_CHECK(cudaMemcpyAsync(D.state.p, st4.data(), sizeof(int) * 16, cudaMemcpyHostToDevice, st));
@@ -1352,48 +1211,24 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     const int steps = P + max_new - 1;
     int launches = 0;
     const bool bf = c.precision == WB_PREC_BF16;
-    // Sub-batches run as independent chains (own step counter, own stream / graph branch): a step is
-    // ~50 dependent small kernels, so two chains in flight hide each other's latency.
-    const char* senv = getenv("WB_DEC_SPLIT");
-    int nsplit = senv ? atoi(senv) : 1;      // measured on B200: 1 chain 102 ms, 2 chains 121 ms, 4 chains 166 ms
-    if (nsplit < 1) nsplit = 1;
-    if (nsplit > 4) nsplit = 4;
-    if (p.want_logits || B < 8 * nsplit) nsplit = 1;
     // enqueue `n_steps` consecutive steps (positions continue from the device-side counter); the last
     // one is followed by a tiny kernel that publishes how many sequences are still running
     auto enqueue_steps = [&](int n_steps, bool with_logits, int first_gi) {
         int n = 0;
-        if (nsplit > 1) {
-            CUDA_CHECK(cudaEventRecord(D.ev_fork, st));
-            for (int k = 1; k < nsplit; ++k) CUDA_CHECK(cudaStreamWaitEvent(D.side[k - 1], D.ev_fork, 0));
-        }
-        for (int k = 0; k < nsplit; ++k) {
-            const int lo = (int)((long long)B * k / nsplit), hi = (int)((long long)B * (k + 1) / nsplit);
-            cudaStream_t sk = k == 0 ? st : D.side[k - 1];
-            int* state_k = D.state.p + 4 * k;
-            for (int s = 0; s < n_steps; ++s) {
-                n += bf ? enqueue_step<bf16>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0)
-                        : enqueue_step<float>(ctx, sk, lo, hi - lo, state_k, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0);
-                if (with_logits && p.want_logits) {
-                    const int gi = first_gi + s;
-                    CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
-                                                 D.logits.p, sizeof(float) * c.vocab, sizeof(float) * c.vocab, B,
-                                                 cudaMemcpyDeviceToDevice, st));
-                }
+        for (int s = 0; s < n_steps; ++s) {
+            n += bf ? enqueue_step<bf16>(ctx, st, B, D.state.p, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0)
+                    : enqueue_step<float>(ctx, st, B, D.state.p, with_logits, prompt_dev, forced_dev, max_new, p.eot, T_total, s == 0);
+            if (with_logits && p.want_logits) {
+                const int gi = first_gi + s;
+                CUDA_CHECK(cudaMemcpy2DAsync(D.logits_all.p + (size_t)gi * c.vocab, sizeof(float) * (size_t)max_new * c.vocab,
+                                             D.logits.p, sizeof(float) * c.vocab, sizeof(float) * c.vocab, B,
+                                             cudaMemcpyDeviceToDevice, st));
             }
-        }
-        for (int k = 1; k < nsplit; ++k) {
-            CUDA_CHECK(cudaEventRecord(D.ev_join[k - 1], D.side[k - 1]));
-            CUDA_CHECK(cudaStreamWaitEvent(st, D.ev_join[k - 1], 0));
         }
         if (with_logits) { count_unfinished_kernel<<<1, 32, 0, st>>>(D.finished.p, B, D.unfinished_dev); ++n; }
         CUDA_CHECK(cudaGetLastError());
         return n;
     };
-    // Experimental: cluster-chained GEMM stages (dec_chain_kernel).  Correct, but measured SLOWER on B200
-    // (decode 111 ms vs 61 ms): 8 CTAs serialise the row tiles that 16-32 independent CTAs do in parallel.
-    const char* cenv = getenv("WB_DEC_CHAIN");
-    D.fuse_chain = cenv && cenv[0] == '1';
     const char* fenv = getenv("WB_FUSE_ARGMAX");
     D.fuse_argmax = !(fenv && fenv[0] == '0');
     D.want_logits = p.want_logits;
@@ -1408,7 +1243,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     auto run_segment = [&](int n_steps, bool with_logits, int first_gi) {
         if (!use_graph) return enqueue_steps(n_steps, with_logits, first_gi);
         const int key[8] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
-                            c.precision * 64 + nsplit * 8 + (D.pdl ? 4 : 0) + (D.fuse_chain ? 2 : 0) + (D.fuse_argmax ? 1 : 0),
+                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0),
                             n_steps, with_logits ? 1 : 0};
         DecGraph* g = nullptr;
         for (auto& e : D.graphs) {
@@ -1488,8 +1323,18 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
         const int l = i % c.dec_layers;
         if (k == "cross_attn") {
             const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * c.n_audio_ctx * 2 * d * ctx->esz();
-            if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, D.xscratch.p, D.xcount.p, H, B, d, Tk);
-            else launch_cross_attn<float>(ctx->stream, bench_pdl, D.q.p, (const float*)ckv, D.att.p, D.xscratch.p, D.xcount.p, H, B, d, Tk);
+            if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk);
+            else launch_cross_attn<float>(ctx->stream, bench_pdl, D.q.p, (const float*)ckv, D.att.p, H, B, d, Tk);
+        } else if (k == "dec_layers") {
+            WB_REQUIRE(bf && dec_cluster_enabled(ctx), WB_EINVAL, "dec_layers: the cluster-chained layer kernel is not active for this context");
+            WB_REQUIRE(D.last_T_total > 0, WB_ESTATE, "dec_layers bench needs a prior decode");
+            const int T_total = D.last_T_total;
+            dec_cluster_layers(ctx, ctx->stream, bench_pdl, D.state.p, D.tokens.p + (size_t)c.max_batch * T_total + c.max_batch,
+                               D.tokens.p + (size_t)c.max_batch * T_total, B);
+        } else if (k == "dec_vocab") {
+            WB_REQUIRE(bf && dec_cluster_vocab_ok(ctx, B) && D.last_T_total > 0, WB_EINVAL, "dec_vocab: the fused vocabulary kernel is not active for this context");
+            dec_cluster_vocab(ctx, ctx->stream, bench_pdl, D.state.p, B, nullptr, nullptr, 1, -1, D.last_T_total,
+                              D.tokens.p + (size_t)c.max_batch * D.last_T_total);
         } else if (k == "vocab_proj") {
             LinearW dummy;
             if (bf) skinny<bf16>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
@@ -1498,6 +1343,12 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
             WB_THROW(WB_EINVAL, "unknown bench kernel '%s'", kernel);
         }
     };
+    int saved_state[2] = {0, 0};
+    if (k == "dec_vocab") {          // the kernel advances the step and writes tokens of running sequences: freeze both
+        CUDA_CHECK(cudaMemcpyAsync(saved_state, D.state.p, sizeof(saved_state), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(D.finished.p, 1, sizeof(int) * c.max_batch, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     launch(0);
     CUDA_CHECK(cudaEventRecord(e0.e, ctx->stream));
     for (int i = 0; i < iters; ++i) launch(i + 1);
@@ -1507,7 +1358,13 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e0.e, e1.e));
     *avg_ms = ms / iters;
-    if (k == "cross_attn") *bytes = (double)B * 2.0 * Tk * d * ctx->esz() + (double)B * d * 8.0;      // K+V stream, q in, out
+    if (k == "dec_vocab") {
+        CUDA_CHECK(cudaMemcpyAsync(D.state.p, saved_state, sizeof(saved_state), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        *bytes = dec_cluster_vocab_bytes(ctx);
+    } else
+    if (k == "dec_layers") { *bytes = dec_cluster_bytes(ctx, B); dec_cluster_print_prof(ctx); }
+    else if (k == "cross_attn") *bytes = (double)B * 2.0 * Tk * d * ctx->esz() + (double)B * d * 8.0;      // K+V stream, q in, out
     else *bytes = (double)c.vocab * d * ctx->esz() + (double)B * c.vocab * 4.0 + (double)B * d * 4.0;  // weights, logits out
 }
 
