@@ -95,10 +95,17 @@ def kernels(argv):
     m.greedy_decode(B, PROMPT, int(argv[0]) if argv else 64, EOT)
     out = {}
     for k, it in (("cross_attn", 30), ("vocab_proj", 20), ("dec_vocab", 20), ("logmel", 10)):
-        ms, by = m.bench_kernel(k, B, it)
+        try:
+            ms, by = m.bench_kernel(k, B, it)
+        except wb200.WbError as e:          # a path that is switched off in this process
+            out[k] = {"ms": float("nan"), "bytes": 0.0, "GBps": float("nan"), "skipped": str(e)}
+            continue
         out[k] = {"ms": ms, "bytes": by, "GBps": by / ms / 1e6}
     for b in ([int(x) for x in os.environ["WB_PROBE_B"].split(",")] if "WB_PROBE_B" in os.environ else (1, 4, 7, 14, 28, 32)):
-        ms, by = m.bench_kernel("dec_layers", b, 20)
+        try:
+            ms, by = m.bench_kernel("dec_layers", b, 20)
+        except wb200.WbError:
+            break
         out[f"dec_layers_B{b}"] = {"ms": ms, "bytes": by, "GBps": by / ms / 1e6}
     print(json.dumps(out, indent=1))
     m.close()

@@ -189,6 +189,9 @@ void dec_cluster_alloc(wb_ctx* ctx);
 void dec_cluster_free(wb_ctx* ctx);
 bool dec_cluster_enabled(const wb_ctx* ctx);
 bool dec_cluster_vocab_ok(const wb_ctx* ctx, int B);
+// stand-alone cross-attention on the TMA ring + tensor cores (bf16 build, head_dim 64)
+bool cross_attn_tc_ok(const wb_ctx* ctx);
+void cross_attn_tc(wb_ctx* ctx, cudaStream_t st, bool pdl, int layer, const float* q, float* out, int B);
 void dec_cluster_vocab(wb_ctx* ctx, cudaStream_t st, bool pdl, int* state, int B, float* logits, const int* forced, int max_new, int eot,
                        int T_total, int* cur_tok);
 double dec_cluster_vocab_bytes(const wb_ctx* ctx);

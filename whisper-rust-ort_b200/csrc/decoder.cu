@@ -1093,7 +1093,9 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
             launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max); ++n;   // K3d
             skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, x, x); ++n;                                                      // K3f
             skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
-            launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk); ++n;                          // K3e
+            if (sizeof(WT) == 2 && cross_attn_tc_ok(ctx)) cross_attn_tc(ctx, st, pdl, l, D.q.p, D.att.p, B);                // K3e
+            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk);
+            ++n;
             skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, x, x); ++n;
             skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                                               // K3g
             skinny<WT>(ctx, D.ffn.p, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
@@ -1243,7 +1245,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     auto run_segment = [&](int n_steps, bool with_logits, int first_gi) {
         if (!use_graph) return enqueue_steps(n_steps, with_logits, first_gi);
         const int key[8] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
-                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0),
+                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0) + (cross_attn_tc_ok(ctx) ? 8 : 0),
                             n_steps, with_logits ? 1 : 0};
         DecGraph* g = nullptr;
         for (auto& e : D.graphs) {
@@ -1323,7 +1325,8 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
         const int l = i % c.dec_layers;
         if (k == "cross_attn") {
             const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * c.n_audio_ctx * 2 * d * ctx->esz();
-            if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk);
+            if (bf && cross_attn_tc_ok(ctx) && Tk == c.n_audio_ctx) cross_attn_tc(ctx, ctx->stream, bench_pdl, l, D.q.p, D.att.p, B);
+            else if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk);
             else launch_cross_attn<float>(ctx->stream, bench_pdl, D.q.p, (const float*)ckv, D.att.p, H, B, d, Tk);
         } else if (k == "dec_layers") {
             WB_REQUIRE(bf && dec_cluster_enabled(ctx), WB_EINVAL, "dec_layers: the cluster-chained layer kernel is not active for this context");
