@@ -1347,6 +1347,9 @@ struct DecCluster {
     DevBuf<int> pidx;
     DevBuf<unsigned int> counter;
     int n_vchunks = 0;
+    // which of the optional kernels this context uses: read from the environment when the context is created
+    // (WB_DEC_CLUSTER / WB_DEC_VOCAB / WB_XATTN_TC = 1), so one process can hold contexts of either kind
+    bool use_layers = false, use_vocab = false, use_xattn = false;
     bool vocab_ok = false;              // fused vocabulary kernel usable (whisper-base widths)
     bool xa_ok = false;                 // stand-alone tensor-core cross-attention usable (even key-tile count, head_dim 64)
     DevBuf<bf16> att, ffn;
@@ -1368,6 +1371,8 @@ void dec_cluster_alloc(wb_ctx* ctx) {
     if (c.precision != WB_PREC_BF16) return;
     auto* dc = new DecCluster();
     ctx->dec.cluster = dc;
+    auto env_on = [](const char* name) { const char* e = getenv(name); return e && e[0] == '1'; };
+    dc->use_layers = env_on("WB_DEC_CLUSTER"); dc->use_vocab = env_on("WB_DEC_VOCAB"); dc->use_xattn = env_on("WB_XATTN_TC");
 
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -1399,8 +1404,7 @@ void dec_cluster_alloc(wb_ctx* ctx) {
     dc->pidx.reserve((size_t)ctx->sm_count * DV_SEQ);
     dc->counter.reserve_zero(4);
     dc->vocab_ok = true;
-    const char* env = getenv("WB_DEC_CLUSTER");
-    if (!(env && env[0] == '1')) return;                   // the layer kernel's weight images (47 MB) are built only when asked for
+    if (!dc->use_layers) return;                           // the layer kernel's weight images (47 MB) are built only when asked for
     int want = 16;
     if (const char* e = getenv("WB_DEC_CS")) want = atoi(e);
     const int n16 = want >= 16 ? max_active_clusters_of(dec_layers_kernel<16>, 16) : 0;
@@ -1447,9 +1451,7 @@ void dec_cluster_alloc(wb_ctx* ctx) {
 // batch (46 ms per 128-token decode of 32 sequences) but, holding 112 SMs for a whole step, it does not interleave with
 // other batches in flight (21 k vs 33 k audio-s/s at 4 in flight); DESIGN.md has the stage profile.
 bool dec_cluster_enabled(const wb_ctx* ctx) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("WB_DEC_CLUSTER"); on = (e && e[0] == '1') ? 1 : 0; }
-    return on == 1 && ctx->dec.cluster != nullptr && ctx->dec.cluster->cs > 0;
+    return ctx->dec.cluster != nullptr && ctx->dec.cluster->use_layers && ctx->dec.cluster->cs > 0;
 }
 
 // All decoder layers of one step for sequences [0, B) (input token from prompt / cur_tok, output: x = residual stream
@@ -1478,10 +1480,8 @@ void dec_cluster_layers(wb_ctx* ctx, cudaStream_t st, bool pdl, const int* state
 }
 
 // Cross-attention of decoder layer l for sequences [0, B) on the tensor-map / ring kernel (bf16 build, head_dim 64).
-bool cross_attn_tc_ok(const wb_ctx* ctx) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("WB_XATTN_TC"); on = (e && e[0] == '1') ? 1 : 0; }     // opt-in: 18.8 us vs 18.4 us for cross_attn_kernel<bf16> (both PDL)
-    return on == 1 && ctx->dec.cluster != nullptr && ctx->dec.cluster->xa_ok;
+bool cross_attn_tc_ok(const wb_ctx* ctx) {        // opt-in: 18.8 us vs 18.4 us for cross_attn_kernel<bf16> (both with PDL, B = 32)
+    return ctx->dec.cluster != nullptr && ctx->dec.cluster->use_xattn && ctx->dec.cluster->xa_ok;
 }
 void cross_attn_tc(wb_ctx* ctx, cudaStream_t st, bool pdl, int layer, const float* q, float* out, int B) {
     DecCluster* dc = ctx->dec.cluster;
@@ -1502,10 +1502,8 @@ void cross_attn_tc(wb_ctx* ctx, cudaStream_t st, bool pdl, int layer, const floa
 }
 
 // Final LayerNorm + vocabulary projection + arg-max + token bookkeeping + step advance for sequences [0, B), B <= 32.
-bool dec_cluster_vocab_ok(const wb_ctx* ctx, int B) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("WB_DEC_VOCAB"); on = (e && e[0] == '1') ? 1 : 0; }     // opt-in: measured equal to the 3-launch path
-    return on == 1 && ctx->dec.cluster != nullptr && ctx->dec.cluster->vocab_ok && B <= DV_SEQ;
+bool dec_cluster_vocab_ok(const wb_ctx* ctx, int B) {       // opt-in: measured equal to the 3-launch path
+    return ctx->dec.cluster != nullptr && ctx->dec.cluster->use_vocab && ctx->dec.cluster->vocab_ok && B <= DV_SEQ;
 }
 void dec_cluster_vocab(wb_ctx* ctx, cudaStream_t st, bool pdl, int* state, int B, float* logits, const int* forced, int max_new, int eot,
                        int T_total, int* cur_tok) {
