@@ -11,10 +11,13 @@ chain of small dependent kernels that leaves most SMs idle (`single_batch_in_fli
 `value`  : whole-job audio-s/s with the PCM already resident in HBM (device-timed, max over ranks).
 `e2e`    : same metric through the reference-facing C ABI call wb_transcribe_batch with HOST
            (pinned) PCM buffers — H2D of the PCM and D2H of the token ids inside the timed region.
-`roofline`: dominant kernel (decoder cross-attention, HBM-bound) against MEASURED_PEAKS.json.
+`roofline`: dominant kernel (decoder cross-attention, HBM-bound) against MEASURED_PEAKS.json, replayed on live
+           buffers the way the product launches it (programmatic dependent launch).
 `cpu_baseline`: the CPU oracle port (C log-mel + numpy Whisper) on a bounded sample, rank 0, N=1.
+`other_configs` (N=1): BASELINE.json configs[1] (log-mel, 1024 clips) and configs[2] (encoder bf16, batch 64).
 `--impl reference`: the reference arm — the reference (Rust + ONNX Runtime) cannot be built in this
-image, so it times the oracle port of the same path with all host threads (kind "port").
+image, so it times the oracle port of the same workload (a bounded sample of the batch per step) with all host
+threads, whatever OMP_NUM_THREADS the launcher exported (kind "port").
 Multi-GPU: clips are independent, so ranks shard them with no data-path collective (weak scaling);
 torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the timings.
 """
@@ -40,14 +43,23 @@ MAX_NEW = 128
 CLIP_S = 30.0
 BATCH = 32
 # dram bytes per cross_attn_kernel launch at B=32 from the committed ncu capture (profiles/r1_cross_attn_v3_raw.csv: 98.40 MB read + 4.25 MB write)
-NCU_TRAFFIC_BYTES = {"bf16": 102.65e6, "fp32": None}
+NCU_TRAFFIC_BYTES = {"bf16": 102.65e6, "fp32": None}      # refreshed from profiles/r2_cross_attn_raw.csv when that capture exists
 METRIC = "audio-sec/sec (RTFx) whisper-base"
 UNIT = "audio-s/s"
 
+# per-architecture constants: encoder flops per 30 s clip incl. conv stem and attention
+ARCHS = {
+    "base": {"name": "whisper-base", "cfg": "base", "n_mels": 80, "d": 512, "layers": 6, "vocab": 51865, "enc_flop": 87.368e9,
+             "batch": 32, "config": "BASELINE.json configs[3]"},
+    "large-v3": {"name": "whisper-large-v3 shapes", "cfg": "large-v3", "n_mels": 128, "d": 1280, "layers": 32, "vocab": 51866,
+                 "enc_flop": 2273.8e9, "batch": 16, "config": "BASELINE.json configs[4]"},
+}
 
-def workload_name(batch=BATCH):
-    return (f"whisper-base log-mel + encoder + KV-cache greedy decode, {MAX_NEW} new tokens, "
-            f"batch {batch} x 30 s synthetic clips per GPU (BASELINE.json configs[3])")
+
+def workload_name(batch=BATCH, arch="base"):
+    a = ARCHS[arch]
+    return (f"{a['name']} log-mel + encoder + KV-cache greedy decode, {MAX_NEW} new tokens, "
+            f"batch {batch} x 30 s synthetic clips per GPU ({a['config']})")
 
 
 # ---------------- helpers shared with tests ----------------
@@ -98,13 +110,15 @@ MEL_BYTES_PER_CLIP = 30 * 16000 * 4 + 80 * 3000 * 4
 DEC_WEIGHT_PARAMS = 6 * 14 * 512 * 512 + 51865 * 512          # 6 layers x (qkv 3 + o + cq + co + fc 8) d^2 + tied vocab projection
 
 
-def stage_rooflines(tm, B, esz, hbm_peak, tc_peak):
+def stage_rooflines(tm, B, esz, hbm_peak, tc_peak, arch="base"):
     """north_star: each stage as a fraction of its roofline (HBM for log-mel and decode, tensor peak for the encoder),
     from the stage times of one batch alone on the GPU."""
+    a = ARCHS[arch]
     steps = len(PROMPT) + MAX_NEW - 1
-    dec_bytes = steps * (B * 6 * 2 * 1500 * 512 * esz + DEC_WEIGHT_PARAMS * esz)
-    mel = B * MEL_BYTES_PER_CLIP / (tm["mel_ms"] * 1e-3) / 1e9
-    enc = B * ENC_FLOP_PER_CLIP / (tm["encoder_ms"] * 1e-3) / 1e12
+    weight_params = a["layers"] * 14 * a["d"] ** 2 + a["vocab"] * a["d"]
+    dec_bytes = steps * (B * a["layers"] * 2 * 1500 * a["d"] * esz + weight_params * esz)
+    mel = B * (30 * 16000 * 4 + a["n_mels"] * 3000 * 4) / (tm["mel_ms"] * 1e-3) / 1e9
+    enc = B * a["enc_flop"] / (tm["encoder_ms"] * 1e-3) / 1e12
     dec = dec_bytes / (tm["decode_ms"] * 1e-3) / 1e9
     return {"log_mel": {"bound": "hbm", "achieved": mel, "unit": "GB/s", "frac": mel / hbm_peak},
             "encoder": {"bound": "tensor", "achieved": enc, "unit": "TFLOP/s", "frac": enc / tc_peak},
@@ -180,34 +194,85 @@ def make_cpu_model():
     return wr.WhisperRef(cfg, wb200.weights.generate(cfg, 0))
 
 
+REF_SAMPLE_CLIPS = 2          # clips of the 32-clip batch the CPU arm decodes per step (one 30 s clip costs ~2 s on 16 cores)
+
+
+def host_threads():
+    """All host cores, whatever OMP_NUM_THREADS says: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers,
+    which halved the CPU arm at N >= 2 in round 1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path.  The real one (Rust + ORT)
-    is not buildable offline (no cargo/rustc/onnxruntime), so the oracle port stands in."""
+    """--impl reference: the reference's CPU implementation of the path on the SAME workload (whisper-base, 30 s clips,
+    128 new tokens, the batch of configs[3]); each step decodes a bounded sample of the batch (REF_SAMPLE_CLIPS clips,
+    batched through the oracle) so that K + W steps end within minutes.  The real reference (Rust + ORT) is not buildable
+    offline (no cargo/rustc/onnxruntime), so the oracle port stands in (kind "port")."""
     if rank != 0:
         return
+    if args.arch != "base":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU port of the large-v3 shapes needs minutes per 30 s clip; "
+                          "the reference arm is measured on the headline configuration (--arch base) only"}), flush=True)
+        return
     import wb200
-    threads = os.cpu_count() or 1
+    from threadpoolctl import threadpool_limits
+    threads = host_threads()
     sup, bsup = suppress_lists()
     model = make_cpu_model()
-    n = 1                                         # clips per step: bounded sample of the workload
-    clips = wb200.synth.batch(n, seed=7)
-    for _ in range(args.warmup):
-        cpu_port_pass(model, clips, sup, bsup, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_port_pass(model, clips, sup, bsup, threads)
-    dt = time.perf_counter() - t0
+    n = REF_SAMPLE_CLIPS
+    clips = wb200.synth.fast_batch(args.batch, seed=1)[:n]           # the first clips of the GPU arm's batch
+    with threadpool_limits(limits=threads):
+        for _ in range(min(args.warmup, 2)):                         # numpy/BLAS needs no more to settle
+            cpu_port_pass(model, clips, sup, bsup, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_port_pass(model, clips, sup, bsup, threads)
+        dt = time.perf_counter() - t0
     value = n * CLIP_S * args.steps / dt
-    sample = f"{n} clip x 30 s per step, {MAX_NEW} new tokens, oracle port (C log-mel + numpy/OpenBLAS Whisper fp32)"
+    sample = (f"{n} of the {args.batch} clips of a step per step (batched), 30 s each, {MAX_NEW} new tokens, oracle port "
+              f"(C log-mel + numpy/OpenBLAS Whisper fp32), {threads} host threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "sample": sample},
+            "config": {"workload": workload_name(args.batch), "sample": sample, "same_config": True},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                              "real_reference_toolchains_found": probe_real_references()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference binary (Rust+ONNX Runtime) not buildable offline; published EPYC-9654 4-core figure: 20.3x RT (BASELINE.md)"}
     print(json.dumps(line), flush=True)
+
+
+def other_configs(wb200, device):
+    """BASELINE.json configs[1] and configs[2] on this GPU (rank 0, N=1): a few seconds, outside every timed region."""
+    out = {}
+    peak, _ = measured_peaks()
+    n = 1024
+    m = wb200.Whisper(wb200.default_cfg("toy", max_batch=4, max_chunks=n), device=device)
+    m.upload_pcm(wb200.synth.fast_batch(n, seed=1))
+    best = 1e9
+    for _ in range(4):
+        m.run_log_mel()
+        best = min(best, m.timing()["mel_ms"])
+    gbs = n * MEL_BYTES_PER_CLIP / (best * 1e-3) / 1e9
+    out["configs[1] log-mel, 1024 x 30 s clips"] = {"ms": best, "audio_s_per_s": n * CLIP_S / (best * 1e-3), "bound": "hbm",
+                                                    "achieved": gbs, "unit": "GB/s", "frac": gbs / peak}
+    m.close()
+    B = 64
+    m = wb200.Whisper(wb200.default_cfg("base", precision=wb200.WB_PREC_BF16, max_batch=B, max_chunks=B), device=device)
+    m.upload_pcm(wb200.synth.fast_batch(B, seed=1))
+    m.run_log_mel()
+    best = 1e9
+    for _ in range(4):
+        m.encode(None, 0, B, want_hidden=False)
+        best = min(best, m.timing()["encoder_ms"])
+    tf = B * ENC_FLOP_PER_CLIP / (best * 1e-3) / 1e12
+    out["configs[2] encoder bf16, batch 64"] = {"ms": best, "audio_s_per_s": B * CLIP_S / (best * 1e-3), "bound": "tensor",
+                                                "achieved": tf, "unit": "TFLOP/s", "frac": tf / measured_tensor_peak()[0]}
+    m.close()
+    return out
 
 
 # ---------------- our arm ----------------
@@ -230,7 +295,9 @@ def run_ours(args, rank, world, local_rank):
         os.environ.setdefault("WB_BLOCKING_SYNC", "1")
     # S independent contexts (own stream, activations, KV caches, decode graph) = S batches in flight per GPU:
     # a decode step is ~50 dependent small kernels, so concurrent batches fill the SMs a single chain leaves idle.
-    ctxs = [wb200.Whisper(wb200.default_cfg("base", precision=prec, max_batch=B, max_chunks=B), device=local_rank) for _ in range(S)]
+    A = ARCHS[args.arch]
+    metric = METRIC if args.arch == "base" else f"audio-sec/sec (RTFx) {A['name']}"
+    ctxs = [wb200.Whisper(wb200.default_cfg(A["cfg"], precision=prec, max_batch=B, max_chunks=B), device=local_rank) for _ in range(S)]
     m = ctxs[0]
     sup, bsup = suppress_lists()
 
@@ -310,23 +377,26 @@ def run_ours(args, rank, world, local_rank):
     tm1 = m.timing()
 
     # ---- roofline of the dominant kernel, measured live with CUDA events ----
+    os.environ.pop("WB_BENCH_PDL", None)
+    k_ms_plain, _ = m.bench_kernel("cross_attn", B, iters=30)      # serialised launches: the round-1 way of timing it
+    os.environ["WB_BENCH_PDL"] = "1"              # replay the kernels the way the decode graph launches them (PDL)
     k_ms, k_bytes = m.bench_kernel("cross_attn", B, iters=30)
     v_ms, v_bytes = m.bench_kernel("vocab_proj", B, iters=10)
     peak, peak_src = measured_peaks()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
     steps_dec = len(PROMPT) + MAX_NEW - 1
-    share = 6 * steps_dec * k_ms / max(tm1["decode_ms"] + tm1["encoder_ms"] + tm1["cross_kv_ms"] + tm1["mel_ms"], 1e-9)
+    share = A["layers"] * steps_dec * k_ms / max(tm1["decode_ms"] + tm1["encoder_ms"] + tm1["cross_kv_ms"] + tm1["mel_ms"], 1e-9)
 
     if rank == 0:
         clocks = clk.summary()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(B), "clips_per_gpu_per_step": B, "global_batch": B * world, "max_new_tokens": MAX_NEW,
+            "config": {"workload": workload_name(B, args.arch), "clips_per_gpu_per_step": B, "global_batch": B * world, "max_new_tokens": MAX_NEW,
                        "batches_in_flight_per_gpu": S,
-                       "weights": "seeded random-init whisper-base (no checkpoint offline)",
-                       "l2": "working set per step (61 MB PCM + 145-290 MB weights + 0.6-1.2 GB cross-K/V) exceeds the 126 MB L2; no explicit flush",
+                       "weights": f"seeded random-init {A['name']} (no checkpoint offline)",
+                       "l2": "working set per step (PCM 1.9 MB/clip + weights >= 145 MB + cross-K/V >= 18 MB/clip) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"clips sharded over {world} GPU(s), one process per GPU, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned[0].numel() * 4) * world,
                     "d2h_bytes_per_step": int(B * (len(PROMPT) + MAX_NEW) * 8 + B * 4) * world, "p95_latency_s_per_clip": p95},
@@ -335,24 +405,30 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches_per_step * args.steps),
             "wall_s": wall,
             "stage_ms_per_step_under_load": stage,
-            "stage_rooflines_single_batch": stage_rooflines(tm1, B, 2 if args.precision == "bf16" else 4, peak, measured_tensor_peak()[0]),
+            "stage_rooflines_single_batch": stage_rooflines(tm1, B, 2 if args.precision == "bf16" else 4, peak, measured_tensor_peak()[0], args.arch),
             "clocks": clocks,
-            "roofline": {"kernel": "cross_attn_kernel (decoder cross-attention over cached encoder K/V)", "bound": "hbm",
+            "roofline": {"kernel": "cross_attn_kernel (decoder cross-attention over cached encoder K/V), launched with programmatic dependent launch as in the decode graph", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.precision),
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.precision) if (args.arch == "base" and B == 32) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture in profiles/ (B=32)",
                          "peak_source": peak_src, "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                          "share_of_single_batch_step": share,
+                         "without_pdl": {"ms_per_launch": k_ms_plain, "achieved": k_bytes / (k_ms_plain * 1e-3) / 1e9,
+                                         "frac": k_bytes / (k_ms_plain * 1e-3) / 1e9 / peak},
                          "also": {"vocab_proj": {"achieved": v_bytes / (v_ms * 1e-3) / 1e9, "ms_per_launch": v_ms, "bytes_per_launch": v_bytes}}},
             "tokens_head": toks[0][0][:8],
         }
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+        if world == 1 and not args.no_other_configs and args.arch == "base":
+            line["other_configs"] = other_configs(wb200, local_rank)
+        if world == 1 and not args.no_cpu_baseline and args.arch == "base":
+            from threadpoolctl import threadpool_limits
+            threads = host_threads()
             model = make_cpu_model()
             sample_clips = clips[:1]
-            t0 = time.perf_counter()
-            ref = cpu_port_pass(model, sample_clips, sup, bsup, threads)
-            dt = time.perf_counter() - t0
+            with threadpool_limits(limits=threads):
+                t0 = time.perf_counter()
+                ref = cpu_port_pass(model, sample_clips, sup, bsup, threads)
+                dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": CLIP_S / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"1 clip x 30 s, {MAX_NEW} new tokens, C log-mel + numpy Whisper fp32 ({dt:.1f} s)",
                                     "tokens_match_gpu": bool(ref[0] == toks[0][0]) if args.precision == "fp32" else None,
@@ -371,11 +447,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("WB_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--arch", default="base", choices=sorted(ARCHS), help="base = configs[3] (the headline); large-v3 = configs[4] "
+                    "(128 mel bins, 32+32 layers, d=1280; batch 16 per GPU; no CPU arm: one clip costs minutes on the host)")
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("WB_BENCH_IN_FLIGHT", "4")),
                     help="independent batches of --batch clips in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[1] / configs[2] side measurements")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = ARCHS[args.arch]["batch"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

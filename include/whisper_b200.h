@@ -20,6 +20,7 @@
 #ifndef WHISPER_B200_H
 #define WHISPER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -166,6 +167,10 @@ int wb_host_load_audio_16k_mono(const char* path, float** pcm_out, int64_t* n_ou
 int64_t wb_host_resample_linear(const float* x, int64_t n, uint32_t sr_in, uint32_t sr_out,
                                 float* out, int64_t cap);
 void wb_host_free(void* p);
+/* Page-locked host memory for PCM staging (H2D copies from it are asynchronous and run at link speed; a pageable
+ * source is staged through the driver's bounce buffer first).  `device` = the GPU whose context maps it. */
+int wb_host_alloc_pinned(int device, size_t bytes, void** out);
+void wb_host_free_pinned(void* p);
 /* chunk list of main.rs:875-882; returns count (writes up to cap). */
 int wb_host_chunk_starts(int64_t n_samples, int64_t chunk_len, int64_t step, int64_t* out, int cap);
 /* stitch_texts / word_overlap (main.rs:659-696). Returns needed length (excluding NUL). */

@@ -30,7 +30,10 @@ def lib():
         L.wbref_log_mel.argtypes = [fp, C.c_long, fp, C.c_int, fp, fp]
         L.wbref_log_mel_batch.restype = C.c_int
         L.wbref_log_mel_batch.argtypes = [fp, C.c_long, C.c_long, fp, C.c_int]
+        L.wbref_log_mel_n.restype = C.c_int
+        L.wbref_log_mel_n.argtypes = [fp, C.c_long, fp, C.c_int, C.c_int, fp, fp]
         L.wbref_mel_filterbank.argtypes = [fp]
+        L.wbref_mel_filterbank_n.argtypes = [fp, C.c_int]
         L.wbref_hann.argtypes = [fp, C.c_int]
         L.wbref_fft400_f32.argtypes = [fp, fp, fp, fp]
         _LIB = L
@@ -45,16 +48,17 @@ def n_frames(n: int) -> int:
     return int(lib().wbref_n_frames(n))
 
 
-def log_mel(pcm: np.ndarray, dft64: bool = False, return_raw: bool = False):
-    """whisper_log_mel_80 (main.rs:407-509) on one whole file -> [80, floor(N/160)] f32."""
+def log_mel(pcm: np.ndarray, dft64: bool = False, return_raw: bool = False, n_mels: int = 80):
+    """whisper_log_mel_80 (main.rs:407-509) on one whole file -> [80, floor(N/160)] f32.  n_mels=128: the same function
+    with the 128-triangle filterbank of the large-v3 frontend (BASELINE.json configs[4]; the reference itself only has 80)."""
     x = np.ascontiguousarray(pcm, dtype=np.float32)
     if x.size == 0:
         raise ValueError("Empty audio")          # main.rs:414-416
     nf = n_frames(x.size)
-    out = np.empty((80, nf), np.float32)
-    raw = np.empty((80, nf), np.float32)
+    out = np.empty((n_mels, nf), np.float32)
+    raw = np.empty((n_mels, nf), np.float32)
     g = C.c_float(0)
-    rc = lib().wbref_log_mel(_p(x), x.size, _p(out), int(dft64), _p(raw), C.byref(g))
+    rc = lib().wbref_log_mel_n(_p(x), x.size, _p(out), n_mels, int(dft64), _p(raw), C.byref(g))
     assert rc == 0
     return (out, raw, float(g.value)) if return_raw else out
 
@@ -68,9 +72,9 @@ def log_mel_batch(pcm: np.ndarray, threads: int = 1) -> np.ndarray:
     return out
 
 
-def filterbank() -> np.ndarray:
-    fb = np.empty((80, 201), np.float32)
-    lib().wbref_mel_filterbank(_p(fb))
+def filterbank(n_mels: int = 80) -> np.ndarray:
+    fb = np.empty((n_mels, 201), np.float32)
+    lib().wbref_mel_filterbank_n(_p(fb), n_mels)
     return fb
 
 
@@ -104,10 +108,11 @@ def chunk_mels(mel_full: np.ndarray, n_samples: int, chunk_len: int = 480000, st
     """Chunk slicing of transcribe_longform_chunked (main.rs:895-905): [n_chunks,80,3000],
     zero (literal 0.0) padded in mel space."""
     total = mel_full.shape[1]
+    nm = mel_full.shape[0]
     outs = []
     for pos in chunk_starts(n_samples, chunk_len, step):
         fs = pos // 160
-        m = np.zeros((80, 3000), np.float32)
+        m = np.zeros((nm, 3000), np.float32)
         if fs < total:
             ae = min(fs + 3000, total)
             m[:, : ae - fs] = mel_full[:, fs:ae]

@@ -25,7 +25,8 @@
 
 #define N_FFT 400
 #define HOP 160
-#define N_MELS 80
+#define N_MELS 80          /* the reference's frontend; the _n entry points take 80 or 128 (large-v3) */
+#define N_MELS_MAX 128
 #define N_FREQ 201
 #define SR 16000
 
@@ -58,11 +59,11 @@ static float mel_to_hz_slaney(float mel) {
 }
 
 /* main.rs:354-405 — fb is [n_mels][n_freq] row-major */
-void wbref_mel_filterbank(float* fb) {
-    const int n_mels = N_MELS, n_freq = N_FREQ;
+void wbref_mel_filterbank_n(float* fb, int n_mels) {
+    const int n_freq = N_FREQ;
     float fmax = fminf(8000.0f, (float)SR / 2.0f);
     float mel_min = hz_to_mel_slaney(0.0f), mel_max = hz_to_mel_slaney(fmax);
-    float freq_points[N_MELS + 2], fft_freqs[N_FREQ];
+    float freq_points[N_MELS_MAX + 2], fft_freqs[N_FREQ];
     for (int i = 0; i < n_mels + 2; ++i) {
         float m = mel_min + (mel_max - mel_min) * (float)i / (float)(n_mels + 1);
         freq_points[i] = mel_to_hz_slaney(m);
@@ -85,6 +86,8 @@ void wbref_mel_filterbank(float* fb) {
         for (int k = 0; k < n_freq; ++k) fb[m * n_freq + k] *= enorm;
     }
 }
+
+void wbref_mel_filterbank(float* fb) { wbref_mel_filterbank_n(fb, N_MELS); }
 
 /* ---- 400-point forward FFT, f32 mixed radix (restating rustfft's approach) ---- */
 static cpx g_tw[N_FFT];
@@ -143,9 +146,10 @@ long wbref_n_frames(long n) {
  * use_dft64 != 0 replaces the f32 FFT by an f64 direct DFT (validation mode).
  * If raw_log10 != NULL it also receives log10(max(mel,1e-10)) before clamp/scale, and
  * *gmax_out the file-global maximum (what the two-phase CUDA kernel exchanges). */
-int wbref_log_mel(const float* audio, long n, float* out, int use_dft64, float* raw_log10,
-                  float* gmax_out) {
+int wbref_log_mel_n(const float* audio, long n, float* out, int n_mels, int use_dft64, float* raw_log10,
+                    float* gmax_out) {
     if (n <= 0) return -1;
+    if (n_mels < 1 || n_mels > N_MELS_MAX) return -2;
     init_tw();
     const int pad = N_FFT / 2;
     long plen = n + 2 * pad;
@@ -166,8 +170,8 @@ int wbref_log_mel(const float* audio, long n, float* out, int use_dft64, float* 
     }
     float window[N_FFT];
     wbref_hann(window, N_FFT);
-    float* fb = (float*)malloc(sizeof(float) * N_MELS * N_FREQ);
-    wbref_mel_filterbank(fb);
+    float* fb = (float*)malloc(sizeof(float) * n_mels * N_FREQ);
+    wbref_mel_filterbank_n(fb, n_mels);
     long n_frames = wbref_n_frames(n);
 
     cpx fin[N_FFT], fout[N_FFT];
@@ -194,14 +198,14 @@ int wbref_log_mel(const float* audio, long n, float* out, int use_dft64, float* 
                 pows[k] = fr * fr + fi * fi;
             }
         }
-        for (int m = 0; m < N_MELS; ++m) {
+        for (int m = 0; m < n_mels; ++m) {
             float e = 0.0f;
             for (int k = 0; k < N_FREQ; ++k) e += fb[m * N_FREQ + k] * pows[k];
             out[(size_t)m * n_frames + frame] = fmaxf(e, 1e-10f);
         }
     }
     float max_log = -INFINITY;
-    size_t total = (size_t)N_MELS * (size_t)n_frames;
+    size_t total = (size_t)n_mels * (size_t)n_frames;
     for (size_t i = 0; i < total; ++i) {
         float lv = log10f(out[i]);
         if (lv > max_log) max_log = lv;
@@ -215,6 +219,10 @@ int wbref_log_mel(const float* audio, long n, float* out, int use_dft64, float* 
     }
     free(fb); free(padded);
     return 0;
+}
+/* whisper_log_mel_80 itself */
+int wbref_log_mel(const float* audio, long n, float* out, int use_dft64, float* raw_log10, float* gmax_out) {
+    return wbref_log_mel_n(audio, n, out, N_MELS, use_dft64, raw_log10, gmax_out);
 }
 
 /* Batch of equal-length clips, pthreads over clips (cpu_baseline with all host threads;

@@ -2,7 +2,9 @@
 # GPU counterpart of the reference's core-count sweep (run_container_benchmarks.sh: `for cores in ${CORES_LIST}`):
 # runs the drop-in CLI once per entry of GPUS_LIST and leaves, per entry, the same three result files the
 # Rust SUT writes, under <OUT_ROOT>/gpu_<N>g/without_hf_pipeline_rust/ -- the directory layout
-# compare_container_benchmarks.py reads (--results-dir <OUT_ROOT>/gpu_<N>g).  Prints one table row per entry.
+# compare_container_benchmarks.py reads (--results-dir <OUT_ROOT>/gpu_<N>g --log-dir <OUT_ROOT>/gpu_<N>g/logs), plus
+# logs/without_hf_pipeline_rust.time.txt with the two `/usr/bin/time -v` lines that script parses (elapsed wall clock,
+# maximum resident set size; written by GNU time when it is installed, else from getrusage).  One table row per entry.
 #
 #   GPUS_LIST="1 2 4 8" AUDIO_DIR=audio ONNX_DIR=whisper-base-with-past scripts/run_gpu_benchmarks.sh
 #
@@ -28,8 +30,10 @@ fi
 printf "%-5s %-7s %-10s %-9s %-12s %-10s\n" gpus files audio_s wall_s audio_s/s p95_e2e_s
 for g in ${GPUS_LIST}; do
   out="${OUT_ROOT}/gpu_${g}g/without_hf_pipeline_rust"
-  mkdir -p "${out}"
+  logs="${OUT_ROOT}/gpu_${g}g/logs"
+  mkdir -p "${out}" "${logs}"
   t0=$(date +%s.%N)
+  python "${ROOT}/tools/time_v.py" "${logs}/without_hf_pipeline_rust.time.txt" \
   "${CLI}" --audio-dir "${AUDIO_DIR}" --onnx-dir "${ONNX_DIR}" --language en --task transcribe \
     --max-new-tokens "${MAX_NEW_TOKENS}" --warmup 1 --write-txt --precision "${PRECISION}" \
     --gpus "${g}" --in-flight "${IN_FLIGHT}" --file-batch "${FILE_BATCH}" \

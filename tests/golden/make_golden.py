@@ -89,6 +89,15 @@ def main():
                         frames=np.arange(0, 3000, 7), mel=hf_mel[:, :, ::7].astype(np.float32),
                         edge=hf_mel[:, :, -4:].astype(np.float32))
 
+    # the 128-bin frontend of large-v3 (BASELINE.json configs[4]) on the same clips
+    fe128 = WhisperFeatureExtractor(feature_size=128)
+    hf128 = np.stack([fe128(x[i], sampling_rate=16000, return_tensors="np").input_features[0] for i in range(3)])
+    np.savez_compressed(os.path.join(HERE, "mel_hf128_seed0.npz"),
+                        frames=np.arange(0, 3000, 7), mel=hf128[:, :, ::7].astype(np.float32),
+                        edge=hf128[:, :, -4:].astype(np.float32))
+    if "--mel-only" in sys.argv:
+        return
+
     # ---- model goldens: whisper-base dims, seeded weights ----
     for tag, cfg, nclip, steps in (("base", weights.WHISPER_BASE, 2, 24), ("toy", weights.WHISPER_TOY, 2, 12)):
         W = weights.generate(cfg, seed=0)

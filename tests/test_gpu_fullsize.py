@@ -81,3 +81,39 @@ def test_configs1_many_clips_one_launch(wb):
         else:
             assert np.array_equal(blk, first[k])
     m.close()
+
+
+def test_configs4_large_v3_full_depth_two_steps_vs_oracle(wb):
+    """BASELINE.json configs[4] at its real depth (32 + 32 layers, d = 1280, 128 mel bins, vocab 51866), not the 2 + 2
+    layers of tests/test_gpu_wide.py: one clip from PCM through the 128-bin log-mel, the full encoder and two greedy
+    steps (main.rs:753-829), against the numpy oracle of the same seeded weights (about two minutes of host time:
+    1.5 G parameters to generate, 2.3 TFLOP of fp32 encoder on the CPU).  fp32 build: encoder within 1e-3 absolute
+    (activations reach ~1e1 after 32 residual layers), identical token ids, logits within 1e-3.  bf16 build: encoder
+    within 2e-2 relative (north_star), teacher-forced logits within 1e-1 (32 layers of bf16 rounding, logit std ~1)."""
+    mc = wb.weights.WHISPER_LARGE_V3
+    oracle = wr.WhisperRef(mc, wb.weights.generate(mc, 0))
+    x = wb.synth.batch(1, seed=6)
+    mel = np.stack([mo.log_mel(c, n_mels=128) for c in x])
+    ref_enc = oracle.encode(mel)
+    prompt = [50258, 50259, 50360, 50364]
+    ref_t, ref_l = oracle.greedy(ref_enc, prompt, 2, EOT, [], [], return_logits=True)
+    ref_l = np.stack(ref_l, 1)
+    forced = np.array([s[len(prompt):] for s in ref_t])
+
+    m = wb.Whisper(wb.default_cfg("large-v3", precision=wb.WB_PREC_FP32, max_batch=1, max_chunks=1))
+    mels, _ = m.log_mel(list(x))
+    assert np.abs(mels[0] - mel[0]).max() <= 1e-4
+    enc = m.encode(None, 0, 1)
+    assert np.abs(enc - ref_enc).max() <= 1e-3 * max(1.0, float(np.abs(ref_enc).max()))
+    toks, lg = m.greedy_decode(1, prompt, 2, EOT, want_logits=True)
+    assert toks == ref_t
+    assert np.abs(lg - ref_l).max() <= 1e-3 * max(1.0, float(np.abs(ref_l).max()))
+    m.close()
+
+    m = wb.Whisper(wb.default_cfg("large-v3", precision=wb.WB_PREC_BF16, max_batch=1, max_chunks=1))
+    m.log_mel(list(x), want_mel=False)
+    enc = m.encode(None, 0, 1)
+    assert np.linalg.norm(enc - ref_enc) / np.linalg.norm(ref_enc) <= 2e-2
+    toks, lg = m.greedy_decode(1, prompt, 2, EOT, forced=forced, want_logits=True)
+    assert np.abs(lg - ref_l).max() <= 1e-1 * max(1.0, float(ref_l.std()))
+    m.close()

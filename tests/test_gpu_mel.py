@@ -71,3 +71,44 @@ def test_batch_of_many_clips_is_order_independent(wb, model):
     b, _ = model.log_mel(x[::-1].copy())
     for i in range(6):
         assert np.array_equal(a[i], b[5 - i])
+
+
+def test_128_bin_frontend_large_v3(wb, golden_dir):
+    """BASELINE.json configs[4]: the same kernels with the 128-triangle filterbank (toy widths behind it, so only the
+    frontend differs) against the oracle (<= 1e-4) and the HF large-v3 feature extractor golden (<= 2e-4, see
+    tests/test_oracle_cpu.py for the one bin that needs the slack); ragged and chunked files as for 80 bins."""
+    cfg = wb.default_cfg("toy", max_batch=4, max_chunks=16)
+    cfg.n_mels = 128
+    m = wb.Whisper(cfg)
+    x = wb.synth.batch(3, seed=0)
+    mels, n_chunks = m.log_mel(x)
+    assert n_chunks == 3
+    g = np.load(f"{golden_dir}/mel_hf128_seed0.npz")
+    for i in range(3):
+        assert mels[i].shape == (128, 3000)
+        assert np.abs(mels[i] - mo.log_mel(x[i], n_mels=128)).max() <= TOL
+        assert np.abs(mels[i][:, g["frames"]] - g["mel"][i]).max() <= 2e-4
+    assert np.abs(m.chunk_mel(0, 3) - np.stack(mels)).max() == 0.0
+    long = np.concatenate([0.001 * wb.synth.clip(1, 7, 35.0), wb.synth.clip(2, 7, 35.0)])
+    odd = wb.synth.clip(5, seed=3, seconds=8.0)[:16000 * 7 + 13]
+    mels, n_chunks = m.log_mel([long, odd, odd[:1], odd[:401]])
+    refs = [mo.log_mel(c, n_mels=128) for c in (long, odd, odd[:1], odd[:401])]
+    for a, r in zip(mels, refs):
+        assert a.shape == r.shape and np.abs(a - r).max() <= TOL
+    ref = np.concatenate([mo.chunk_mels(r, n) for r, n in zip(refs, (len(long), len(odd), 1, 401))])
+    assert n_chunks == len(ref) == 6
+    assert np.abs(m.chunk_mel(0, n_chunks) - ref).max() <= TOL
+    m.close()
+
+
+@pytest.mark.parametrize("packed", ["0", "1"])
+@pytest.mark.parametrize("tpc", ["1", "3"])
+def test_kernel_variants_agree(wb, model, monkeypatch, packed, tpc):
+    """FADD2 butterflies or scalar ones, one or several tiles per CTA: same log-mel within the tolerance, on a batch with
+    a tile count that does not divide by the tiles-per-CTA."""
+    monkeypatch.setenv("WB_MEL_PACKED", packed)
+    monkeypatch.setenv("WB_MEL_TPC", tpc)
+    x = [wb.synth.clip(1, 9, 2.0), wb.synth.clip(2, 9, 0.5)[:7777], wb.synth.clip(3, 9, 1.0)]
+    mels, _ = model.log_mel(x)
+    for a, c in zip(mels, x):
+        assert np.abs(a - mo.log_mel(c)).max() <= TOL

@@ -69,3 +69,17 @@ def test_large_v3_widths_bf16_within_tolerance(wb, oracle, mel):
     with pytest.raises(wb.WbError, match="80-bin"):
         m.log_mel([np.zeros(16000, np.float32)])          # the reference has no 128-bin frontend
     m.close()
+
+
+def test_large_v3_widths_from_pcm(wb, oracle):
+    """PCM -> 128-bin log-mel kernel -> encoder of the large-v3 widths, resident end to end (no host mel)."""
+    import mel_oracle as mo
+    m = wb.Whisper(wide_cfg(wb, wb.WB_PREC_FP32))
+    x = wb.synth.batch(2, seed=4)
+    mels, n_chunks = m.log_mel(list(x))
+    assert n_chunks == 2 and mels[0].shape == (128, 3000)
+    ref_mel = np.stack([mo.log_mel(c, n_mels=128) for c in x])
+    assert np.abs(np.stack(mels) - ref_mel).max() <= 1e-4
+    enc = m.encode(None, 0, 2)
+    assert np.abs(enc - oracle.encode(ref_mel)).max() <= 5e-4
+    m.close()

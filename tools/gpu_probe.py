@@ -4,6 +4,7 @@
                                                       token agreement, ms per decode, ms per step
   python tools/gpu_probe.py inflight [S...]           throughput with S batches of 32 in flight
   python tools/gpu_probe.py kernels                   cross_attn / vocab_proj / logmel replays (wb_bench_kernel)
+  python tools/gpu_probe.py mel [n_clips]             BASELINE.json configs[1]: K1a and K1a+K1b per kernel variant
 """
 import json
 import os
@@ -111,5 +112,30 @@ def kernels(argv):
     m.close()
 
 
+def mel(argv):
+    n = int(argv[0]) if argv else 1024
+    pcm = wb200.synth.fast_batch(n, seed=1)
+    out = {}
+    for nm in (80, 128):
+        cfg = wb200.default_cfg("toy", precision=wb200.WB_PREC_BF16, max_batch=4, max_chunks=n)
+        cfg.n_mels = nm
+        m = wb200.Whisper(cfg)
+        m.upload_pcm(pcm)
+        for packed in ("1", "0"):
+            for tpc in ("1", "2", "4", "8"):
+                os.environ["WB_MEL_PACKED"], os.environ["WB_MEL_TPC"] = packed, tpc
+                best = 1e9
+                for _ in range(4):
+                    m.run_log_mel()
+                    best = min(best, m.timing()["mel_ms"])
+                k1a, by = m.bench_kernel("logmel", 1, 5)
+                out[f"n_mels={nm} packed={packed} tpc={tpc}"] = {
+                    "K1a+K1b_ms": best, "K1a_ms": k1a, "K1a_GBps": by / k1a / 1e6,
+                    "pipeline_GBps": n * (1.92e6 + nm * 3000 * 4) / best / 1e6, "audio_s_per_s": n * 30 / (best * 1e-3)}
+        os.environ.pop("WB_MEL_PACKED"); os.environ.pop("WB_MEL_TPC")
+        m.close()
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"decode": decode, "inflight": inflight, "kernels": kernels}[sys.argv[1]](sys.argv[2:])
+    {"decode": decode, "inflight": inflight, "kernels": kernels, "mel": mel}[sys.argv[1]](sys.argv[2:])

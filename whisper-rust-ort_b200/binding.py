@@ -150,7 +150,8 @@ class Whisper:
         return flat, offs
 
     def log_mel(self, clips, chunk_len: int = 0, step: int = 0, want_mel: bool = True):
-        """-> (list of [80, nf_i] arrays or None, n_chunks).  whisper_log_mel_80 per file."""
+        """-> (list of [n_mels, nf_i] arrays or None, n_chunks).  whisper_log_mel_80 per file (n_mels = 80; 128 for large-v3)."""
+        nm = self.cfg.n_mels
         flat, offs = self._pack(clips)
         n_files = len(offs) - 1
         nfr = np.zeros(n_files, np.int64)
@@ -158,7 +159,7 @@ class Whisper:
         # frame count is floor(N/160) (>=1): size the host buffer first
         lens = np.diff(offs)
         nf = np.maximum(lens // 160, 1)
-        out = np.empty(int(nf.sum()) * 80, np.float32) if want_mel else None
+        out = np.empty(int(nf.sum()) * nm, np.float32) if want_mel else None
         _chk(self.L.wb_log_mel(self.h, flat.ctypes.data_as(f32p), offs.ctypes.data_as(i64p), n_files, chunk_len, step,
                                out.ctypes.data_as(f32p) if want_mel else None, nfr.ctypes.data_as(i64p), C.byref(nch)))
         assert np.array_equal(nfr, nf), (nfr, nf)
@@ -166,8 +167,8 @@ class Whisper:
         if want_mel:
             mels, o = [], 0
             for k in nf:
-                mels.append(out[o:o + 80 * int(k)].reshape(80, int(k)))
-                o += 80 * int(k)
+                mels.append(out[o:o + nm * int(k)].reshape(nm, int(k)))
+                o += nm * int(k)
         return mels, nch.value
 
     def upload_pcm(self, clips, chunk_len: int = 0, step: int = 0) -> int:
@@ -185,7 +186,7 @@ class Whisper:
         return fi, sp
 
     def chunk_mel(self, begin, n):
-        out = np.empty((n, 80, N_FRAMES), np.float32)
+        out = np.empty((n, self.cfg.n_mels, N_FRAMES), np.float32)
         _chk(self.L.wb_get_chunk_mel(self.h, begin, n, out.ctypes.data_as(f32p)))
         return out
 

@@ -30,7 +30,8 @@ void require_ctx(const wb_ctx* c) {
 void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files, int64_t chunk_len,
                 int64_t step, int* n_chunks_out) {
     WB_REQUIRE(pcm && offsets && n_files > 0, WB_EINVAL, "wb_upload_pcm: bad arguments");
-    WB_REQUIRE(ctx->cfg.n_mels == 80, WB_EINVAL, "log-mel kernel implements the reference's 80-bin frontend only");
+    const int NM = ctx->cfg.n_mels;
+    WB_REQUIRE(NM == 80 || NM == 128, WB_EINVAL, "log-mel kernel has 80 bins (the reference's frontend) or 128 (large-v3), not %d", NM);
     if (chunk_len <= 0) chunk_len = WB_CHUNK_SAMPLES;
     if (step <= 0) step = 400000;
     WB_REQUIRE(offsets[0] == 0, WB_EINVAL, "offsets[0] must be 0");
@@ -44,7 +45,7 @@ void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_fil
         WB_REQUIRE(n > 0, WB_EINVAL, "Empty audio (file %d)", i);                      // main.rs:414-416
         const int64_t nf = mel_n_frames(n);
         h_frame_off[i + 1] = h_frame_off[i] + nf;
-        h_tile_off[i + 1] = h_tile_off[i] + (int)ceil_div64(nf, 32);
+        h_tile_off[i + 1] = h_tile_off[i] + (int)ceil_div64(nf, WB_MEL_FPT);
         int64_t pos = 0;                                                               // main.rs:875-882
         while (pos < n) {
             const int64_t end = pos + chunk_len < n ? pos + chunk_len : n;
@@ -73,7 +74,7 @@ void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_fil
     s.frame_off.reserve(n_files + 1);
     s.tile_off.reserve(n_files + 1);
     s.fmax.reserve(n_files);
-    s.raw.reserve((size_t)s.total_frames * 80);
+    s.raw.reserve((size_t)s.total_frames * NM);
     s.chunks.reserve(n_chunks);
     cudaStream_t st = ctx->stream;
     CudaEvent e0, e1;
@@ -95,15 +96,13 @@ void run_log_mel(wb_ctx* ctx, bool sync) {
     MelState& s = ctx->mel;
     WB_REQUIRE(s.n_files > 0, WB_ESTATE, "wb_run_log_mel before wb_upload_pcm");
     ctx->timing.mel_launches = 0;
-    CUDA_CHECK(cudaEventRecord(ctx->ev0.e, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->mel_e0.e, ctx->stream));
     mel_launch_raw(ctx);
     mel_launch_chunks(ctx, 0, s.n_chunks, ctx->enc.mel_tm.p);
-    CUDA_CHECK(cudaEventRecord(ctx->ev1.e, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ctx->mel_e1.e, ctx->stream));
     s.raw_valid = true;
-    if (sync) {
-        CUDA_CHECK(cudaEventSynchronize(ctx->ev1.e));
-        CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.mel_ms, ctx->ev0.e, ctx->ev1.e));
-    }
+    ctx->mel_t_pending = true;
+    if (sync) timing_flush(ctx);
 }
 
 DecodeParams make_params(int B, const int64_t* prompt, int prompt_len, int max_new, int64_t eot,
@@ -121,7 +120,7 @@ DecodeParams make_params(int B, const int64_t* prompt, int prompt_len, int max_n
 void transcribe_resident(wb_ctx* ctx, const DecodeParams& proto, int64_t* tokens_out, int32_t* lens_out, int cap_chunks) {
     MelState& s = ctx->mel;
     WB_REQUIRE(s.n_chunks <= cap_chunks, WB_ECAP, "output capacity %d < %d chunks", cap_chunks, s.n_chunks);
-    run_log_mel(ctx, true);
+    run_log_mel(ctx, false);             // the encoder is enqueued right behind it; mel_ms is read back after the decode
     const int stride = proto.prompt_len + (proto.max_new < 1 ? 1 : proto.max_new);
     const size_t chunk_elems = (size_t)(WB_N_FRAMES + 2) * ctx->cfg.n_mels * ctx->esz();
     float enc_ms = 0, ckv_ms = 0, dec_ms = 0;
@@ -142,9 +141,34 @@ void transcribe_resident(wb_ctx* ctx, const DecodeParams& proto, int64_t* tokens
 
 }  // namespace
 
+void timing_flush(wb_ctx* ctx) {
+    if (ctx->mel_t_pending) {
+        CUDA_CHECK(cudaEventSynchronize(ctx->mel_e1.e));
+        CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.mel_ms, ctx->mel_e0.e, ctx->mel_e1.e));
+        ctx->mel_t_pending = false;
+    }
+    if (ctx->enc_t_pending) {
+        CUDA_CHECK(cudaEventSynchronize(ctx->enc_e2.e));
+        CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.encoder_ms, ctx->enc_e0.e, ctx->enc_e1.e));
+        CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.cross_kv_ms, ctx->enc_e1.e, ctx->enc_e2.e));
+        ctx->enc_t_pending = false;
+    }
+}
+
 extern "C" {
 
 const char* wb_last_error(void) { return g_err.c_str(); }
+
+int wb_host_alloc_pinned(int device, size_t bytes, void** out) {
+    WB_TRY
+    WB_REQUIRE(out != nullptr && bytes > 0, WB_EINVAL, "wb_host_alloc_pinned: bad arguments");
+    *out = nullptr;
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    WB_CATCH
+}
+
+void wb_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 int wb_device_count(int* count_out) {
     WB_TRY
@@ -207,7 +231,7 @@ int wb_create(wb_ctx** out, int device, const wb_model_cfg* cfg, const char* wei
         mel_set_attrs();
         gemm_tc_set_attrs();
         attn_tc_set_attrs();
-        mel_build_tables(ctx->mel_tables);
+        mel_build_tables(ctx->mel_tables, ctx->cfg.n_mels);
         CUDA_CHECK(cudaMalloc(&ctx->mel_tables_dev, sizeof(MelTables)));
         CUDA_CHECK(cudaMemcpy(ctx->mel_tables_dev, &ctx->mel_tables, sizeof(MelTables), cudaMemcpyHostToDevice));
         lap("mel tables");
@@ -244,6 +268,7 @@ void wb_destroy(wb_ctx* ctx) {
     weights_free(ctx);
     for (auto& g : ctx->dec.graphs) cudaGraphExecDestroy(g.exec);
     if (ctx->dec.unfinished_host) cudaFreeHost(ctx->dec.unfinished_host);
+    if (ctx->dec.stage_host) cudaFreeHost(ctx->dec.stage_host);
     if (ctx->mel_tables_dev) cudaFree(ctx->mel_tables_dev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -261,6 +286,7 @@ int wb_get_timing(const wb_ctx* ctx, wb_timing* out) {
     WB_TRY
     require_ctx(ctx);
     WB_REQUIRE(out, WB_EINVAL, "null out");
+    timing_flush(const_cast<wb_ctx*>(ctx));        // waits for the stages whose events are still outstanding
     *out = ctx->timing;
     WB_CATCH
 }
@@ -297,7 +323,7 @@ int wb_bench_kernel(wb_ctx* ctx, const char* kernel, int B, int iters, float* av
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, e0.e, e1.e));
         *avg_ms_out = ms / iters;
-        *bytes_out = 4.0 * (double)(ctx->mel.h_file_off[ctx->mel.n_files]) + 4.0 * 80.0 * (double)ctx->mel.total_frames;
+        *bytes_out = 4.0 * (double)(ctx->mel.h_file_off[ctx->mel.n_files]) + 4.0 * (double)ctx->cfg.n_mels * (double)ctx->mel.total_frames;
     } else {
         decoder_bench(ctx, kernel, B, iters, avg_ms_out, bytes_out);
     }
@@ -427,19 +453,20 @@ int wb_log_mel(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_file
     WB_TRY
     require_ctx(ctx);
     upload_pcm(ctx, pcm, offsets, n_files, chunk_len, step, n_chunks_out);
-    run_log_mel(ctx, true);
+    run_log_mel(ctx, false);              // mel_ms is read back by the next wait (wb_get_timing, the decode, the copy below)
     MelState& s = ctx->mel;
     if (n_frames_out)
         for (int i = 0; i < n_files; ++i) n_frames_out[i] = s.h_frame_off[i + 1] - s.h_frame_off[i];
     if (mel_out) {
-        s.export_buf.reserve((size_t)s.total_frames * 80);
+        const int NM = ctx->cfg.n_mels;
+        s.export_buf.reserve((size_t)s.total_frames * NM);
         for (int i = 0; i < n_files; ++i) {
             const int64_t nf = s.h_frame_off[i + 1] - s.h_frame_off[i];
-            mel_launch_export(ctx, i, 0, nf, s.export_buf.p + s.h_frame_off[i] * 80);
+            mel_launch_export(ctx, i, 0, nf, s.export_buf.p + s.h_frame_off[i] * NM);
         }
         CudaEvent e0, e1;
         CUDA_CHECK(cudaEventRecord(e0.e, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(mel_out, s.export_buf.p, sizeof(float) * (size_t)s.total_frames * 80, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(mel_out, s.export_buf.p, sizeof(float) * (size_t)s.total_frames * NM, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaEventRecord(e1.e, ctx->stream));
         CUDA_CHECK(wb_stream_sync(ctx->stream));
         CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.d2h_ms, e0.e, e1.e));
@@ -465,12 +492,13 @@ int wb_get_chunk_mel(wb_ctx* ctx, int chunk_begin, int n, float* out) {
     MelState& s = ctx->mel;
     WB_REQUIRE(s.raw_valid, WB_ESTATE, "no log-mel resident");
     WB_REQUIRE(out && chunk_begin >= 0 && n >= 0 && chunk_begin + n <= s.n_chunks, WB_EINVAL, "chunk range out of bounds");
-    s.export_buf.reserve((size_t)n * 80 * WB_N_FRAMES);
+    const int NM = ctx->cfg.n_mels;
+    s.export_buf.reserve((size_t)n * NM * WB_N_FRAMES);
     for (int i = 0; i < n; ++i) {
         const MelChunk& ch = s.h_chunks[chunk_begin + i];
-        mel_launch_export(ctx, ch.file, ch.frame_start, WB_N_FRAMES, s.export_buf.p + (size_t)i * 80 * WB_N_FRAMES);
+        mel_launch_export(ctx, ch.file, ch.frame_start, WB_N_FRAMES, s.export_buf.p + (size_t)i * NM * WB_N_FRAMES);
     }
-    CUDA_CHECK(cudaMemcpyAsync(out, s.export_buf.p, sizeof(float) * (size_t)n * 80 * WB_N_FRAMES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out, s.export_buf.p, sizeof(float) * (size_t)n * NM * WB_N_FRAMES, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(wb_stream_sync(ctx->stream));
     WB_CATCH
 }

@@ -13,8 +13,8 @@
 struct MelTables {                 // POD, copied to the device once
     float window[400];             // periodic Hann, main.rs:323-330
     float tw_re[400], tw_im[400];  // W_400^k
-    float fb_w[400];               // non-zero filterbank weights, mel-major runs
-    int fb_idx[240];               // start[80], len[80], offset-into-fb_w[80]
+    float fb_w[512];               // non-zero filterbank weights, mel-major runs
+    int fb_idx[384];               // start[n_mels], len[n_mels], offset-into-fb_w[n_mels]  (n_mels = 80 or 128)
 };
 struct MelChunk {
     int file;
@@ -24,7 +24,7 @@ struct MelState {
     DevBuf<float> pcm;
     DevBuf<int64_t> file_off, frame_off;
     DevBuf<int> tile_off, fmax;
-    DevBuf<float> raw;             // [total_frames][80] log10 mel, time-major
+    DevBuf<float> raw;             // [total_frames][n_mels] log10 mel, time-major
     DevBuf<MelChunk> chunks;
     DevBuf<float> export_buf;
     std::vector<int64_t> h_file_off, h_frame_off, h_chunk_pos;
@@ -117,6 +117,8 @@ struct DecBufs {
     int* unfinished_host = nullptr;    // mapped: sequences still running, written at the end of a segment
     int* unfinished_dev = nullptr;
     bool pdl = false;                  // programmatic dependent launch for the decode chain
+    int* stage_host = nullptr;         // pinned staging of the per-decode control state (ids, bitmaps, lens): a pageable
+    size_t stage_ints = 0;             //   source would make every cudaMemcpyAsync wait for the stream to drain first
     struct DecCluster* cluster = nullptr;   // dec_cluster.cu: all layers of a step in one launch (bf16, whisper-base widths)
 };
 
@@ -134,12 +136,19 @@ struct wb_ctx {
     bool debug = false;
     int sm_count = 148;
     CudaEvent ev0, ev1;
+    // stage timings are read back lazily (timing_flush): no host wait between log-mel, encoder and decode
+    CudaEvent mel_e0, mel_e1, enc_e0, enc_e1, enc_e2;
+    bool mel_t_pending = false, enc_t_pending = false;
     CudaEvent marks[8];
     size_t esz() const { return cfg.precision == WB_PREC_BF16 ? 2 : 4; }
 };
 
+// api.cpp — waits for and publishes the stage timings whose events are still outstanding
+void timing_flush(wb_ctx* ctx);
+
 // mel.cu
-void mel_build_tables(MelTables& t);
+#define WB_MEL_FPT 24                 // frames per log-mel tile (mel.cu); wb_upload_pcm builds the tile prefix sums with it
+void mel_build_tables(MelTables& t, int n_mels);
 void mel_set_attrs();
 int64_t mel_n_frames(int64_t n);
 void mel_launch_raw(wb_ctx* ctx);

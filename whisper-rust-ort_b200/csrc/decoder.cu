@@ -1173,41 +1173,57 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     WB_REQUIRE(P >= 1 && T_total <= D.T_max, WB_ECAP, "prompt_len + max_new_tokens = %d exceeds n_text_ctx %d", T_total, D.T_max);
     for (int i = 0; i < P; ++i) WB_REQUIRE(p.prompt[i] >= 0 && p.prompt[i] < c.vocab, WB_EINVAL, "prompt id out of range");
 
-    // host -> device control state (small)
+    // host -> device control state (small), staged in pinned memory: a pageable source makes cudaMemcpyAsync wait for
+    // the stream to drain (the encoder enqueued just before) and only then copy
     const size_t words = ((size_t)c.vocab + 31) / 32;
-    std::vector<unsigned> base(words, 0u), first;
+    const size_t n_tok = (size_t)c.max_batch * T_total + c.max_batch + P;
+    const size_t n_forced = p.forced ? (size_t)B * max_new : 0;
+    const size_t need = n_tok + 2 * words + (size_t)B + 16 + n_forced;
+    if (need > D.stage_ints) {
+        if (D.stage_host) CUDA_CHECK(cudaFreeHost(D.stage_host));
+        D.stage_host = nullptr; D.stage_ints = 0;
+        CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&D.stage_host), sizeof(int) * need, cudaHostAllocDefault));
+        D.stage_ints = need;
+    }
+    int* tok = D.stage_host;
+    unsigned* base = reinterpret_cast<unsigned*>(tok + n_tok);
+    unsigned* first = base + words;
+    int* lens = reinterpret_cast<int*>(first + words);
+    int* st4 = lens + B;
+    int* forced = st4 + 16;
+    std::fill(base, base + words, 0u);
     for (int i = 0; i < p.n_suppress; ++i)
         if (p.suppress[i] >= 0 && p.suppress[i] < c.vocab) base[(size_t)p.suppress[i] >> 5] |= 1u << (p.suppress[i] & 31);
-    first = base;
+    std::copy(base, base + words, first);
     for (int i = 0; i < p.n_begin_suppress; ++i)
         if (p.begin_suppress[i] >= 0 && p.begin_suppress[i] < c.vocab) first[(size_t)p.begin_suppress[i] >> 5] |= 1u << (p.begin_suppress[i] & 31);
-    std::vector<int> tok((size_t)c.max_batch * T_total + c.max_batch + P, -1);
+    std::fill(tok, tok + n_tok, -1);
     for (int b = 0; b < B; ++b)
         for (int i = 0; i < P; ++i) tok[(size_t)b * T_total + i] = (int)p.prompt[i];
     int* cur_tok = D.tokens.p + (size_t)c.max_batch * T_total;
     int* prompt_dev = cur_tok + c.max_batch;
     for (int i = 0; i < P; ++i) tok[(size_t)c.max_batch * T_total + c.max_batch + i] = (int)p.prompt[i];
-    cudaStream_t st = ctx->stream;
-    CUDA_CHECK(cudaMemcpyAsync(D.tokens.p, tok.data(), sizeof(int) * tok.size(), cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(D.sup_base.p, base.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(D.sup_first.p, first.data(), sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
-    std::vector<int> lens(B, P), st4 = {0, P, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(D.lens.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemsetAsync(D.finished.p, 0, sizeof(int) * B, st));
-    CUDA_CHECK(cudaMemcpyAsync(D.state.p, st4.data(), sizeof(int) * 16, cudaMemcpyHostToDevice, st));
+    std::fill(lens, lens + B, P);
+    std::fill(st4, st4 + 16, 0);
+    st4[1] = P;
     int* forced_dev = nullptr;
-    std::vector<int> forced;
     if (p.forced) {
-        forced.resize((size_t)B * max_new);
-        for (size_t i = 0; i < forced.size(); ++i) {
+        for (size_t i = 0; i < n_forced; ++i) {
             WB_REQUIRE(p.forced[i] >= 0 && p.forced[i] < c.vocab, WB_EINVAL, "forced id out of range");
             forced[i] = (int)p.forced[i];
         }
-        CUDA_CHECK(cudaMemcpyAsync(D.forced.p, forced.data(), sizeof(int) * forced.size(), cudaMemcpyHostToDevice, st));
         forced_dev = D.forced.p;
     }
+    cudaStream_t st = ctx->stream;
+    CUDA_CHECK(cudaMemcpyAsync(D.tokens.p, tok, sizeof(int) * n_tok, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.sup_base.p, base, sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.sup_first.p, first, sizeof(unsigned) * words, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.lens.p, lens, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemsetAsync(D.finished.p, 0, sizeof(int) * B, st));
+    CUDA_CHECK(cudaMemcpyAsync(D.state.p, st4, sizeof(int) * 16, cudaMemcpyHostToDevice, st));
+    if (p.forced) CUDA_CHECK(cudaMemcpyAsync(D.forced.p, forced, sizeof(int) * n_forced, cudaMemcpyHostToDevice, st));
     if (p.want_logits) D.logits_all.reserve((size_t)B * max_new * c.vocab);
-    CUDA_CHECK(wb_stream_sync(st));      // host staging vectors go out of scope below
+    // the staging block is rewritten by the next decoder_run only, which starts after this one's final wait
 
     CudaEvent e0, e1;
     const int steps = P + max_new - 1;
@@ -1289,21 +1305,27 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     CUDA_CHECK(cudaEventRecord(e0.e, st));
     if (P > 1) { launches += run_segment(P - 1, false, 0); steps_done += P - 1; }
     int gi = 0;
-    CudaEvent eseg;
+    // One segment of look-ahead: segment k+1 is enqueued before the host waits for segment k's "still running" count,
+    // so the GPU never idles on the poll; after the last EOT at most one surplus segment runs (finished sequences do
+    // not change, main.rs:781-783).
+    CudaEvent eseg[2];
+    int n_seg = 0;
     while (gi < max_new) {
         const int n = max_new - gi < SEG ? max_new - gi : SEG;
         launches += run_segment(n, true, gi);
         gi += n;
         steps_done += n;
-        if (gi < max_new) {
-            CUDA_CHECK(cudaEventRecord(eseg.e, st));
-            CUDA_CHECK(cudaEventSynchronize(eseg.e));
+        CUDA_CHECK(cudaEventRecord(eseg[n_seg & 1].e, st));
+        if (n_seg > 0 && gi < max_new) {
+            CUDA_CHECK(cudaEventSynchronize(eseg[(n_seg - 1) & 1].e));
             if (*D.unfinished_host == 0 && !p.forced) break;      // every sequence emitted EOT
         }
+        ++n_seg;
     }
     CUDA_CHECK(cudaEventRecord(e1.e, st));
     CUDA_CHECK(cudaEventSynchronize(e1.e));
     CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.decode_ms, e0.e, e1.e));
+    timing_flush(ctx);                       // log-mel / encoder events completed long ago: no wait
     ctx->timing.decode_launches = launches;
     ctx->timing.decode_steps = steps_done;
     (void)steps;

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <future>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -322,9 +323,10 @@ struct Timing { double preprocess_s = 0, model_only_s = 0, decode_s = 0, end_to_
 // transcribe_longform_chunked, main.rs:834-1008, for a GROUP of files: one log-mel launch over all of them
 // (the clamp maximum stays per file, quirk Q1), all their chunks packed into GPU batches of max_batch, then
 // per-file detokenise + stitch.  With one file per group this is exactly the reference's per-file call.
-struct FilePcm { const float* p; int64_t n; };
-std::vector<std::string> transcribe(wb_ctx* ctx, int max_batch, const std::vector<FilePcm>& files, const Args& a,
+// `pcm` holds the files back to back (offs[i] .. offs[i+1]), in pinned memory when it comes from the group loader.
+std::vector<std::string> transcribe(wb_ctx* ctx, int max_batch, const float* pcm, const std::vector<int64_t>& offs, const Args& a,
                                     const wb_tokenizer* tok, const GenCfg& gen, Timing& t) {
+    const size_t n_files = offs.size() - 1;
     auto t0 = Clock::now();
     int64_t sp[5];
     CK(wb_host_special_tokens(tok, a.language.c_str(), a.task.c_str(), sp));
@@ -336,17 +338,8 @@ std::vector<std::string> transcribe(wb_ctx* ctx, int max_batch, const std::vecto
     const int64_t step = std::max<int64_t>(chunk_len > overlap ? chunk_len - overlap : 0, 1);
 
     auto tp0 = Clock::now();
-    std::vector<int64_t> offs(files.size() + 1, 0);
-    for (size_t i = 0; i < files.size(); ++i) offs[i + 1] = offs[i] + files[i].n;
-    const float* pcm = files[0].p;
-    std::vector<float> packed;
-    if (files.size() > 1) {                       // several files: one contiguous host buffer for the H2D copy
-        packed.resize((size_t)offs.back());
-        for (size_t i = 0; i < files.size(); ++i) std::memcpy(packed.data() + offs[i], files[i].p, sizeof(float) * (size_t)files[i].n);
-        pcm = packed.data();
-    }
     int n_chunks = 0;
-    CK(wb_log_mel(ctx, pcm, offs.data(), (int)files.size(), chunk_len, step, nullptr, nullptr, &n_chunks));
+    CK(wb_log_mel(ctx, pcm, offs.data(), (int)n_files, chunk_len, step, nullptr, nullptr, &n_chunks));
     std::vector<int32_t> chunk_file((size_t)n_chunks);
     CK(wb_get_chunks(ctx, chunk_file.data(), nullptr, n_chunks));
     t.preprocess_s += since(tp0);
@@ -366,7 +359,7 @@ std::vector<std::string> transcribe(wb_ctx* ctx, int max_batch, const std::vecto
     t.model_only_s += since(tm0);
 
     auto td0 = Clock::now();
-    std::vector<std::vector<std::string>> texts(files.size());
+    std::vector<std::vector<std::string>> texts(n_files);
     for (int c = 0; c < n_chunks; ++c) {                                             // main.rs:925-943
         const int64_t* row = toks.data() + (size_t)c * stride;
         int len = lens[c];
@@ -403,8 +396,58 @@ struct Pcm {
     Pcm() = default; Pcm(const Pcm&) = delete; Pcm& operator=(const Pcm&) = delete;
     ~Pcm() { wb_host_free(p); }
 };
+// page-locked staging of one group's PCM (grown on demand, reused from group to group)
+struct PinnedPcm {
+    float* p = nullptr; size_t cap = 0;
+    PinnedPcm() = default; PinnedPcm(const PinnedPcm&) = delete; PinnedPcm& operator=(const PinnedPcm&) = delete;
+    ~PinnedPcm() { wb_host_free_pinned(p); }
+    void reserve(int device, size_t n) {
+        if (n <= cap) return;
+        wb_host_free_pinned(p); p = nullptr; cap = 0;
+        void* q = nullptr;
+        CK(wb_host_alloc_pinned(device, sizeof(float) * n, &q));
+        p = static_cast<float*>(q); cap = n;
+    }
+};
+// One group of files, decoded and packed back to back: what a worker hands to transcribe().
+struct LoadedGroup {
+    size_t g = SIZE_MAX, g0 = 0, g1 = 0;          // g == SIZE_MAX: no group left
+    std::vector<int64_t> offs;
+    std::vector<double> dur, load_s;
+    double load_total = 0;
+};
 
-// One worker = one wb_ctx on `device`: warm up like main.rs:1131-1152, then take groups off the cursor.
+// The k-th group of this rank: read + decode + downmix/resample every file (main.rs:207-316), pack into `slot`.
+LoadedGroup load_group(const Job& J, int device, const std::vector<std::pair<size_t, size_t>>& groups, size_t rank, size_t world,
+                       std::atomic<size_t>& cursor, PinnedPcm& slot) {
+    LoadedGroup L;
+    const size_t k = cursor.fetch_add(1);
+    const size_t g = rank + k * world;
+    if (g >= groups.size()) return L;
+    L.g = g; L.g0 = groups[g].first; L.g1 = groups[g].second;
+    const size_t n = L.g1 - L.g0;
+    std::vector<Pcm> au(n);
+    L.offs.assign(n + 1, 0); L.dur.resize(n); L.load_s.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        auto tl0 = Clock::now();
+        Pcm& p = au[i];
+        CK(wb_host_load_audio_16k_mono(join(J.args.audio_dir, J.files[L.g0 + i]).c_str(), &p.p, &p.n, &p.dur));
+        WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
+        L.offs[i + 1] = L.offs[i] + p.n;
+        L.dur[i] = p.dur;
+        L.load_s[i] = since(tl0);
+    }
+    auto tc0 = Clock::now();
+    slot.reserve(device, (size_t)L.offs.back());
+    for (size_t i = 0; i < n; ++i) std::memcpy(slot.p + L.offs[i], au[i].p, sizeof(float) * (size_t)au[i].n);
+    const double pack_s = since(tc0) / (double)n;               // the staging copy is part of loading a file
+    for (size_t i = 0; i < n; ++i) { L.load_s[i] += pack_s; L.load_total += L.load_s[i]; }
+    return L;
+}
+
+// One worker = one wb_ctx on `device`: warm up like main.rs:1131-1152, then take groups off the cursor.  A loader
+// thread decodes the worker's NEXT group into the other pinned slot while the GPU works on the current one, so with
+// one context per GPU the device only waits for the first group of the run.
 void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, size_t>>& groups, size_t rank, size_t world,
                 std::atomic<size_t>& cursor, std::vector<FileResult>& out) {
     const Args& args = J.args;
@@ -413,36 +456,30 @@ void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, si
     CK(wb_create(&ctx, device, &J.mc, J.wpath.empty() ? nullptr : J.wpath.c_str()));
     struct Guard { wb_ctx* c; ~Guard() { wb_destroy(c); } } guard{ctx};
     TRACE("worker on gpu %d: context ready", device);
+    PinnedPcm slots[2];
+    auto prefetch = [&](int which) {
+        return std::async(std::launch::async, [&, which] { return load_group(J, device, groups, rank, world, cursor, slots[which]); });
+    };
+    std::future<LoadedGroup> next = prefetch(0);                 // overlaps the warm-up
+    struct Drain { std::future<LoadedGroup>& f; ~Drain() { if (f.valid()) f.wait(); } } drain{next};   // never leave a loader running
     if (args.warmup > 0) {
         Pcm a0;
         CK(wb_host_load_audio_16k_mono(join(args.audio_dir, J.files[0]).c_str(), &a0.p, &a0.n, &a0.dur));
         WB_REQUIRE(a0.n > 0, WB_EINVAL, "Empty audio");
-        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, J.mc.max_batch, {FilePcm{a0.p, a0.n}}, args, J.tok, J.gen, t); }
+        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, J.mc.max_batch, a0.p, {0, a0.n}, args, J.tok, J.gen, t); }
         TRACE("worker on gpu %d: warm-up done", device);
     }
-    for (;;) {
-        const size_t k = cursor.fetch_add(1);                 // k-th group of this rank
-        const size_t g = rank + k * world;
-        if (g >= groups.size()) break;
-        const size_t g0 = groups[g].first, g1 = groups[g].second;
-        std::vector<Pcm> au(g1 - g0);
-        std::vector<double> load_s(g1 - g0);
-        std::vector<FilePcm> group;
-        for (size_t i = g0; i < g1; ++i) {
-            auto tl0 = Clock::now();
-            Pcm& p = au[i - g0];
-            CK(wb_host_load_audio_16k_mono(join(args.audio_dir, J.files[i]).c_str(), &p.p, &p.n, &p.dur));
-            load_s[i - g0] = since(tl0);
-            WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
-            group.push_back(FilePcm{p.p, p.n});
-        }
+    for (int cur = 0;; cur ^= 1) {
+        LoadedGroup L = next.get();
+        if (L.g == SIZE_MAX) break;
+        next = prefetch(cur ^ 1);
         Timing t;
-        std::vector<std::string> texts = transcribe(ctx, J.mc.max_batch, group, args, J.tok, J.gen, t);
-        TRACE("gpu %d: group %zu (%zu files) load %.3f s, preprocess %.3f s, model %.3f s, detokenise %.3f s", device, g, g1 - g0,
-              [&] { double a = 0; for (double x : load_s) a += x; return a; }(), t.preprocess_s, t.model_only_s, t.decode_s);
-        for (size_t i = g0; i < g1; ++i) {
+        std::vector<std::string> texts = transcribe(ctx, J.mc.max_batch, slots[cur].p, L.offs, args, J.tok, J.gen, t);
+        TRACE("gpu %d: group %zu (%zu files) load %.3f s, preprocess %.3f s, model %.3f s, detokenise %.3f s", device, L.g, L.g1 - L.g0,
+              L.load_total, t.preprocess_s, t.model_only_s, t.decode_s);
+        for (size_t i = L.g0; i < L.g1; ++i) {
             FileResult& fr = out[i];
-            fr.dur = au[i - g0].dur; fr.load_s = load_s[i - g0]; fr.t = t; fr.text = texts[i - g0];
+            fr.dur = L.dur[i - L.g0]; fr.load_s = L.load_s[i - L.g0]; fr.t = t; fr.text = texts[i - L.g0];
             fr.done = true;
         }
     }

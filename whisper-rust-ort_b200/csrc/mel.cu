@@ -1,26 +1,34 @@
 // mel.cu — kernel group 1: batched Whisper log-mel (replaces whisper_log_mel_80,
 // /root/reference/src/main.rs:407-509, and the chunk slicing of :895-905).
 //
-// K1a logmel_raw_kernel : PCM -> log10(max(mel,1e-10)) time-major [frame][80] + per-FILE max
+// K1a logmel_raw_kernel : PCM -> log10(max(mel,1e-10)) time-major [frame][n_mels] + per-FILE max
 //                         (the reference clamps against the max of the whole file, quirk Q1).
 // K1b mel_chunks_kernel : clamp(max-8), (x+4)/4, cut 3000-frame windows, zero-pad in mel space
 //                         (Q2) -> [chunk][1+3000+1][n_mels] time-major in the encoder's compute
 //                         dtype, the layout the conv-stem GEMM consumes without im2col.
-// K1c mel_export_kernel : same normalisation, reference layout [80][frames] f32 (API/test only).
+// K1c mel_export_kernel : same normalisation, reference layout [n_mels][frames] f32 (API/test only).
+// n_mels is 80 (the reference's whisper_log_mel_80) or 128 (the large-v3 frontend: same code, filterbank of 128
+// triangles over the same 201 bins — BASELINE.json configs[4]).
 //
 // HBM-bound by design (1.92 MB in + 0.96 MB out per 30 s clip); the FFT is a
 // register-resident 20x20 four-step (mel_math.h) so the only global traffic is PCM in, mel out.
 #include "ctx.h"
 #include "mel_math.h"
+#define WB_PACKED_F32X2
+#include "mel_math.h"
+#undef WB_PACKED_F32X2
 
 namespace {
 
-constexpr int FPT = 32;                       // frames per tile (one CTA)
-constexpr int MEL_WARPS = 8;
-constexpr int MEL_THREADS = MEL_WARPS * 32;   // each warp owns 2 of the tile's 16 frame pairs
+constexpr int FPT = WB_MEL_FPT;               // frames per tile (24: 3000 frames = 125 tiles exactly)
+constexpr int NPAIR = FPT / 2;                // two real frames ride one complex FFT
+constexpr int MEL_THREADS = NPAIR * 20;       // thread = (frame pair, FFT column): every lane of every warp has a column
 constexpr int SPAN = (FPT - 1) * 160 + 400;   // padded samples a tile touches
 constexpr int SCR = 420;                      // 20 x 21 (padded) complex per FFT
-constexpr int POW_LD = 204;
+constexpr int PLD = 419;                      // power-spectrum row pitch (odd: frames land in different banks)
+constexpr int FBW_MAX = 512;                  // non-zero filterbank weights (<= 2 per FFT bin + slack)
+static_assert(FPT * PLD <= NPAIR * SCR * 2, "power rows live in the FFT scratch");
+static_assert(FPT * 128 <= SPAN, "log-mel tile is staged in the PCM buffer");
 
 __device__ __forceinline__ float padded_sample(const float* __restrict__ x, int64_t N, int64_t p) {
     // main.rs:419-435: reflect-pad 200 each side (N >= 2), else audio then zeros.
@@ -44,147 +52,191 @@ __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// K1a.  One CTA = 32 frames of one file.  The PCM span is staged once (128-bit loads for interior
-// tiles); after that every warp works alone on its frame pairs — two real frames packed into one
-// complex 400-point FFT (20 lanes x 20-point DFT, twiddle, transpose through the warp's scratch,
-// 20-point DFT), Hermitian split into two power spectra, sparse mel, log10 — with warp-level
-// synchronisation only: no CTA barrier inside the frame loop.
+// K1a.  One CTA walks `tiles_per_cta` consecutive tiles of 24 frames.  Per tile: the PCM span is staged once (128-bit
+// loads for interior tiles); thread (pair, column) runs the 20-point column DFT of the pair's packed complex frame,
+// twiddles and scatters it; the same thread then runs the 20-point row DFT; the Hermitian split gives both power
+// spectra; the sparse mel filterbank runs with a warp's lanes on the SAME mel bins of different frame groups (no
+// divergence on the run length, weights broadcast); the [24][n_mels] log10 tile goes out in 128-bit stores.
+template <int NM, bool PACKED>
 __global__ void __launch_bounds__(MEL_THREADS, 3)
 logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ file_off,
                   const int64_t* __restrict__ frame_off, const int* __restrict__ tile_off,
-                  int n_files, const MelTables* __restrict__ tab, float* __restrict__ raw,
-                  int* __restrict__ fmax) {
+                  int n_files, int total_tiles, int tiles_per_cta, const MelTables* __restrict__ tab,
+                  float* __restrict__ raw, int* __restrict__ fmax) {
     extern __shared__ __align__(16) float smem[];
-    float* s_pcm = smem;                                       // SPAN
+    float* s_pcm = smem;                                       // SPAN; later the [FPT][NM] output tile
     float* s_win = s_pcm + SPAN;                               // 400
     float2* s_tw = reinterpret_cast<float2*>(s_win + 400);     // 400
-    float* s_fbw = reinterpret_cast<float*>(s_tw + 400);       // 400
-    int* s_fbi = reinterpret_cast<int*>(s_fbw + 400);          // start[80], len[80], off[80]
-    float2* s_scr = reinterpret_cast<float2*>(s_fbi + 240);    // MEL_WARPS * SCR
-    float* s_pow = reinterpret_cast<float*>(s_scr + MEL_WARPS * SCR);   // MEL_WARPS * 2 * POW_LD
-    __shared__ float s_red[MEL_WARPS];
+    float* s_fbw = reinterpret_cast<float*>(s_tw + 400);       // FBW_MAX
+    int* s_fbi = reinterpret_cast<int*>(s_fbw + FBW_MAX);      // start[NM], len[NM], off[NM]
+    float2* s_scr = reinterpret_cast<float2*>(s_fbi + 3 * NM); // NPAIR * SCR complex; later FPT power rows
+    float* s_pow = reinterpret_cast<float*>(s_scr);
+    __shared__ int s_tmax;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // tile -> file (binary search over the tile prefix sums)
-    int lo = 0, hi = n_files - 1;
-    const int tile = blockIdx.x;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
-    }
-    const int file = lo;
-    const int64_t N = file_off[file + 1] - file_off[file];
-    const float* x = pcm + file_off[file];
-    const int64_t nf = frame_off[file + 1] - frame_off[file];
-    const int64_t f0 = (int64_t)(tile - tile_off[file]) * FPT;
-
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int pair = tid / 20, col = tid - pair * 20;
     for (int i = tid; i < 400; i += MEL_THREADS) {
         s_win[i] = tab->window[i];
         s_tw[i] = make_float2(tab->tw_re[i], tab->tw_im[i]);
-        s_fbw[i] = tab->fb_w[i];
     }
-    for (int i = tid; i < 240; i += MEL_THREADS) s_fbi[i] = tab->fb_idx[i];
-    {
-        const int64_t p0 = f0 * 160;                             // first padded sample of the tile
-        const float* src = x + (p0 - 200);
-        const bool interior = p0 >= 200 && p0 - 200 + SPAN <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-        if (interior) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            float4* d4 = reinterpret_cast<float4*>(s_pcm);
-            for (int j = tid; j < SPAN / 4; j += MEL_THREADS) d4[j] = __ldg(s4 + j);
-        } else {
-            for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j] = padded_sample(x, N, p0 + j);
-        }
-    }
-    __syncthreads();
+    for (int i = tid; i < FBW_MAX; i += MEL_THREADS) s_fbw[i] = tab->fb_w[i];
+    for (int i = tid; i < 3 * NM; i += MEL_THREADS) s_fbi[i] = tab->fb_idx[i];
+    if (tid == 0) s_tmax = (int)0xff800000u;                   // -inf
 
-    float2* scr = s_scr + warp * SCR;
-    float* pw = s_pow + warp * 2 * POW_LD;
-    float tmax = -INFINITY;
-    for (int pair = warp; pair < FPT / 2; pair += MEL_WARPS) {
-        const int fa = 2 * pair;                                 // tile-local frame A (B = A + 1)
-        // ---- step 1: 20-pt DFT over n1 for column n2 = lane, twiddle, scatter ----
-        if (lane < 20) {
-            const float* pa = s_pcm + fa * 160;
+    const int tile_end = min(total_tiles, (int)(blockIdx.x + 1) * tiles_per_cta);
+    for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
+        // tile -> file (binary search over the tile prefix sums)
+        int lo = 0, hi = n_files - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
+        }
+        const int file = lo;
+        const int64_t N = file_off[file + 1] - file_off[file];
+        const float* x = pcm + file_off[file];
+        const int64_t nf = frame_off[file + 1] - frame_off[file];
+        const int64_t f0 = (int64_t)(tile - tile_off[file]) * FPT;
+        {
+            const int64_t p0 = f0 * 160;                             // first padded sample of the tile
+            const float* src = x + (p0 - 200);
+            const bool interior = p0 >= 200 && p0 - 200 + SPAN <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+            if (interior) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4* d4 = reinterpret_cast<float4*>(s_pcm);
+                for (int j = tid; j < SPAN / 4; j += MEL_THREADS) d4[j] = __ldg(s4 + j);
+            } else {
+                for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j] = padded_sample(x, N, p0 + j);
+            }
+        }
+        __syncthreads();
+
+        float2* scr = s_scr + pair * SCR;
+        // ---- step 1: 20-pt DFT over n1 for column n2 = col, twiddle, scatter ----
+        {
+            const float* pa = s_pcm + pair * 320;
             c32 v[20];
 #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
-                int i = 20 * n1 + lane;
+                int i = 20 * n1 + col;
                 float w = s_win[i];
                 v[n1] = {pa[i] * w, pa[160 + i] * w};
             }
-            dft20(v);
+            if (PACKED) fft_packed::dft20(v); else fft_scalar::dft20(v);
 #pragma unroll
             for (int k1 = 0; k1 < 20; ++k1) {
-                float2 t = s_tw[lane * k1];
-                c32 z = cmul(v[k1], c32{t.x, t.y});
-                scr[k1 * 21 + lane] = make_float2(z.x, z.y);
+                float2 t = s_tw[col * k1];
+                c32 z = fft_scalar::cmul(v[k1], c32{t.x, t.y});
+                scr[k1 * 21 + col] = make_float2(z.x, z.y);
             }
         }
-        __syncwarp();
-        // ---- step 2: 20-pt DFT over n2 for row k1 = lane ----
+        __syncthreads();
+        // ---- step 2: 20-pt DFT over n2 for row k1 = col ----
         {
             c32 v[20];
-            if (lane < 20) {
 #pragma unroll
-                for (int n2 = 0; n2 < 20; ++n2) {
-                    float2 t = scr[lane * 21 + n2];
-                    v[n2] = {t.x, t.y};
+            for (int n2 = 0; n2 < 20; ++n2) {
+                float2 t = scr[col * 21 + n2];
+                v[n2] = {t.x, t.y};
+            }
+            if (PACKED) fft_packed::dft20(v); else fft_scalar::dft20(v);
+            __syncthreads();                                         // every row has been read
+#pragma unroll
+            for (int k2 = 0; k2 < 20; ++k2) scr[col + 20 * k2] = make_float2(v[k2].x, v[k2].y);
+        }
+        __syncthreads();
+        // ---- power spectra of both packed frames, k = 0..200 (through registers: the rows overwrite the scratch) ----
+        {
+            constexpr int NIT = (NPAIR * 201 + MEL_THREADS - 1) / MEL_THREADS;
+            float pa[NIT], pb[NIT];
+#pragma unroll
+            for (int r = 0; r < NIT; ++r) {
+                int it = tid + r * MEL_THREADS;
+                if (it < NPAIR * 201) {
+                    int p = it / 201, k = it - p * 201;
+                    float2 z = s_scr[p * SCR + k];
+                    float2 c = s_scr[p * SCR + (k == 0 ? 0 : 400 - k)];
+                    float ar = z.x + c.x, ai = z.y - c.y;          // 2*A[k]
+                    float br = z.x - c.x, bi = z.y + c.y;          // 2i*B[k]
+                    pa[r] = 0.25f * (ar * ar + ai * ai);
+                    pb[r] = 0.25f * (br * br + bi * bi);
                 }
-                dft20(v);
             }
-            __syncwarp();                                        // every row has been read
-            if (lane < 20) {
+            __syncthreads();
 #pragma unroll
-                for (int k2 = 0; k2 < 20; ++k2) scr[lane + 20 * k2] = make_float2(v[k2].x, v[k2].y);
+            for (int r = 0; r < NIT; ++r) {
+                int it = tid + r * MEL_THREADS;
+                if (it < NPAIR * 201) {
+                    int p = it / 201, k = it - p * 201;
+                    s_pow[(2 * p) * PLD + k] = pa[r];
+                    s_pow[(2 * p + 1) * PLD + k] = pb[r];
+                }
             }
         }
-        __syncwarp();
-        // ---- power spectra of both packed frames, k = 0..200 ----
-        for (int k = lane; k < 201; k += 32) {
-            float2 z = scr[k];
-            float2 c = scr[k == 0 ? 0 : 400 - k];
-            float ar = z.x + c.x, ai = z.y - c.y;          // 2*A[k]
-            float br = z.x - c.x, bi = z.y + c.y;          // 2i*B[k]
-            pw[k] = 0.25f * (ar * ar + ai * ai);
-            pw[POW_LD + k] = 0.25f * (br * br + bi * bi);
-        }
-        __syncwarp();
-        // ---- mel filterbank (sequential f32 sum in k order, main.rs:484-490), log10 ----
-        const int64_t fbase = f0 + fa;
-        for (int it = lane; it < 2 * 80; it += 32) {
-            int fl = it / 80, m = it - fl * 80;
-            if (fbase + fl < nf) {
-                const float* p = pw + fl * POW_LD + s_fbi[m];
-                const float* w = s_fbw + s_fbi[160 + m];
-                int len = s_fbi[80 + m];
-                float e = 0.0f;
-                for (int j = 0; j < len; ++j) e = __fadd_rn(e, __fmul_rn(w[j], p[j]));
-                float lv = log10f(fmaxf(e, 1e-10f));
-                raw[(frame_off[file] + fbase) * 80 + it] = lv;
-                tmax = fmaxf(tmax, lv);
+        __syncthreads();
+        // ---- mel filterbank (f32 sum in k order, main.rs:484-490) for 4 frames at a time, log10 -> s_out[frame][NM] ----
+        float* s_out = s_pcm;
+        float tmax = -INFINITY;
+        for (int it = tid; it < NM * (FPT / 4); it += MEL_THREADS) {
+            const int m = it / (FPT / 4), fg = it - m * (FPT / 4);
+            const float* p = s_pow + (4 * fg) * PLD + s_fbi[m];
+            const float* w = s_fbw + s_fbi[2 * NM + m];
+            const int len = s_fbi[NM + m];
+            float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
+            for (int j = 0; j < len; ++j) {
+                const float wj = w[j];
+                e0 = fmaf(wj, p[j], e0);
+                e1 = fmaf(wj, p[PLD + j], e1);
+                e2 = fmaf(wj, p[2 * PLD + j], e2);
+                e3 = fmaf(wj, p[3 * PLD + j], e3);
             }
-        }
-        __syncwarp();
-    }
-    // ---- block max -> one atomic per tile ----
+            const float e[4] = {e0, e1, e2, e3};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if (lane == 0) s_red[warp] = tmax;
-    __syncthreads();
-    if (tid == 0) {
-        float m = s_red[0];
-        for (int w = 1; w < MEL_WARPS; ++w) m = fmaxf(m, s_red[w]);
-        if (m > -INFINITY) atomic_max_float(fmax + file, m);
+            for (int q = 0; q < 4; ++q) {
+                const float lv = 0.30102999566398120f * __log2f(fmaxf(e[q], 1e-10f));
+                s_out[(4 * fg + q) * NM + m] = lv;
+                if (f0 + 4 * fg + q < nf) tmax = fmaxf(tmax, lv);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0 && tmax > -INFINITY) atomic_max_float(&s_tmax, tmax);
+        __syncthreads();
+        {
+            const int64_t left = nf - f0;
+            const int n_valid = (int)(left < FPT ? left : FPT) * NM;          // floats, a multiple of 4
+            float4* dst = reinterpret_cast<float4*>(raw + (frame_off[file] + f0) * NM);
+            const float4* src4 = reinterpret_cast<const float4*>(s_out);
+            for (int j = tid; j < n_valid / 4; j += MEL_THREADS) dst[j] = src4[j];
+        }
+        if (tid == 0) {
+            const int m = s_tmax;
+            if (m != (int)0xff800000u) atomic_max_float(fmax + file, __int_as_float(m));
+            s_tmax = (int)0xff800000u;
+        }
+        __syncthreads();                                             // s_out (= s_pcm) is free for the next tile
     }
+}
+
+__global__ void fill_int_kernel(int* __restrict__ p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 template <typename T> __device__ __forceinline__ T to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
-// K1b: one CTA row-block per chunk; out [chunk][3002][n_mels], rows 0 and 3001 stay zero.
-template <typename T>
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// K1b: grid (x, chunk); out [chunk][3002][NM], rows 0 and 3001 stay zero.  Four mel bins per thread (128-bit loads).
+template <typename T, int NM>
 __global__ void mel_chunks_kernel(const float* __restrict__ raw, const int64_t* __restrict__ frame_off,
                                   const int* __restrict__ fmax, const MelChunk* __restrict__ chunks,
                                   T* __restrict__ out, int chunk0) {
@@ -192,37 +244,41 @@ __global__ void mel_chunks_kernel(const float* __restrict__ raw, const int64_t* 
     const MelChunk ch = chunks[chunk0 + c];
     const int64_t nf = frame_off[ch.file + 1] - frame_off[ch.file];
     const float floor_v = __int_as_float(fmax[ch.file]) - 8.0f;
-    const float* src = raw + (frame_off[ch.file] + ch.frame_start) * 80;
-    T* dst = out + (size_t)c * (WB_N_FRAMES + 2) * 80;
-    const int total = (WB_N_FRAMES + 2) * 80;
+    const float4* src = reinterpret_cast<const float4*>(raw + (frame_off[ch.file] + ch.frame_start) * NM);
+    T* dst = out + (size_t)c * (WB_N_FRAMES + 2) * NM;
+    constexpr int V = NM / 4;
+    const int total = (WB_N_FRAMES + 2) * V;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int row = i / 80;
-        int t = row - 1;
-        float v = 0.0f;                                           // literal 0.0 padding (Q2)
+        const int t = i / V - 1;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);                // literal 0.0 padding (Q2)
         if (t >= 0 && t < WB_N_FRAMES && ch.frame_start + t < nf) {
-            float lv = src[i - 80];
-            v = (fmaxf(lv, floor_v) + 4.0f) / 4.0f;               // main.rs:502-506
+            const float4 lv = __ldg(src + (i - V));
+            v.x = (fmaxf(lv.x, floor_v) + 4.0f) / 4.0f;               // main.rs:502-506
+            v.y = (fmaxf(lv.y, floor_v) + 4.0f) / 4.0f;
+            v.z = (fmaxf(lv.z, floor_v) + 4.0f) / 4.0f;
+            v.w = (fmaxf(lv.w, floor_v) + 4.0f) / 4.0f;
         }
-        dst[i] = to_out<T>(v);
+        store4(dst + (size_t)i * 4, v);
     }
 }
 
 // K1c: reference layout out[m][f] for f in [0,n_out), source frames frame0+f (valid if < nf).
+template <int NM>
 __global__ void mel_export_kernel(const float* __restrict__ raw, int64_t frame_base, int64_t frame0,
                                   int64_t nf, const int* __restrict__ fmax, int file,
                                   float* __restrict__ out, int64_t n_out) {
-    __shared__ float tile[32][81];
+    __shared__ float tile[32][NM + 1];
     const float floor_v = __int_as_float(fmax[file]) - 8.0f;
     const int64_t fb = (int64_t)blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * 80; i += blockDim.x) {
-        int fl = i / 80, m = i - fl * 80;
+    for (int i = threadIdx.x; i < 32 * NM; i += blockDim.x) {
+        int fl = i / NM, m = i - fl * NM;
         int64_t f = frame0 + fb + fl;
         float v = 0.0f;
-        if (fb + fl < n_out && f < nf) v = (fmaxf(raw[(frame_base + f) * 80 + m], floor_v) + 4.0f) / 4.0f;
+        if (fb + fl < n_out && f < nf) v = (fmaxf(raw[(frame_base + f) * NM + m], floor_v) + 4.0f) / 4.0f;
         tile[fl][m] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 80; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 32 * NM; i += blockDim.x) {
         int m = i / 32, fl = i - m * 32;
         if (fb + fl < n_out) out[(int64_t)m * n_out + fb + fl] = tile[fl][m];
     }
@@ -247,12 +303,13 @@ __global__ void mel_transpose_in_kernel(const float* __restrict__ in, T* __restr
     }
 }
 
-constexpr size_t MEL_SMEM = sizeof(float) * (SPAN + 400 + 800 + 400 + 240 + 2 * MEL_WARPS * SCR + MEL_WARPS * 2 * POW_LD);
+constexpr size_t mel_smem(int nm) { return sizeof(float) * (size_t)(SPAN + 400 + 800 + FBW_MAX + 3 * nm + 2 * NPAIR * SCR); }
 
 }  // namespace
 
 // ---------------- host side ----------------
-void mel_build_tables(MelTables& t) {
+void mel_build_tables(MelTables& t, int n_mels) {
+    if (n_mels != 80 && n_mels != 128) return;      // encoder-only use with host mel input; wb_upload_pcm rejects the config
     // main.rs:323-330
     for (int i = 0; i < 400; ++i) {
         float x = (3.14159265358979323846f * 2.0f * (float)i) / 400.0f;
@@ -276,10 +333,10 @@ void mel_build_tables(MelTables& t) {
         if (mel >= 15.0f) hz = 1000.0f * expf(logstep * (mel - 15.0f));
         return hz;
     };
-    const int n_mels = 80, n_freq = 201;
+    const int n_freq = 201;
     float fmax_hz = fminf(8000.0f, 16000.0f / 2.0f);
     float mel_min = hz_to_mel(0.0f), mel_max = hz_to_mel(fmax_hz);
-    float fp[82], ff[201];
+    float fp[130], ff[201];
     for (int i = 0; i < n_mels + 2; ++i) {
         float m = mel_min + (mel_max - mel_min) * (float)i / (float)(n_mels + 1);
         fp[i] = mel_to_hz(m);
@@ -297,7 +354,7 @@ void mel_build_tables(MelTables& t) {
     }
     // compact: contiguous non-zero run per mel (zeros contribute exactly 0 to the f32 sum)
     int off = 0;
-    for (int i = 0; i < 400; ++i) t.fb_w[i] = 0.0f;
+    for (int i = 0; i < FBW_MAX; ++i) t.fb_w[i] = 0.0f;
     for (int m = 0; m < n_mels; ++m) {
         int s = 0, e = 0;
         bool any = false;
@@ -308,10 +365,10 @@ void mel_build_tables(MelTables& t) {
                 e = k + 1;
             }
         if (!any) { s = 0; e = 0; }
-        WB_REQUIRE(off + (e - s) <= 400, WB_EINVAL, "mel filterbank has too many non-zeros");
+        WB_REQUIRE(off + (e - s) <= FBW_MAX, WB_EINVAL, "mel filterbank has too many non-zeros");
         t.fb_idx[m] = s;
-        t.fb_idx[80 + m] = e - s;
-        t.fb_idx[160 + m] = off;
+        t.fb_idx[n_mels + m] = e - s;
+        t.fb_idx[2 * n_mels + m] = off;
         for (int k = s; k < e; ++k) t.fb_w[off++] = fb[(size_t)m * n_freq + k];
     }
 }
@@ -325,27 +382,40 @@ int64_t mel_n_frames(int64_t n) {
 // cudaFuncSetAttribute applies to the CURRENT device only: called from wb_create for every context (after
 // cudaSetDevice), never behind a process-wide flag (a second GPU in the same process would miss the opt-in).
 void mel_set_attrs() {
-    CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MEL_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel<80, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem(80)));
+    CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem(80)));
+    CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem(128)));
+    CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem(128)));
 }
 
 void mel_launch_raw(wb_ctx* ctx) {
     MelState& s = ctx->mel;
-    // -inf as int bits
-    std::vector<int> init(s.n_files, (int)0xff800000u);
-    CUDA_CHECK(cudaMemcpyAsync(s.fmax.p, init.data(), sizeof(int) * s.n_files, cudaMemcpyHostToDevice, ctx->stream));
-    logmel_raw_kernel<<<s.total_tiles, MEL_THREADS, MEL_SMEM, ctx->stream>>>(
-        s.pcm.p, s.file_off.p, s.frame_off.p, s.tile_off.p, s.n_files, ctx->mel_tables_dev, s.raw.p, s.fmax.p);
+    fill_int_kernel<<<ceil_div(s.n_files, 256), 256, 0, ctx->stream>>>(s.fmax.p, s.n_files, (int)0xff800000u);   // -inf as int bits
+    // a CTA keeps its tables for `tpc` consecutive tiles; small uploads stay one tile per CTA so they still fill the SMs
+    int tpc = s.total_tiles >= 8 * 3 * ctx->sm_count ? 4 : (s.total_tiles >= 2 * 3 * ctx->sm_count ? 2 : 1);
+    if (const char* e = getenv("WB_MEL_TPC")) tpc = std::max(1, atoi(e));
+    const int grid = ceil_div(s.total_tiles, tpc);
+    bool packed = true;                                     // FADD2 butterflies
+    if (const char* e = getenv("WB_MEL_PACKED")) packed = atoi(e) != 0;
+#define WB_MEL_RAW(NM, PK) logmel_raw_kernel<NM, PK><<<grid, MEL_THREADS, mel_smem(NM), ctx->stream>>>( \
+        s.pcm.p, s.file_off.p, s.frame_off.p, s.tile_off.p, s.n_files, s.total_tiles, tpc, ctx->mel_tables_dev, s.raw.p, s.fmax.p)
+    if (ctx->cfg.n_mels == 128) { if (packed) WB_MEL_RAW(128, true); else WB_MEL_RAW(128, false); }
+    else { if (packed) WB_MEL_RAW(80, true); else WB_MEL_RAW(80, false); }
+#undef WB_MEL_RAW
     CUDA_CHECK(cudaGetLastError());
-    ctx->timing.mel_launches += 1;
+    ctx->timing.mel_launches += 2;          // fill + K1a
 }
 
 void mel_launch_chunks(wb_ctx* ctx, int chunk0, int n, void* out) {
     MelState& s = ctx->mel;
-    dim3 grid(60, n);
-    if (ctx->cfg.precision == WB_PREC_BF16)
-        mel_chunks_kernel<__nv_bfloat16><<<grid, 256, 0, ctx->stream>>>(s.raw.p, s.frame_off.p, s.fmax.p, s.chunks.p, (__nv_bfloat16*)out, chunk0);
-    else
-        mel_chunks_kernel<float><<<grid, 256, 0, ctx->stream>>>(s.raw.p, s.frame_off.p, s.fmax.p, s.chunks.p, (float*)out, chunk0);
+    dim3 grid(30, n);
+    const bool bf = ctx->cfg.precision == WB_PREC_BF16, big = ctx->cfg.n_mels == 128;
+#define WB_MEL_CHUNKS(T, NM) mel_chunks_kernel<T, NM><<<grid, 256, 0, ctx->stream>>>(s.raw.p, s.frame_off.p, s.fmax.p, s.chunks.p, (T*)out, chunk0)
+    if (bf && big) WB_MEL_CHUNKS(__nv_bfloat16, 128);
+    else if (bf) WB_MEL_CHUNKS(__nv_bfloat16, 80);
+    else if (big) WB_MEL_CHUNKS(float, 128);
+    else WB_MEL_CHUNKS(float, 80);
+#undef WB_MEL_CHUNKS
     CUDA_CHECK(cudaGetLastError());
     ctx->timing.mel_launches += 1;
 }
@@ -354,7 +424,10 @@ void mel_launch_export(wb_ctx* ctx, int file, int64_t frame0, int64_t n_out, flo
     MelState& s = ctx->mel;
     int64_t nf = s.h_frame_off[file + 1] - s.h_frame_off[file];
     int blocks = (int)ceil_div64(n_out, 32);
-    mel_export_kernel<<<blocks, 256, 0, ctx->stream>>>(s.raw.p, s.h_frame_off[file], frame0, nf, s.fmax.p, file, out_dev, n_out);
+    if (ctx->cfg.n_mels == 128)
+        mel_export_kernel<128><<<blocks, 256, 0, ctx->stream>>>(s.raw.p, s.h_frame_off[file], frame0, nf, s.fmax.p, file, out_dev, n_out);
+    else
+        mel_export_kernel<80><<<blocks, 256, 0, ctx->stream>>>(s.raw.p, s.h_frame_off[file], frame0, nf, s.fmax.p, file, out_dev, n_out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -370,6 +443,7 @@ void mel_launch_transpose_in(wb_ctx* ctx, const float* in_dev, void* out, int B)
 
 // CPU emulation of the kernel's FFT data flow (same mel_math.h code) for the no-GPU unit test.
 extern "C" int wb_selftest_fft400(const float* re, const float* im, float* out_re, float* out_im) {
+    using namespace fft_scalar;
     std::vector<c32> scr(SCR), X(400);
     for (int n2 = 0; n2 < 20; ++n2) {
         c32 v[20];

@@ -1,11 +1,14 @@
 // mel_math.h — register-resident FFT building blocks for the log-mel kernel (K1).
-// 400 = 20 x 20 (four-step): each of 20 threads runs a 20-point DFT (4 x 5 Cooley-Tukey, fully
-// unrolled, constants folded), exchanges through shared memory with a W_400 twiddle, and runs a
+// 400 = 20 x 20 (four-step): each of 20 threads runs a 20-point DFT (4 x 5 prime-factor, fully
+// unrolled, no inner twiddles), exchanges through shared memory with a W_400 twiddle, and runs a
 // second 20-point DFT.  Two real frames are packed as one complex signal (re = frame A,
 // im = frame B) and separated by Hermitian symmetry.  Host+device so the math is unit-tested on
 // the CPU (wb_selftest_fft400) before it ever meets a GPU.
 // Replaces rustfft's 400-point plan (reference call sites /root/reference/src/main.rs:440-441,473).
-#pragma once
+// Included twice by mel.cu: once as namespace fft_scalar (one FADD per component) and once, with WB_PACKED_F32X2
+// defined, as fft_packed (sm_100 FADD2: both components of a complex add in one instruction).
+#ifndef WB_MEL_MATH_COMMON
+#define WB_MEL_MATH_COMMON
 #ifdef __CUDA_ARCH__
 #define WB_UNROLL _Pragma("unroll")
 #else
@@ -20,8 +23,21 @@
 struct c32 {
     float x, y;
 };
+#endif
+
+#ifdef WB_PACKED_F32X2
+namespace fft_packed {
+#else
+namespace fft_scalar {
+#endif
+#if defined(__CUDA_ARCH__) && defined(WB_PACKED_F32X2)
+// sm_100: one FADD2 adds both halves of a complex number
+WB_HD c32 cadd(c32 a, c32 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return {r.x, r.y}; }
+WB_HD c32 csub(c32 a, c32 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y)); return {r.x, r.y}; }
+#else
 WB_HD c32 cadd(c32 a, c32 b) { return {a.x + b.x, a.y + b.y}; }
 WB_HD c32 csub(c32 a, c32 b) { return {a.x - b.x, a.y - b.y}; }
+#endif
 WB_HD c32 cmul(c32 a, c32 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 WB_HD c32 mul_negi(c32 a) { return {a.y, -a.x}; }   // (-i) * a
 WB_HD c32 mul_posi(c32 a) { return {-a.y, a.x}; }   // (+i) * a
@@ -54,40 +70,30 @@ WB_HD void dft5(c32& x0, c32& x1, c32& x2, c32& x3, c32& x4) {
     x3 = csub(m2, in2);
 }
 
-// W_20^j = exp(-2*pi*i*j/20), j = 0..12 (largest b*c used is 4*3)
-WB_HD c32 w20(int j) {
-    const float C[13] = {1.0f, 0.95105651629515357f, 0.80901699437494742f, 0.58778525229247313f,
-                         0.30901699437494742f, 0.0f, -0.30901699437494742f, -0.58778525229247313f,
-                         -0.80901699437494742f, -0.95105651629515357f, -1.0f, -0.95105651629515357f,
-                         -0.80901699437494742f};
-    const float S[13] = {0.0f, 0.30901699437494742f, 0.58778525229247313f, 0.80901699437494742f,
-                         0.95105651629515357f, 1.0f, 0.95105651629515357f, 0.80901699437494742f,
-                         0.58778525229247313f, 0.30901699437494742f, 0.0f, -0.30901699437494742f,
-                         -0.58778525229247313f};
-    return {C[j], -S[j]};
-}
-
-// In-place forward 20-point DFT. Input v[n] (natural order), output v[k] (natural order).
+// In-place forward 20-point DFT, prime-factor (Good-Thomas) form: 4 and 5 are coprime, so with
+//   n = (5 n1 + 4 n2) mod 20   and   k = (5 k1 + 16 k2) mod 20
+// W_20^(nk) = W_4^(n1 k1) * W_5^(n2 k2): five radix-4 and four radix-5 butterflies and NO twiddles in between.
+// Every index is a compile-time constant after unrolling, so v[] stays in registers.
 WB_HD void dft20(c32 (&v)[20]) {
-    // n = 5a + b ; k = c + 4e
-    c32 u[5][4];
+    c32 u[4][5];
 WB_UNROLL
-    for (int b = 0; b < 5; ++b) {
-        c32 a0 = v[b], a1 = v[5 + b], a2 = v[10 + b], a3 = v[15 + b];
+    for (int n2 = 0; n2 < 5; ++n2) {
+        c32 a0 = v[(4 * n2) % 20], a1 = v[(5 + 4 * n2) % 20], a2 = v[(10 + 4 * n2) % 20], a3 = v[(15 + 4 * n2) % 20];
         dft4(a0, a1, a2, a3);
-        u[b][0] = a0;
-        u[b][1] = (b == 0) ? a1 : cmul(a1, w20(b * 1));
-        u[b][2] = (b == 0) ? a2 : cmul(a2, w20(b * 2));
-        u[b][3] = (b == 0) ? a3 : cmul(a3, w20(b * 3));
+        u[0][n2] = a0;
+        u[1][n2] = a1;
+        u[2][n2] = a2;
+        u[3][n2] = a3;
     }
 WB_UNROLL
-    for (int c = 0; c < 4; ++c) {
-        c32 y0 = u[0][c], y1 = u[1][c], y2 = u[2][c], y3 = u[3][c], y4 = u[4][c];
+    for (int k1 = 0; k1 < 4; ++k1) {
+        c32 y0 = u[k1][0], y1 = u[k1][1], y2 = u[k1][2], y3 = u[k1][3], y4 = u[k1][4];
         dft5(y0, y1, y2, y3, y4);
-        v[c] = y0;
-        v[c + 4] = y1;
-        v[c + 8] = y2;
-        v[c + 12] = y3;
-        v[c + 16] = y4;
+        v[(5 * k1) % 20] = y0;
+        v[(5 * k1 + 16) % 20] = y1;
+        v[(5 * k1 + 32) % 20] = y2;
+        v[(5 * k1 + 48) % 20] = y3;
+        v[(5 * k1 + 64) % 20] = y4;
     }
 }
+}  // namespace fft_scalar / fft_packed
