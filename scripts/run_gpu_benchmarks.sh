@@ -13,7 +13,7 @@ set -euo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 CLI="${CLI:-${ROOT}/whisper-rust-ort_b200/whisper_b200_cli}"
 GPUS_LIST="${GPUS_LIST:-1 2 4 8}"
-AUDIO_DIR="${AUDIO_DIR:-${ROOT}/gpurun_out/audio_synth}"
+AUDIO_DIR="${AUDIO_DIR:-/tmp/wb200_audio_synth}"          # not under gpurun_out/: that directory is copied back and is capped at 64 MiB
 ONNX_DIR="${ONNX_DIR:-${ROOT}/gpurun_out/onnx_empty}"
 OUT_ROOT="${OUT_ROOT:-${ROOT}/gpurun_out/results/benchmarks}"
 N_SYNTH="${N_SYNTH:-256}"

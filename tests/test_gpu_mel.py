@@ -102,13 +102,14 @@ def test_128_bin_frontend_large_v3(wb, golden_dir):
 
 
 @pytest.mark.parametrize("packed", ["0", "1"])
-@pytest.mark.parametrize("tpc", ["1", "3"])
-def test_kernel_variants_agree(wb, model, monkeypatch, packed, tpc):
-    """FADD2 butterflies or scalar ones, one or several tiles per CTA: same log-mel within the tolerance, on a batch with
-    a tile count that does not divide by the tiles-per-CTA."""
+@pytest.mark.parametrize("ctas", ["1", "3"])
+def test_kernel_variants_agree(wb, model, monkeypatch, packed, ctas):
+    """FADD2 butterflies or scalar ones; a grid of 1 x or 3 x the SM count of persistent CTAs (so a CTA walks several
+    tiles, of different files, with the next tile's PCM streaming in under the current one): same log-mel within the
+    tolerance.  The second file is 4-byte- but not 16-byte-aligned in the packed PCM buffer (the cp.async 4-byte path)."""
     monkeypatch.setenv("WB_MEL_PACKED", packed)
-    monkeypatch.setenv("WB_MEL_TPC", tpc)
-    x = [wb.synth.clip(1, 9, 2.0), wb.synth.clip(2, 9, 0.5)[:7777], wb.synth.clip(3, 9, 1.0)]
+    monkeypatch.setenv("WB_MEL_CTAS_PER_SM", ctas)
+    x = [wb.synth.clip(1, 9, 20.0)[:300001], wb.synth.clip(2, 9, 25.0), wb.synth.clip(3, 9, 1.0)[:7777], wb.synth.clip(4, 9, 30.0)]
     mels, _ = model.log_mel(x)
     for a, c in zip(mels, x):
         assert np.abs(a - mo.log_mel(c)).max() <= TOL

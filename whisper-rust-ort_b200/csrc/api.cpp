@@ -84,6 +84,8 @@ void upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_fil
     CUDA_CHECK(cudaMemcpyAsync(s.frame_off.p, s.h_frame_off.data(), sizeof(int64_t) * (n_files + 1), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(s.tile_off.p, s.h_tile_off.data(), sizeof(int) * (n_files + 1), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(s.chunks.p, s.h_chunks.data(), sizeof(MelChunk) * n_chunks, cudaMemcpyHostToDevice, st));
+    s.n_files_staged = n_files;
+    mel_build_tiles(ctx);
     CUDA_CHECK(cudaEventRecord(e1.e, st));
     CUDA_CHECK(wb_stream_sync(st));
     CUDA_CHECK(cudaEventElapsedTime(&ctx->timing.h2d_ms, e0.e, e1.e));

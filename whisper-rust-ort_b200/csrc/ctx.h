@@ -16,6 +16,10 @@ struct MelTables {                 // POD, copied to the device once
     float fb_w[512];               // non-zero filterbank weights, mel-major runs
     int fb_idx[384];               // start[n_mels], len[n_mels], offset-into-fb_w[n_mels]  (n_mels = 80 or 128)
 };
+struct MelTile {                   // one 24-frame tile of K1a (built on the device by mel_tiles_kernel)
+    int64_t pcm_off, N, raw_base;  // file start in the PCM buffer, file length, first log-mel row of the tile
+    int f0, nf, file, pad;         // first frame of the tile within the file, frames of the file, file index
+};
 struct MelChunk {
     int file;
     int frame_start;               // chunk_pos / 160 (main.rs:895)
@@ -24,6 +28,8 @@ struct MelState {
     DevBuf<float> pcm;
     DevBuf<int64_t> file_off, frame_off;
     DevBuf<int> tile_off, fmax;
+    DevBuf<MelTile> tiles;
+    int n_files_staged = 0;        // files whose offsets are on the device (= n_files once the upload is committed)
     DevBuf<float> raw;             // [total_frames][n_mels] log10 mel, time-major
     DevBuf<MelChunk> chunks;
     DevBuf<float> export_buf;
@@ -151,6 +157,7 @@ void timing_flush(wb_ctx* ctx);
 void mel_build_tables(MelTables& t, int n_mels);
 void mel_set_attrs();
 int64_t mel_n_frames(int64_t n);
+void mel_build_tiles(wb_ctx* ctx);
 void mel_launch_raw(wb_ctx* ctx);
 void mel_launch_chunks(wb_ctx* ctx, int chunk0, int n, void* out);
 void mel_launch_export(wb_ctx* ctx, int file, int64_t frame0, int64_t n_out, float* out_dev);

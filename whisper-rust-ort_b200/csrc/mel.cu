@@ -22,13 +22,14 @@ namespace {
 
 constexpr int FPT = WB_MEL_FPT;               // frames per tile (24: 3000 frames = 125 tiles exactly)
 constexpr int NPAIR = FPT / 2;                // two real frames ride one complex FFT
-constexpr int MEL_THREADS = NPAIR * 20;       // thread = (frame pair, FFT column): every lane of every warp has a column
+constexpr int MEL_THREADS = NPAIR * 20;       // thread = (frame pair, FFT column): every lane has a column (15 half-warps)
 constexpr int SPAN = (FPT - 1) * 160 + 400;   // padded samples a tile touches
-constexpr int SCR = 420;                      // 20 x 21 (padded) complex per FFT
-constexpr int PLD = 419;                      // power-spectrum row pitch (odd: frames land in different banks)
+constexpr int SKEW = 20;                      // sample j sits at j + SKEW*(j/320): pair p's column reads hit bank tid%32
+constexpr int PCM_LD = SPAN + SKEW * ((SPAN + 319) / 320);
+constexpr int SCR = 420;                      // complex per FFT: 20 x 21 (padded) rows; 420 = 4 mod 16 keeps (pair, column) lanes apart
+constexpr int PPL = 205;                      // power-spectrum row pitch: 4 rows apart = 20 mod 32 (six frame groups, six banks)
 constexpr int FBW_MAX = 512;                  // non-zero filterbank weights (<= 2 per FFT bin + slack)
-static_assert(FPT * PLD <= NPAIR * SCR * 2, "power rows live in the FFT scratch");
-static_assert(FPT * 128 <= SPAN, "log-mel tile is staged in the PCM buffer");
+static_assert(FPT * PPL + FPT * (128 + 1) <= 2 * NPAIR * SCR, "power rows and the output tile live in the FFT scratch");
 
 __device__ __forceinline__ float padded_sample(const float* __restrict__ x, int64_t N, int64_t p) {
     // main.rs:419-435: reflect-pad 200 each side (N >= 2), else audio then zeros.
@@ -52,85 +53,118 @@ __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// K1a.  One CTA walks `tiles_per_cta` consecutive tiles of 24 frames.  Per tile: the PCM span is staged once (128-bit
-// loads for interior tiles); thread (pair, column) runs the 20-point column DFT of the pair's packed complex frame,
-// twiddles and scatters it; the same thread then runs the 20-point row DFT; the Hermitian split gives both power
-// spectra; the sparse mel filterbank runs with a warp's lanes on the SAME mel bins of different frame groups (no
-// divergence on the run length, weights broadcast); the [24][n_mels] log10 tile goes out in 128-bit stores.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+// tile -> (file, first frame, where its log-mel rows go): built once per upload, so K1a does one load per tile
+// instead of a binary search (a chain of dependent global loads) in front of every tile.
+__global__ void mel_tiles_kernel(const int64_t* __restrict__ file_off, const int64_t* __restrict__ frame_off,
+                                 const int* __restrict__ tile_off, int n_files, int total_tiles, MelTile* __restrict__ out) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= total_tiles) return;
+    int lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
+    }
+    MelTile t;
+    t.pcm_off = file_off[lo];
+    t.N = file_off[lo + 1] - file_off[lo];
+    t.f0 = (tile - tile_off[lo]) * FPT;
+    t.nf = (int)(frame_off[lo + 1] - frame_off[lo]);
+    t.raw_base = frame_off[lo] + t.f0;
+    t.file = lo;
+    t.pad = 0;
+    out[tile] = t;
+}
+
+// Stage the padded PCM span of a tile (skewed layout).  Interior tiles go through cp.async, so the copy of the NEXT
+// tile runs under the FFTs of the current one; the first / last tile of a file takes the reflecting scalar path.
+__device__ __forceinline__ void stage_pcm(float* s_pcm, const float* __restrict__ pcm, const MelTile& t, int tid) {
+    const int64_t p0 = (int64_t)t.f0 * 160;                      // first padded sample of the tile
+    const float* x = pcm + t.pcm_off;
+    const float* src = x + (p0 - 200);
+    if (p0 >= 200 && p0 - 200 + SPAN <= t.N) {
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int j = tid; j < SPAN / 4; j += MEL_THREADS) cp_async_16(s_pcm + 4 * (j + (SKEW / 4) * (j / 80)), src + 4 * j);
+        } else {
+            for (int j = tid; j < SPAN; j += MEL_THREADS) cp_async_4(s_pcm + j + SKEW * (j / 320), src + j);
+        }
+    } else {
+        for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j + SKEW * (j / 320)] = padded_sample(x, t.N, p0 + j);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+}
+
+// K1a.  Persistent CTAs (three per SM) walk the tiles of 24 frames.  Per tile: thread (pair, column) runs the 20-point
+// column DFT of the pair's packed complex frame out of the staged PCM, twiddles and scatters it; the next tile's PCM
+// starts streaming in; the same thread runs the 20-point row DFT; the Hermitian split gives both power spectra; the
+// sparse mel filterbank runs with a warp's lanes on the same few mel bins of different frame groups (weights
+// broadcast, no divergence on the run length); the [24][n_mels] log10 tile goes out in coalesced stores.
+// Shared-memory bandwidth and latency bound this kernel, so every access pattern is laid out conflict-free (SKEW, SCR,
+// the [k1][column] twiddle table, the rotated spectrum base, PPL, the odd output pitch).
 template <int NM, bool PACKED>
 __global__ void __launch_bounds__(MEL_THREADS, 3)
-logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ file_off,
-                  const int64_t* __restrict__ frame_off, const int* __restrict__ tile_off,
-                  int n_files, int total_tiles, int tiles_per_cta, const MelTables* __restrict__ tab,
-                  float* __restrict__ raw, int* __restrict__ fmax) {
+logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ tiles, int total_tiles,
+                  const MelTables* __restrict__ tab, float* __restrict__ raw, int* __restrict__ fmax) {
+    constexpr int OP = NM + 1;                                 // output tile pitch
     extern __shared__ __align__(16) float smem[];
-    float* s_pcm = smem;                                       // SPAN; later the [FPT][NM] output tile
-    float* s_win = s_pcm + SPAN;                               // 400
-    float2* s_tw = reinterpret_cast<float2*>(s_win + 400);     // 400
-    float* s_fbw = reinterpret_cast<float*>(s_tw + 400);       // FBW_MAX
+    float* s_pcm = smem;                                       // PCM_LD (skewed)
+    float* s_win = s_pcm + PCM_LD;                             // 400
+    float2* s_tw = reinterpret_cast<float2*>(s_win + 400);     // 400: W_400^(k1*col) at [k1*20 + col]
+    float* s_fbw = reinterpret_cast<float*>(s_tw + 400);       // FBW_MAX, pre-scaled by 1/4 (the Hermitian split's 1/2, squared)
     int* s_fbi = reinterpret_cast<int*>(s_fbw + FBW_MAX);      // start[NM], len[NM], off[NM]
-    float2* s_scr = reinterpret_cast<float2*>(s_fbi + 3 * NM); // NPAIR * SCR complex; later FPT power rows
-    float* s_pow = reinterpret_cast<float*>(s_scr);
+    float2* s_scr = reinterpret_cast<float2*>(s_fbi + 3 * NM + ((3 * NM) & 1));   // NPAIR * SCR complex
+    float* s_pow = reinterpret_cast<float*>(s_scr);            // later: FPT power rows of PPL ...
+    float* s_out = s_pow + FPT * PPL;                          // ... and the [FPT][OP] output tile behind them
     __shared__ int s_tmax;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int pair = tid / 20, col = tid - pair * 20;
+    if ((int)blockIdx.x < total_tiles) stage_pcm(s_pcm, pcm, tiles[blockIdx.x], tid);
     for (int i = tid; i < 400; i += MEL_THREADS) {
         s_win[i] = tab->window[i];
-        s_tw[i] = make_float2(tab->tw_re[i], tab->tw_im[i]);
+        const int k = ((i / 20) * (i % 20)) % 400;
+        s_tw[i] = make_float2(tab->tw_re[k], tab->tw_im[k]);
     }
-    for (int i = tid; i < FBW_MAX; i += MEL_THREADS) s_fbw[i] = tab->fb_w[i];
+    for (int i = tid; i < FBW_MAX; i += MEL_THREADS) s_fbw[i] = 0.25f * tab->fb_w[i];
     for (int i = tid; i < 3 * NM; i += MEL_THREADS) s_fbi[i] = tab->fb_idx[i];
     if (tid == 0) s_tmax = (int)0xff800000u;                   // -inf
 
-    const int tile_end = min(total_tiles, (int)(blockIdx.x + 1) * tiles_per_cta);
-    for (int tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
-        // tile -> file (binary search over the tile prefix sums)
-        int lo = 0, hi = n_files - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
-        }
-        const int file = lo;
-        const int64_t N = file_off[file + 1] - file_off[file];
-        const float* x = pcm + file_off[file];
-        const int64_t nf = frame_off[file + 1] - frame_off[file];
-        const int64_t f0 = (int64_t)(tile - tile_off[file]) * FPT;
-        {
-            const int64_t p0 = f0 * 160;                             // first padded sample of the tile
-            const float* src = x + (p0 - 200);
-            const bool interior = p0 >= 200 && p0 - 200 + SPAN <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-            if (interior) {
-                const float4* s4 = reinterpret_cast<const float4*>(src);
-                float4* d4 = reinterpret_cast<float4*>(s_pcm);
-                for (int j = tid; j < SPAN / 4; j += MEL_THREADS) d4[j] = __ldg(s4 + j);
-            } else {
-                for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j] = padded_sample(x, N, p0 + j);
-            }
-        }
-        __syncthreads();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const MelTile cur = tiles[tile];                             // used from the mel phase on: the load hides under step 1
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();                                             // this tile's PCM is in; the previous tile's output is out
 
         float2* scr = s_scr + pair * SCR;
         // ---- step 1: 20-pt DFT over n1 for column n2 = col, twiddle, scatter ----
         {
-            const float* pa = s_pcm + pair * 320;
+            const float* pa = s_pcm + pair * (320 + SKEW) + col;     // sample i of frame A: pa[i + SKEW*(i >= 320)]
             c32 v[20];
 #pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
-                int i = 20 * n1 + col;
-                float w = s_win[i];
-                v[n1] = {pa[i] * w, pa[160 + i] * w};
+                const float w = s_win[20 * n1 + col];
+                v[n1] = {pa[20 * n1 + (n1 >= 16 ? SKEW : 0)] * w, pa[160 + 20 * n1 + (n1 >= 8 ? SKEW : 0)] * w};
             }
             if (PACKED) fft_packed::dft20(v); else fft_scalar::dft20(v);
 #pragma unroll
             for (int k1 = 0; k1 < 20; ++k1) {
-                float2 t = s_tw[col * k1];
+                float2 t = s_tw[k1 * 20 + col];
                 c32 z = fft_scalar::cmul(v[k1], c32{t.x, t.y});
                 scr[k1 * 21 + col] = make_float2(z.x, z.y);
             }
         }
         __syncthreads();
-        // ---- step 2: 20-pt DFT over n2 for row k1 = col ----
+        {   // the PCM buffer is free: start the next tile's copy under the rest of this one
+            const int next = tile + gridDim.x;
+            if (next < total_tiles) stage_pcm(s_pcm, pcm, tiles[next], tid);
+        }
+        // ---- step 2: 20-pt DFT over n2 for row k1 = col; the spectrum of pair p lands at scr_p + (p >> 2), so that
+        //      the twelve pairs sit in twelve different bank pairs for the pair-parallel reads below ----
         {
             c32 v[20];
 #pragma unroll
@@ -140,80 +174,87 @@ logmel_raw_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ fil
             }
             if (PACKED) fft_packed::dft20(v); else fft_scalar::dft20(v);
             __syncthreads();                                         // every row has been read
+            float2* zp = scr + (pair >> 2) + col;
 #pragma unroll
-            for (int k2 = 0; k2 < 20; ++k2) scr[col + 20 * k2] = make_float2(v[k2].x, v[k2].y);
+            for (int k2 = 0; k2 < 20; ++k2) zp[20 * k2] = make_float2(v[k2].x, v[k2].y);
         }
         __syncthreads();
-        // ---- power spectra of both packed frames, k = 0..200 (through registers: the rows overwrite the scratch) ----
+        // ---- power spectra of both packed frames, k = 0..200: 2A = Z[k] + conj Z[400-k], 2iB = Z[k] - conj Z[400-k]
+        //      (through registers: the rows overwrite the scratch; the 1/4 is folded into the filterbank weights) ----
         {
             constexpr int NIT = (NPAIR * 201 + MEL_THREADS - 1) / MEL_THREADS;
             float pa[NIT], pb[NIT];
 #pragma unroll
             for (int r = 0; r < NIT; ++r) {
-                int it = tid + r * MEL_THREADS;
+                const int it = tid + r * MEL_THREADS;
                 if (it < NPAIR * 201) {
-                    int p = it / 201, k = it - p * 201;
-                    float2 z = s_scr[p * SCR + k];
-                    float2 c = s_scr[p * SCR + (k == 0 ? 0 : 400 - k)];
-                    float ar = z.x + c.x, ai = z.y - c.y;          // 2*A[k]
-                    float br = z.x - c.x, bi = z.y + c.y;          // 2i*B[k]
-                    pa[r] = 0.25f * (ar * ar + ai * ai);
-                    pb[r] = 0.25f * (br * br + bi * bi);
+                    const int p = it / 201, k = it - p * 201;
+                    const float2* Z = s_scr + p * SCR + (p >> 2);
+                    const float2 z = Z[k];
+                    const float2 c = Z[k == 0 ? 0 : 400 - k];
+                    const float ar = z.x + c.x, ai = z.y - c.y;
+                    const float br = z.x - c.x, bi = z.y + c.y;
+                    pa[r] = fmaf(ar, ar, ai * ai);
+                    pb[r] = fmaf(br, br, bi * bi);
                 }
             }
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < NIT; ++r) {
-                int it = tid + r * MEL_THREADS;
+                const int it = tid + r * MEL_THREADS;
                 if (it < NPAIR * 201) {
-                    int p = it / 201, k = it - p * 201;
-                    s_pow[(2 * p) * PLD + k] = pa[r];
-                    s_pow[(2 * p + 1) * PLD + k] = pb[r];
+                    const int p = it / 201, k = it - p * 201;
+                    s_pow[(2 * p) * PPL + k] = pa[r];
+                    s_pow[(2 * p + 1) * PPL + k] = pb[r];
                 }
             }
         }
         __syncthreads();
-        // ---- mel filterbank (f32 sum in k order, main.rs:484-490) for 4 frames at a time, log10 -> s_out[frame][NM] ----
-        float* s_out = s_pcm;
+        // ---- mel filterbank (f32 sum in k order, main.rs:484-490) for 4 frames at a time, log10 -> s_out[frame][OP] ----
         float tmax = -INFINITY;
         for (int it = tid; it < NM * (FPT / 4); it += MEL_THREADS) {
             const int m = it / (FPT / 4), fg = it - m * (FPT / 4);
-            const float* p = s_pow + (4 * fg) * PLD + s_fbi[m];
+            const float* p = s_pow + (4 * fg) * PPL + s_fbi[m];
             const float* w = s_fbw + s_fbi[2 * NM + m];
             const int len = s_fbi[NM + m];
             float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
             for (int j = 0; j < len; ++j) {
                 const float wj = w[j];
                 e0 = fmaf(wj, p[j], e0);
-                e1 = fmaf(wj, p[PLD + j], e1);
-                e2 = fmaf(wj, p[2 * PLD + j], e2);
-                e3 = fmaf(wj, p[3 * PLD + j], e3);
+                e1 = fmaf(wj, p[PPL + j], e1);
+                e2 = fmaf(wj, p[2 * PPL + j], e2);
+                e3 = fmaf(wj, p[3 * PPL + j], e3);
             }
             const float e[4] = {e0, e1, e2, e3};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float lv = 0.30102999566398120f * __log2f(fmaxf(e[q], 1e-10f));
-                s_out[(4 * fg + q) * NM + m] = lv;
-                if (f0 + 4 * fg + q < nf) tmax = fmaxf(tmax, lv);
+                s_out[(4 * fg + q) * OP + m] = lv;
+                if (cur.f0 + 4 * fg + q < cur.nf) tmax = fmaxf(tmax, lv);
             }
         }
+        {   // 15 half-warps: reduce inside each (the CTA's last warp has only its lower half)
+            const unsigned mask = tid >= (MEL_THREADS & ~31) ? 0x0000ffffu : 0xffffffffu;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-        if (lane == 0 && tmax > -INFINITY) atomic_max_float(&s_tmax, tmax);
+            for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(mask, tmax, o, 16));
+            if ((tid & 15) == 0 && tmax > -INFINITY) atomic_max_float(&s_tmax, tmax);
+        }
         __syncthreads();
         {
-            const int64_t left = nf - f0;
-            const int n_valid = (int)(left < FPT ? left : FPT) * NM;          // floats, a multiple of 4
-            float4* dst = reinterpret_cast<float4*>(raw + (frame_off[file] + f0) * NM);
-            const float4* src4 = reinterpret_cast<const float4*>(s_out);
-            for (int j = tid; j < n_valid / 4; j += MEL_THREADS) dst[j] = src4[j];
+            const int left = cur.nf - cur.f0;
+            const int n_valid = (left < FPT ? left : FPT) * NM;
+            float* dst = raw + cur.raw_base * NM;
+            for (int j = tid; j < n_valid; j += MEL_THREADS) {
+                const int f = j / NM;
+                dst[j] = s_out[j + f];                               // f*OP + (j - f*NM)
+            }
         }
         if (tid == 0) {
             const int m = s_tmax;
-            if (m != (int)0xff800000u) atomic_max_float(fmax + file, __int_as_float(m));
+            if (m != (int)0xff800000u) atomic_max_float(fmax + cur.file, __int_as_float(m));
             s_tmax = (int)0xff800000u;
         }
-        __syncthreads();                                             // s_out (= s_pcm) is free for the next tile
+        // the barrier at the top of the next tile (after its PCM wait) frees s_out / s_pow / s_tmax
     }
 }
 
@@ -303,7 +344,7 @@ __global__ void mel_transpose_in_kernel(const float* __restrict__ in, T* __restr
     }
 }
 
-constexpr size_t mel_smem(int nm) { return sizeof(float) * (size_t)(SPAN + 400 + 800 + FBW_MAX + 3 * nm + 2 * NPAIR * SCR); }
+constexpr size_t mel_smem(int nm) { return sizeof(float) * (size_t)(PCM_LD + 400 + 800 + FBW_MAX + 3 * nm + ((3 * nm) & 1) + 2 * NPAIR * SCR); }
 
 }  // namespace
 
@@ -388,17 +429,24 @@ void mel_set_attrs() {
     CUDA_CHECK(cudaFuncSetAttribute(logmel_raw_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel_smem(128)));
 }
 
+void mel_build_tiles(wb_ctx* ctx) {
+    MelState& s = ctx->mel;
+    s.tiles.reserve((size_t)s.total_tiles);
+    mel_tiles_kernel<<<ceil_div(s.total_tiles, 256), 256, 0, ctx->stream>>>(s.file_off.p, s.frame_off.p, s.tile_off.p, s.n_files_staged,
+                                                                            s.total_tiles, s.tiles.p);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void mel_launch_raw(wb_ctx* ctx) {
     MelState& s = ctx->mel;
     fill_int_kernel<<<ceil_div(s.n_files, 256), 256, 0, ctx->stream>>>(s.fmax.p, s.n_files, (int)0xff800000u);   // -inf as int bits
-    // a CTA keeps its tables for `tpc` consecutive tiles; small uploads stay one tile per CTA so they still fill the SMs
-    int tpc = s.total_tiles >= 8 * 3 * ctx->sm_count ? 4 : (s.total_tiles >= 2 * 3 * ctx->sm_count ? 2 : 1);
-    if (const char* e = getenv("WB_MEL_TPC")) tpc = std::max(1, atoi(e));
-    const int grid = ceil_div(s.total_tiles, tpc);
+    int per_sm = 3;                                         // resident CTAs per SM (registers and shared memory both allow 3)
+    if (const char* e = getenv("WB_MEL_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+    const int grid = std::min(s.total_tiles, per_sm * ctx->sm_count);
     bool packed = true;                                     // FADD2 butterflies
     if (const char* e = getenv("WB_MEL_PACKED")) packed = atoi(e) != 0;
 #define WB_MEL_RAW(NM, PK) logmel_raw_kernel<NM, PK><<<grid, MEL_THREADS, mel_smem(NM), ctx->stream>>>( \
-        s.pcm.p, s.file_off.p, s.frame_off.p, s.tile_off.p, s.n_files, s.total_tiles, tpc, ctx->mel_tables_dev, s.raw.p, s.fmax.p)
+        s.pcm.p, s.tiles.p, s.total_tiles, ctx->mel_tables_dev, s.raw.p, s.fmax.p)
     if (ctx->cfg.n_mels == 128) { if (packed) WB_MEL_RAW(128, true); else WB_MEL_RAW(128, false); }
     else { if (packed) WB_MEL_RAW(80, true); else WB_MEL_RAW(80, false); }
 #undef WB_MEL_RAW
@@ -444,7 +492,7 @@ void mel_launch_transpose_in(wb_ctx* ctx, const float* in_dev, void* out, int B)
 // CPU emulation of the kernel's FFT data flow (same mel_math.h code) for the no-GPU unit test.
 extern "C" int wb_selftest_fft400(const float* re, const float* im, float* out_re, float* out_im) {
     using namespace fft_scalar;
-    std::vector<c32> scr(SCR), X(400);
+    std::vector<c32> scr(420), X(400);
     for (int n2 = 0; n2 < 20; ++n2) {
         c32 v[20];
         for (int n1 = 0; n1 < 20; ++n1) v[n1] = {re[20 * n1 + n2], im[20 * n1 + n2]};
