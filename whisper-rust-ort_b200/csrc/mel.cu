@@ -27,9 +27,12 @@ constexpr int SPAN = (FPT - 1) * 160 + 400;   // padded samples a tile touches
 constexpr int SKEW = 20;                      // sample j sits at j + SKEW*(j/320): pair p's column reads hit bank tid%32
 constexpr int PCM_LD = SPAN + SKEW * ((SPAN + 319) / 320);
 constexpr int SCR = 420;                      // complex per FFT: 20 x 21 (padded) rows; 420 = 4 mod 16 keeps (pair, column) lanes apart
-constexpr int PPL = 205;                      // power-spectrum row pitch: 4 rows apart = 20 mod 32 (six frame groups, six banks)
+constexpr int PPL = 230;                      // power-spectrum row pitch = 6 mod 32: the six frame groups of a warp sit 6 banks apart
 constexpr int FBW_MAX = 512;                  // non-zero filterbank weights (<= 2 per FFT bin + slack)
-static_assert(FPT * PPL + FPT * (128 + 1) <= 2 * NPAIR * SCR, "power rows and the output tile live in the FFT scratch");
+static_assert(FPT * PPL + FPT * (128 + 6) <= 2 * NPAIR * SCR, "power rows and the output tile live in the FFT scratch");
+// frame f of a tile = 4*fg + q (frame group fg, lane-parallel; q = 0..3, register-parallel) lives in row fg + 6*q of the
+// power and output tiles: the lanes of a warp then walk consecutive rows, 6 banks apart, each up to 6 mel bins wide
+__device__ __forceinline__ int tile_row(int f) { return (f >> 2) + 6 * (f & 3); }
 
 __device__ __forceinline__ float padded_sample(const float* __restrict__ x, int64_t N, int64_t p) {
     // main.rs:419-435: reflect-pad 200 each side (N >= 2), else audio then zeros.
@@ -53,9 +56,6 @@ __device__ __forceinline__ void atomic_max_float(int* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
-}
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
@@ -82,22 +82,45 @@ __global__ void mel_tiles_kernel(const int64_t* __restrict__ file_off, const int
     out[tile] = t;
 }
 
-// Stage the padded PCM span of a tile (skewed layout).  Interior tiles go through cp.async, so the copy of the NEXT
-// tile runs under the FFTs of the current one; the first / last tile of a file takes the reflecting scalar path.
-__device__ __forceinline__ void stage_pcm(float* s_pcm, const float* __restrict__ pcm, const MelTile& t, int tid) {
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 100000;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
+// Stage the padded PCM span of a tile (skewed layout: 320-sample regions, 340 floats apart) while the previous
+// tile's FFTs run.  Interior 16-byte-aligned tiles (all but the first / last of a file) are 13 bulk copies issued by
+// one thread and written by the TMA unit (no load/store-unit wavefronts; completion on `bar`); interior tiles of a
+// file that starts off a 16-byte boundary use 4-byte cp.async; file edges take the reflecting scalar path.
+// Returns true when the data arrives on the mbarrier (uniform over the CTA).
+__device__ __forceinline__ bool stage_pcm(float* s_pcm, uint32_t bar, const float* __restrict__ pcm, const MelTile& t, int tid) {
     const int64_t p0 = (int64_t)t.f0 * 160;                      // first padded sample of the tile
     const float* x = pcm + t.pcm_off;
     const float* src = x + (p0 - 200);
     if (p0 >= 200 && p0 - 200 + SPAN <= t.N) {
         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            for (int j = tid; j < SPAN / 4; j += MEL_THREADS) cp_async_16(s_pcm + 4 * (j + (SKEW / 4) * (j / 80)), src + 4 * j);
-        } else {
-            for (int j = tid; j < SPAN; j += MEL_THREADS) cp_async_4(s_pcm + j + SKEW * (j / 320), src + j);
+            if (tid == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SPAN * 4)) : "memory");
+#pragma unroll
+                for (int r = 0; r < (SPAN + 319) / 320; ++r) {
+                    const uint32_t bytes = (uint32_t)((SPAN - 320 * r < 320 ? SPAN - 320 * r : 320) * 4);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_addr(s_pcm + r * (320 + SKEW))), "l"(src + 320 * r), "r"(bytes), "r"(bar) : "memory");
+                }
+            }
+            return true;
         }
+        for (int j = tid; j < SPAN; j += MEL_THREADS) cp_async_4(s_pcm + j + SKEW * (j / 320), src + j);
     } else {
         for (int j = tid; j < SPAN; j += MEL_THREADS) s_pcm[j + SKEW * (j / 320)] = padded_sample(x, t.N, p0 + j);
     }
     asm volatile("cp.async.commit_group;\n" ::);
+    return false;
 }
 
 // K1a.  Persistent CTAs (three per SM) walk the tiles of 24 frames.  Per tile: thread (pair, column) runs the 20-point
@@ -111,25 +134,37 @@ template <int NM, bool PACKED>
 __global__ void __launch_bounds__(MEL_THREADS, 3)
 logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ tiles, int total_tiles,
                   const MelTables* __restrict__ tab, float* __restrict__ raw, int* __restrict__ fmax) {
-    constexpr int OP = NM + 1;                                 // output tile pitch
+    constexpr int OP = NM + (6 - NM % 32 + 32) % 32;           // output tile pitch = 6 mod 32 (80 -> 102, 128 -> 134)
+    static_assert(OP % 32 == 6 && FPT * PPL + FPT * OP <= 2 * NPAIR * SCR, "output tile");
     extern __shared__ __align__(16) float smem[];
     float* s_pcm = smem;                                       // PCM_LD (skewed)
     float* s_win = s_pcm + PCM_LD;                             // 400
-    float2* s_tw = reinterpret_cast<float2*>(s_win + 400);     // 400: W_400^(k1*col) at [k1*20 + col]
-    float* s_fbw = reinterpret_cast<float*>(s_tw + 400);       // FBW_MAX, pre-scaled by 1/4 (the Hermitian split's 1/2, squared)
+    float* s_twr = s_win + 400;                                // 400 + 400: W_400^(k1*col) at [k1*20 + col], re and im planes (two
+    float* s_twi = s_twr + 400;                                //   32-bit loads: lanes of different pairs broadcast, columns never collide)
+    float* s_fbw = s_twi + 400;                                // FBW_MAX, pre-scaled by 1/4 (the Hermitian split's 1/2, squared)
     int* s_fbi = reinterpret_cast<int*>(s_fbw + FBW_MAX);      // start[NM], len[NM], off[NM]
     float2* s_scr = reinterpret_cast<float2*>(s_fbi + 3 * NM + ((3 * NM) & 1));   // NPAIR * SCR complex
     float* s_pow = reinterpret_cast<float*>(s_scr);            // later: FPT power rows of PPL ...
     float* s_out = s_pow + FPT * PPL;                          // ... and the [FPT][OP] output tile behind them
     __shared__ int s_tmax;
+    __shared__ __align__(8) uint64_t s_bar;                    // PCM of a bulk-copied tile has landed
 
     const int tid = threadIdx.x;
     const int pair = tid / 20, col = tid - pair * 20;
-    if ((int)blockIdx.x < total_tiles) stage_pcm(s_pcm, pcm, tiles[blockIdx.x], tid);
+    const uint32_t bar = smem_addr(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t bulk_phase = 0;                                   // parity of the next bulk completion
+    bool on_bar = false;                                       // the tile at the top of the loop arrives on the mbarrier
+    if ((int)blockIdx.x < total_tiles) on_bar = stage_pcm(s_pcm, bar, pcm, tiles[blockIdx.x], tid);
     for (int i = tid; i < 400; i += MEL_THREADS) {
         s_win[i] = tab->window[i];
         const int k = ((i / 20) * (i % 20)) % 400;
-        s_tw[i] = make_float2(tab->tw_re[k], tab->tw_im[k]);
+        s_twr[i] = tab->tw_re[k];
+        s_twi[i] = tab->tw_im[k];
     }
     for (int i = tid; i < FBW_MAX; i += MEL_THREADS) s_fbw[i] = 0.25f * tab->fb_w[i];
     for (int i = tid; i < 3 * NM; i += MEL_THREADS) s_fbi[i] = tab->fb_idx[i];
@@ -137,7 +172,13 @@ logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ til
 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const MelTile cur = tiles[tile];                             // used from the mel phase on: the load hides under step 1
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        if (on_bar) {
+            int spins = 0;
+            while (!mbar_try(bar, bulk_phase)) if (++spins > 20000) __trap();      // bounded: a bug must not hang the GPU
+            bulk_phase ^= 1u;
+        } else {
+            asm volatile("cp.async.wait_all;\n" ::: "memory");
+        }
         __syncthreads();                                             // this tile's PCM is in; the previous tile's output is out
 
         float2* scr = s_scr + pair * SCR;
@@ -153,15 +194,14 @@ logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ til
             if (PACKED) fft_packed::dft20(v); else fft_scalar::dft20(v);
 #pragma unroll
             for (int k1 = 0; k1 < 20; ++k1) {
-                float2 t = s_tw[k1 * 20 + col];
-                c32 z = fft_scalar::cmul(v[k1], c32{t.x, t.y});
+                c32 z = fft_scalar::cmul(v[k1], c32{s_twr[k1 * 20 + col], s_twi[k1 * 20 + col]});
                 scr[k1 * 21 + col] = make_float2(z.x, z.y);
             }
         }
         __syncthreads();
         {   // the PCM buffer is free: start the next tile's copy under the rest of this one
             const int next = tile + gridDim.x;
-            if (next < total_tiles) stage_pcm(s_pcm, pcm, tiles[next], tid);
+            on_bar = next < total_tiles && stage_pcm(s_pcm, bar, pcm, tiles[next], tid);
         }
         // ---- step 2: 20-pt DFT over n2 for row k1 = col; the spectrum of pair p lands at scr_p + (p >> 2), so that
         //      the twelve pairs sit in twelve different bank pairs for the pair-parallel reads below ----
@@ -204,8 +244,8 @@ logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ til
                 const int it = tid + r * MEL_THREADS;
                 if (it < NPAIR * 201) {
                     const int p = it / 201, k = it - p * 201;
-                    s_pow[(2 * p) * PPL + k] = pa[r];
-                    s_pow[(2 * p + 1) * PPL + k] = pb[r];
+                    s_pow[tile_row(2 * p) * PPL + k] = pa[r];
+                    s_pow[tile_row(2 * p + 1) * PPL + k] = pb[r];
                 }
             }
         }
@@ -214,22 +254,22 @@ logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ til
         float tmax = -INFINITY;
         for (int it = tid; it < NM * (FPT / 4); it += MEL_THREADS) {
             const int m = it / (FPT / 4), fg = it - m * (FPT / 4);
-            const float* p = s_pow + (4 * fg) * PPL + s_fbi[m];
+            const float* p = s_pow + fg * PPL + s_fbi[m];              // rows fg, fg + 6, fg + 12, fg + 18 = frames 4 fg + q
             const float* w = s_fbw + s_fbi[2 * NM + m];
             const int len = s_fbi[NM + m];
             float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
             for (int j = 0; j < len; ++j) {
                 const float wj = w[j];
                 e0 = fmaf(wj, p[j], e0);
-                e1 = fmaf(wj, p[PPL + j], e1);
-                e2 = fmaf(wj, p[2 * PPL + j], e2);
-                e3 = fmaf(wj, p[3 * PPL + j], e3);
+                e1 = fmaf(wj, p[6 * PPL + j], e1);
+                e2 = fmaf(wj, p[12 * PPL + j], e2);
+                e3 = fmaf(wj, p[18 * PPL + j], e3);
             }
             const float e[4] = {e0, e1, e2, e3};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float lv = 0.30102999566398120f * __log2f(fmaxf(e[q], 1e-10f));
-                s_out[(4 * fg + q) * OP + m] = lv;
+                s_out[(fg + 6 * q) * OP + m] = lv;
                 if (cur.f0 + 4 * fg + q < cur.nf) tmax = fmaxf(tmax, lv);
             }
         }
@@ -246,7 +286,7 @@ logmel_raw_kernel(const float* __restrict__ pcm, const MelTile* __restrict__ til
             float* dst = raw + cur.raw_base * NM;
             for (int j = tid; j < n_valid; j += MEL_THREADS) {
                 const int f = j / NM;
-                dst[j] = s_out[j + f];                               // f*OP + (j - f*NM)
+                dst[j] = s_out[tile_row(f) * OP + (j - f * NM)];
             }
         }
         if (tid == 0) {
