@@ -93,7 +93,8 @@ def test_eot_stops_a_sequence_and_max_new_quirks(base, oracle, clips):
 
 def test_early_exit_when_every_sequence_hit_eot(base, oracle, clips):
     """The device loop stops at a segment boundary once all sequences emitted EOT (the host looks at one
-    mapped int per 16 tokens, never per token); outputs stay those of main.rs:753-829."""
+    mapped int per 16 tokens, never per token, and with one segment of look-ahead so the GPU never idles on the
+    poll: one surplus segment may run); outputs stay those of main.rs:753-829."""
     _, mel = clips
     enc = base.encode(mel[:1])
     prompt = [50258, 50259, 50359, 50363]
@@ -102,7 +103,7 @@ def test_early_exit_when_every_sequence_hit_eot(base, oracle, clips):
     first = free[0][len(prompt)]
     got = base.greedy_decode(1, prompt, 40, first)                  # "eot" = the first generated token
     assert got == oracle.greedy(enc, prompt, 40, first) == [prompt + [first]]
-    assert base.timing()["decode_steps"] == len(prompt) - 1 + 16     # prefix + one segment, then stop
+    assert base.timing()["decode_steps"] == len(prompt) - 1 + 32     # prefix + the segment with the EOT + one of look-ahead
     # a batch only stops when ALL of its sequences are done
     base.encode(mel)
     both = base.greedy_decode(2, prompt, 40, first)

@@ -66,8 +66,6 @@ def test_large_v3_widths_bf16_within_tolerance(wb, oracle, mel):
     clear = (top2[..., 1] - top2[..., 0]) > 0.1
     got = np.array([t[len(prompt):] for t in ft])
     assert np.all(got[clear] == forced[clear])
-    with pytest.raises(wb.WbError, match="80-bin"):
-        m.log_mel([np.zeros(16000, np.float32)])          # the reference has no 128-bin frontend
     m.close()
 
 
