@@ -6,8 +6,9 @@ whisper-base hot path (log-mel -> encoder -> 128-token KV-cache greedy decode) a
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32] [--in-flight S]
 
 One "step" = one pass of the hot path over one batch of 32 synthetic 30 s clips per GPU; S steps
-(default 4) are in flight per GPU at a time, each in its own context/stream, because one decode is a
-chain of small dependent kernels that leaves most SMs idle (`single_batch_in_flight` reports S = 1).
+(default 8) are in flight per GPU at a time, each in its own context/stream, because one decode is a
+chain of small dependent kernels that leaves most SMs idle (`single_batch_in_flight` reports S = 1; one B200:
+S = 1 / 2 / 4 / 6 / 8 -> 18.1 / 26.6 / 32.6 / 34.6 / 35.8 k audio-s/s, profiles/r2_inflight.json).
 `value`  : whole-job audio-s/s with the PCM already resident in HBM (device-timed, max over ranks).
 `e2e`    : same metric through the reference-facing C ABI call wb_transcribe_batch with HOST
            (pinned) PCM buffers — H2D of the PCM and D2H of the token ids inside the timed region.
@@ -42,8 +43,8 @@ EOT = 50257
 MAX_NEW = 128
 CLIP_S = 30.0
 BATCH = 32
-# dram bytes per cross_attn_kernel launch at B=32 from the committed ncu capture (profiles/r1_cross_attn_v3_raw.csv: 98.40 MB read + 4.25 MB write)
-NCU_TRAFFIC_BYTES = {"bf16": 102.65e6, "fp32": None}      # refreshed from profiles/r2_cross_attn_raw.csv when that capture exists
+# dram bytes per cross_attn_kernel launch at B=32 from the committed ncu capture (profiles/r2_cross_attn_raw.csv: 98.39 MB read + 4.15 MB write)
+NCU_TRAFFIC_BYTES = {"bf16": 102.55e6, "fp32": None}
 METRIC = "audio-sec/sec (RTFx) whisper-base"
 UNIT = "audio-s/s"
 
@@ -127,16 +128,49 @@ def stage_rooflines(tm, B, esz, hbm_peak, tc_peak, arch="base"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML in-process (a query costs
+    microseconds, so a 0.4 s timed region still gets a few dozen samples); `nvidia-smi` polling is the fall-back where
+    the NVML binding is missing (one call takes ~0.2 s)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int, enabled: bool = True, interval: float = 0.2):
-        # rank 0 only: nvidia-smi takes driver locks, and 8 ranks polling it stall each other's launches
+    def __init__(self, index: int, enabled: bool = True, interval: float = 0.02):
+        # rank 0 only: the driver locks these queries take are shared by all ranks of a box
         self.index, self.rows, self.stop, self.enabled, self.interval = index, [], threading.Event(), enabled, interval
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.source = "nvml"
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES renumbers CUDA devices; NVML does not: go through the PCI bus id of the CUDA device
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+            dev = torch.cuda.get_device_properties(self.index).pci_device_id
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def _run(self):
+        try:
+            nv, h = self._nvml_handle()
+            bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+                self.stop.wait(self.interval)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -161,11 +195,10 @@ class ClockSampler:
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
         mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 # ---------------- CPU oracle port (cpu_baseline / reference arm) ----------------
@@ -339,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
         toks[i] = ctxs[i].transcribe_resident(B, PROMPT, MAX_NEW, EOT, sup, bsup)
     run_workers(resident_step, args.warmup * S)
     barrier()
-    with ClockSampler(local_rank, enabled=(rank == 0), interval=0.05 if world == 1 else 0.2) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0), interval=0.02 if world == 1 else 0.05) as clk:
         m.mark(0)
         t0 = time.perf_counter()
         lat_res = run_workers(resident_step, args.steps)
@@ -450,7 +483,7 @@ def main():
     ap.add_argument("--arch", default="base", choices=sorted(ARCHS), help="base = configs[3] (the headline); large-v3 = configs[4] "
                     "(128 mel bins, 32+32 layers, d=1280; batch 16 per GPU; no CPU arm: one clip costs minutes on the host)")
     ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("WB_BENCH_IN_FLIGHT", "4")),
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("WB_BENCH_IN_FLIGHT", "8")),
                     help="independent batches of --batch clips in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[1] / configs[2] side measurements")

@@ -466,7 +466,21 @@ void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, si
         Pcm a0;
         CK(wb_host_load_audio_16k_mono(join(args.audio_dir, J.files[0]).c_str(), &a0.p, &a0.n, &a0.dur));
         WB_REQUIRE(a0.n > 0, WB_EINVAL, "Empty audio");
-        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, J.mc.max_batch, a0.p, {0, a0.n}, args, J.tok, J.gen, t); }
+        // main.rs:1131-1152 warms up on the first file.  With file groups, the warm-up runs that file as many times as a
+        // group has files, so the decode graphs of the real batch shape are built here and not inside the first group.
+        const int64_t w_chunk = (int64_t)std::lround(args.chunk_length_s * 16000.0f), w_ov = (int64_t)std::lround(args.overlap_s * 16000.0f);
+        const int n_ch0 = std::max(1, wb_host_chunk_starts(a0.n, w_chunk, std::max<int64_t>(w_chunk > w_ov ? w_chunk - w_ov : 0, 1), nullptr, 0));
+        const size_t copies = std::max<size_t>(1, std::min<size_t>({args.file_batch, (size_t)J.mc.max_batch, (size_t)(J.mc.max_chunks / n_ch0)}));
+        std::vector<int64_t> woffs(copies + 1, 0);
+        for (size_t i = 0; i < copies; ++i) woffs[i + 1] = woffs[i] + a0.n;
+        PinnedPcm wbuf;
+        const float* wp = a0.p;
+        if (copies > 1) {
+            wbuf.reserve(device, (size_t)woffs.back());
+            for (size_t i = 0; i < copies; ++i) std::memcpy(wbuf.p + woffs[i], a0.p, sizeof(float) * (size_t)a0.n);
+            wp = wbuf.p;
+        }
+        for (size_t i = 0; i < args.warmup; ++i) { Timing t; transcribe(ctx, J.mc.max_batch, wp, woffs, args, J.tok, J.gen, t); }
         TRACE("worker on gpu %d: warm-up done", device);
     }
     for (int cur = 0;; cur ^= 1) {
