@@ -87,6 +87,41 @@ def inflight(argv):
     print(json.dumps(out, indent=1))
 
 
+def stages(argv):
+    """S contexts in flight, each looping ONE stage (decode only / encoder only): which stage saturates the GPU, and where?"""
+    counts = [int(x) for x in argv] or [1, 8]
+    B = 32
+    pcm = wb200.synth.fast_batch(B, seed=1)
+    out = {}
+    ctxs = [make(B) for _ in range(max(counts))]
+    for c in ctxs:
+        c.upload_pcm(pcm)
+        c.run_log_mel()
+        c.encode(None, 0, B, want_hidden=False)
+        c.greedy_decode(B, PROMPT, 128, EOT)
+    for stage in ("decode", "encode"):
+        for S in counts:
+            n = 6 if stage == "decode" else 30
+            def work(i):
+                for _ in range(n):
+                    if stage == "decode":
+                        ctxs[i].greedy_decode(B, PROMPT, 128, EOT)
+                    else:
+                        ctxs[i].encode(None, 0, B, want_hidden=False)
+                ctxs[i].timing()          # waits for the last enqueued stage
+            th = [threading.Thread(target=work, args=(i,)) for i in range(S)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            dt = time.perf_counter() - t0
+            out[f"{stage} S={S}"] = {"ms_per_batch": 1000 * dt / (S * n)}
+    print(json.dumps(out, indent=1))
+    for c in ctxs:
+        c.close()
+
+
 def kernels(argv):
     B = 32
     m = make(B)
@@ -137,5 +172,42 @@ def mel(argv):
     print(json.dumps(out, indent=1))
 
 
+def xconc(argv):
+    """cross_attn / vocab_proj replayed from S contexts at once: does the aggregate stream faster than one kernel alone?"""
+    counts = [int(x) for x in argv] or [1, 2, 4, 8]
+    B = 32
+    pcm = wb200.synth.fast_batch(B, seed=1)
+    out = {}
+    ctxs = [make(B) for _ in range(max(counts))]
+    for c in ctxs:
+        c.upload_pcm(pcm)
+        c.run_log_mel()
+        c.encode(None, 0, B, want_hidden=False)
+        c.greedy_decode(B, PROMPT, 8, EOT)
+    for pdl in ("0", "1"):
+        if pdl == "1":
+            os.environ["WB_BENCH_PDL"] = "1"
+        else:
+            os.environ.pop("WB_BENCH_PDL", None)
+        for kern in ("cross_attn", "vocab_proj"):
+            for S in counts:
+                res = [None] * S
+                def work(i):
+                    res[i] = ctxs[i].bench_kernel(kern, B, 300)
+                th = [threading.Thread(target=work, args=(i,)) for i in range(S)]
+                t0 = time.perf_counter()
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                dt = time.perf_counter() - t0
+                tot = sum(r[1] for r in res) * 300
+                out[f"{kern} pdl={pdl} S={S}"] = {"aggregate_GBps_wall": tot / dt / 1e9, "ms_per_launch_per_ctx": [round(r[0], 5) for r in res],
+                                                 "aggregate_GBps_events": sum(r[1] / r[0] / 1e6 for r in res)}
+    print(json.dumps(out, indent=1))
+    for c in ctxs:
+        c.close()
+
+
 if __name__ == "__main__":
-    {"decode": decode, "inflight": inflight, "kernels": kernels, "mel": mel}[sys.argv[1]](sys.argv[2:])
+    {"decode": decode, "inflight": inflight, "kernels": kernels, "mel": mel, "xconc": xconc, "stages": stages}[sys.argv[1]](sys.argv[2:])

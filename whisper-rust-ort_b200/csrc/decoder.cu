@@ -296,12 +296,31 @@ skinny_gemm_kernel(const float* __restrict__ X, int B, int K, const WT* __restri
 // loading the K and the V row of UN keys together (raw 128-bit registers, converted on use), so a
 // CTA exposes Tk / (groups * UN) memory round trips instead of two passes over the keys.
 // Groups merge by shuffles, warps through shared memory.
+// 128-bit load with an L2 eviction policy: the cross-attention K/V stream (0.6 GB per step and batch, read once per step)
+// is marked evict-first so that it does not push the decoder weights (97 MB, re-read by every step of every batch in
+// flight) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_hint(const void* p, uint64_t pol) {
+    uint4 v;
+    asm("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
 template <typename KT> struct RowRaw;
 template <> struct RowRaw<float> {
     static constexpr int DPL = 8;
     uint4 a, b;
     // p points at the lane's first segment; the second segment lives 32 dims further (next 128-byte line)
     __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const uint4*>(p); b = *reinterpret_cast<const uint4*>(p + 32); }
+    __device__ __forceinline__ void load(const float* p, uint64_t pol) { a = ldg_hint(p, pol); b = ldg_hint(p + 32, pol); }
     __device__ __forceinline__ void get(float (&f)[8]) const {
         f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
         f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
@@ -311,6 +330,7 @@ template <> struct RowRaw<bf16> {
     static constexpr int DPL = 16;
     uint4 a, b;
     __device__ __forceinline__ void load(const bf16* p) { a = *reinterpret_cast<const uint4*>(p); b = *reinterpret_cast<const uint4*>(p + 32); }
+    __device__ __forceinline__ void load(const bf16* p, uint64_t pol) { a = ldg_hint(p, pol); b = ldg_hint(p + 32, pol); }
     __device__ __forceinline__ void get(float (&f)[16]) const {
         const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -336,11 +356,12 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
 
     // the first K/V rows do not depend on the predecessor kernel: get them moving before the sync
     RowRaw<KT> kr[UN], vr[UN];
+    const uint64_t pol = l2_evict_first_policy();
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
         const int j = min(k_lo + grp + u * NG, k_hi - 1);
-        kr[u].load(kbase + (size_t)j * 2 * d);
-        vr[u].load(vbase + (size_t)j * 2 * d);
+        kr[u].load(kbase + (size_t)j * 2 * d, pol);
+        vr[u].load(vbase + (size_t)j * 2 * d, pol);
     }
     pdl_sync();
     float qv[DPL];
@@ -371,7 +392,7 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
         const int jn = j0 + NG * UN;
         if (jn < k_hi) {
 #pragma unroll
-            for (int u = 0; u < UN; ++u) kr[u].load(kbase + (size_t)min(jn + u * NG, k_hi - 1) * 2 * d);
+            for (int u = 0; u < UN; ++u) kr[u].load(kbase + (size_t)min(jn + u * NG, k_hi - 1) * 2 * d, pol);
         }
         const float scale = (mx == -INFINITY) ? 1.f : expf(m - mx);      // m = -inf on the first round -> 0
         l *= scale;
@@ -389,7 +410,7 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
         m = mx;
         if (jn < k_hi) {
 #pragma unroll
-            for (int u = 0; u < UN; ++u) vr[u].load(vbase + (size_t)min(jn + u * NG, k_hi - 1) * 2 * d);
+            for (int u = 0; u < UN; ++u) vr[u].load(vbase + (size_t)min(jn + u * NG, k_hi - 1) * 2 * d, pol);
         }
     }
     // merge lane groups inside the warp (l is replicated over the LPR lanes of a group)
@@ -428,21 +449,26 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
 // with the same single-pass lane-group scheme as the cross-attention (32 bytes of a row per lane, 4 keys
 // in flight per group), so its cost stays one memory round trip as the cache grows (the first version
 // walked the keys one warp at a time: 5.8 us at s = 4 but 27 us averaged over a 128-token decode).
-template <typename KT>
-__global__ void __launch_bounds__(256)
+// NW warps per (b,h).  8 warps cover 256 keys per round trip (lowest latency for one batch alone); 2 warps cover 64 and
+// take 1/4 of the registers and SM slots: with several batches in flight the GPU is bound by the SM-time its kernels
+// hold (a 256-thread CTA idling through a memory round trip blocks other contexts' CTAs), so the narrow shape wins there.
+template <typename KT, int NW>
+__global__ void __launch_bounds__(NW * 32)
 self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, KT* __restrict__ cache,
                  float* __restrict__ out, int d, int T_max) {
-    constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = 256 / LPR, UN = 4, HPL = DPL / 2;
-    __shared__ float s_m[8], s_l[8];
-    __shared__ float s_acc[8][64];
+    constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = NW * 32 / LPR, UN = 4, HPL = DPL / 2;
+    __shared__ float s_m[NW], s_l[NW];
+    __shared__ float s_acc[NW][64];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / LPR, li = tid % LPR;
     pdl_sync();
     const int s = state[0], nk = s + 1;
     const float* row = qkv + (size_t)b * 3 * d;
     KT* kv = cache + (size_t)b * T_max * 2 * d;
-    if (tid < 64) store1(kv + (size_t)s * 2 * d + h * 64 + tid, row[d + h * 64 + tid]);
-    else if (tid < 128) store1(kv + (size_t)s * 2 * d + d + h * 64 + (tid - 64), row[2 * d + h * 64 + (tid - 64)]);
+    for (int i = tid; i < 128; i += NW * 32) {            // this step's k (i < 64) and v rows of the head
+        const int kvsel = i >> 6, c = i & 63;
+        store1(kv + (size_t)s * 2 * d + kvsel * d + h * 64 + c, row[(1 + kvsel) * d + h * 64 + c]);
+    }
     float qv[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) qv[i] = row[h * 64 + (i < HPL ? li * HPL + i : 32 + li * HPL + (i - HPL))] * 0.125f;
@@ -507,12 +533,12 @@ self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, K
         if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
     }
     __syncthreads();
-    if (tid < 64) {                                     // merge the 8 warps: thread <-> output dim
+    if (tid < 64) {                                     // merge the warps: thread <-> output dim
         float mt = -INFINITY, my = 0.f, lt = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) mt = fmaxf(mt, s_m[w]);
+        for (int w = 0; w < NW; ++w) mt = fmaxf(mt, s_m[w]);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < NW; ++w) {
             const float wgt = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - mt);
             my = fmaf(s_acc[w][tid], wgt, my);
             lt = fmaf(s_l[w], wgt, lt);
@@ -644,21 +670,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // one cross-attention launch over B sequences
 template <typename WT>
-void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, int H, int B, int d, int Tk) {
+void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, int H, int B, int d, int Tk, bool four_warps = false) {
     // 8-warp CTAs hold 2 per SM (register file), 4-warp CTAs 4 per SM.  When the (b,h) pairs overflow one wave of
     // 8-warp CTAs but fit one wave of 4-warp CTAs, the smaller shape keeps every pair streaming at once instead of
     // leaving a few CTAs to run alone at the end (large-v3 widths at batch 16: 320 pairs on 148 SMs).
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const int units = H * B;
-    if (units > 2 * sms && units <= 4 * sms)
+    if (four_warps || (units > 2 * sms && units <= 4 * sms))
         launch_k(cross_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, q, ckv, att, d, Tk);
     else
         launch_k(cross_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, q, ckv, att, d, Tk);
 }
 
 constexpr int MM_THREADS = 256;
-
 // One skinny GEMM executed by CTA `cta` of the `ncta` CTAs of the grid.
 template <int RW, int KS, int NCH, int NP>   // K = KS slices x NP passes x NCH chunks of 32
 __device__ __forceinline__ void
@@ -670,6 +695,10 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
           const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
           float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     static_assert(RW * KS == 8, "8 warps");
+    // decoder weights are re-read by every step of every batch in flight: keep them in L2 (evict-last) against the
+    // streams that pass through it (cross-attention K/V is evict-first, encoder activations are untagged)
+    const uint64_t wpol = l2_evict_last_policy();
+#define WB_WLOAD(ptr) ldg_hint((ptr), wpol)
     const int xstride = K * 2 + 64;                                  // bytes per activation row
     const int rows_st = ((B + 7) >> 3) << 3;                         // staged sequences: whole n-tiles of 8
     unsigned char* xs = mm_smem;                                     // [rows_st][K] bf16 (padded rows)
@@ -696,8 +725,8 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             const bf16* p1 = W + (size_t)r1 * K + kbase + 8 * t;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                wa[c] = *reinterpret_cast<const uint4*>(p0 + c * 32);
-                wb[c] = *reinterpret_cast<const uint4*>(p1 + c * 32);
+                wa[c] = WB_WLOAD(p0 + c * 32);
+                wb[c] = WB_WLOAD(p1 + c * 32);
             }
         }
         if (!synced) {
@@ -837,8 +866,8 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                 const bf16* p1 = W + (size_t)r1 * K + kbase + (p + 1) * NCH * 32 + 8 * t;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    na[c] = *reinterpret_cast<const uint4*>(p0 + c * 32);
-                    nb[c] = *reinterpret_cast<const uint4*>(p1 + c * 32);
+                    na[c] = WB_WLOAD(p0 + c * 32);
+                    nb[c] = WB_WLOAD(p1 + c * 32);
                 }
             }
 #pragma unroll
@@ -961,6 +990,21 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                                      state, sup_base, sup_first, amax_val, amax_idx);
 }
 
+// The same kernel capped at 192 registers ("lean").  A 256-thread CTA then takes 48 K of the SM's 64 K registers, which
+// leaves exactly the 16 K that a 4-warp cross-attention CTA of ANOTHER batch in flight needs: the latency-bound GEMMs
+// stop locking the HBM-bound kernel out of their SMs (__maxnreg__ and __launch_bounds__ cannot be combined).
+template <int RW, int KS, int NCH, int NP>
+__global__ void __maxnreg__(192)
+skinny_mma_lean_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
+                       const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                       int act, const float* residual, float* Y,
+                       const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
+                       float* __restrict__ amax_val, int* __restrict__ amax_idx) {
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    mma_stage<RW, KS, NCH, NP>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
+                                     state, sup_base, sup_first, amax_val, amax_idx);
+}
+
 template <int RW, int KS, int NCH, int NP = 1>
 void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
                        const float* lb, int act, const float* residual, float* Y, bool fused_argmax = false) {
@@ -970,6 +1014,10 @@ void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W,
     const int tiles = ceil_div(N, RW * 16);
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     DecBufs& D = ctx->dec;
+    if (D.lean && !fused_argmax)
+        launch_k(skinny_mma_lean_kernel<RW, KS, NCH, NP>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
+                 act, residual, Y, (const int*)nullptr, (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p, (float*)nullptr, (int*)nullptr);
+    else
     launch_k(skinny_mma_kernel<RW, KS, NCH, NP>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
              act, residual, Y, (const int*)(fused_argmax ? D.amax_state : nullptr), (const unsigned*)D.sup_base.p,
              (const unsigned*)D.sup_first.p, fused_argmax ? D.amax_val : (float*)nullptr, fused_argmax ? D.amax_idx : (int*)nullptr);
@@ -1024,6 +1072,17 @@ void skinny_mma_set_attrs() {       // once per process, outside any stream capt
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<8, 1, 5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<2, 4, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<1, 8, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<1, 8, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<8, 1, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<8, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<4, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<2, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<2, 4, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<2, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<2, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
 inline bool skinny_mma(wb_ctx*, const float*, int, int, const float*, int, const float*, const float*, const float*, int,
@@ -1090,11 +1149,14 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
             WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + (size_t)l * c.max_batch * D.T_max * 2 * d;
             const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + (size_t)l * c.max_batch * Tk * 2 * d;
             skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, D.qkv.p); ++n;                                             // K3c
-            launch_k(self_attn_kernel<WT>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max); ++n;   // K3d
+            if (D.self_attn_warps == 2) launch_k(self_attn_kernel<WT, 2>, dim3(H, B), dim3(64), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);   // K3d
+            else if (D.self_attn_warps == 4) launch_k(self_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);
+            else launch_k(self_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);
+            ++n;
             skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, x, x); ++n;                                                      // K3f
             skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
             if (sizeof(WT) == 2 && cross_attn_tc_ok(ctx)) cross_attn_tc(ctx, st, pdl, l, D.q.p, D.att.p, B);                // K3e
-            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk);
+            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean);
             ++n;
             skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, x, x); ++n;
             skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                                               // K3g
@@ -1159,6 +1221,10 @@ void decoder_alloc(wb_ctx* ctx) {
     D.sup_base.reserve(words);
     D.sup_first.reserve(words);
     if (c.precision == WB_PREC_BF16) { set_func_attrs<bf16>(); skinny_mma_set_attrs(); } else set_func_attrs<float>();
+    D.lean = false;                    // WB_DEC_LEAN=1: 192-register GEMM kernels + 4-warp cross-attention CTAs (co-residency across batches in flight)
+    if (const char* e = getenv("WB_DEC_LEAN")) D.lean = e[0] == '1';
+    D.self_attn_warps = 4;            // measured: 4 warps is the best of 2 / 4 / 8 both for one batch alone and for 8 in flight
+    if (const char* e = getenv("WB_SELF_ATTN_WARPS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) D.self_attn_warps = v; }
     dec_cluster_alloc(ctx);           // bf16 build at whisper-base widths: all layers of a step in one launch
 }
 
@@ -1348,7 +1414,7 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
         if (k == "cross_attn") {
             const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * c.n_audio_ctx * 2 * d * ctx->esz();
             if (bf && cross_attn_tc_ok(ctx) && Tk == c.n_audio_ctx) cross_attn_tc(ctx, ctx->stream, bench_pdl, l, D.q.p, D.att.p, B);
-            else if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk);
+            else if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk, D.lean);
             else launch_cross_attn<float>(ctx->stream, bench_pdl, D.q.p, (const float*)ckv, D.att.p, H, B, d, Tk);
         } else if (k == "dec_layers") {
             WB_REQUIRE(bf && dec_cluster_enabled(ctx), WB_EINVAL, "dec_layers: the cluster-chained layer kernel is not active for this context");
