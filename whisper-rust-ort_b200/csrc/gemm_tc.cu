@@ -299,8 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(bp + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
                     }
                     if (a.act == 1) {
-                        // bf16 outputs: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 rounding);
-                        // f32 outputs keep the exact erff
+                        // bf16 outputs: tanh-form GELU on tanh.approx (gelu_fast above: within 5e-4 of the reference's erf
+                        // form, below the bf16 rounding of the stored value); f32 outputs keep the exact erff
                         if (a.tc == WB_BF16) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
