@@ -65,9 +65,10 @@ def model(nodes, initializers) -> bytes:
     return _field(1, 0, _varint(8)) + _ld(2, b"pytorch") + _ld(7, graph) + _ld(8, _field(2, 0, _varint(17)))   # ir_version, producer, graph, opset
 
 
-def export_like_optimum(cfg, W: dict, out_dir: str, prefix_enc="", prefix_dec="model.decoder.", f16=False):
+def export_like_optimum(cfg, W: dict, out_dir: str, prefix_enc="", prefix_dec="model.decoder.", f16=False, reorder=None):
     """W: HF state_dict-style name -> f32 array (weights.generate).  Writes encoder_model.onnx and
-    decoder_model.onnx into out_dir."""
+    decoder_model.onnx into out_dir.  reorder(list of linear keys) -> the order their MatMul nodes are emitted in
+    (default: the order the Hugging Face forward executes them)."""
     dt = "f16" if f16 else "f32"
     counter = [100]
 
@@ -77,7 +78,7 @@ def export_like_optimum(cfg, W: dict, out_dir: str, prefix_enc="", prefix_dec="m
             inits.append(tensor(name_prefix + key, W[hf_prefix + key], packed_dims=(i % 2 == 0), use_float_data=(i % 5 == 0 and not f16), dtype=dt))
         cur = "x0"
         nodes.append(node("Identity", ["input"], [cur]))
-        for key in linears:
+        for key in (reorder(list(linears)) if reorder else linears):
             counter[0] += 7
             an = f"onnx::MatMul_{counter[0]}"
             inits.append(tensor(an, W[hf_prefix + key + ".weight"].T, dtype=dt))         # [in, out]

@@ -178,14 +178,43 @@ const Tensor* find_named(const Model& m, const std::string& key, const std::vect
     return nullptr;
 }
 
-// anonymous nn.Linear weights: 2-D initializers consumed by MatMul nodes, in node order
-std::vector<const Tensor*> matmul_weights(const Model& m) {
-    std::vector<const Tensor*> out;
+// anonymous nn.Linear weights: 2-D initializers consumed by MatMul nodes, in node order.  Each is resolved to its HF
+// module through the Add that consumes the MatMul output and that Add's NAMED bias initializer ("...q_proj.bias");
+// `key` stays empty for the bias-less ones (k_proj, the tied proj_out).
+struct AnonLinear {
+    const Tensor* w = nullptr;
+    std::string out, key;       // MatMul output tensor; HF module path relative to the encoder/decoder ("layers.0.self_attn.q_proj")
+    bool used = false;
+};
+std::vector<AnonLinear> matmul_weights(const Model& m, const std::vector<std::string>& prefixes) {
+    std::vector<AnonLinear> out;
     for (const auto& n : m.nodes) {
-        if (n.op != "MatMul" || n.in.size() != 2) continue;
+        if (n.op != "MatMul" || n.in.size() != 2 || n.out.empty()) continue;
         for (const auto& i : n.in) {
             auto it = m.init.find(i);
-            if (it != m.init.end() && it->second.dims.size() == 2) out.push_back(&it->second);
+            if (it != m.init.end() && it->second.dims.size() == 2) {
+                AnonLinear a;
+                a.w = &it->second;
+                a.out = n.out[0];
+                out.push_back(a);
+            }
+        }
+    }
+    for (const auto& n : m.nodes) {
+        if (n.op != "Add" || n.in.size() != 2) continue;
+        for (int side = 0; side < 2; ++side) {
+            const std::string& b = n.in[side];
+            const std::string& x = n.in[1 - side];
+            if (b.size() < 6 || b.compare(b.size() - 5, 5, ".bias") != 0 || m.init.find(b) == m.init.end()) continue;
+            std::string key = b.substr(0, b.size() - 5);
+            for (const auto& p : prefixes)
+                if (!p.empty() && key.compare(0, p.size(), p) == 0) { key = key.substr(p.size()); break; }
+            for (auto& a : out)
+                if (a.out == x) {
+                    WB_REQUIRE(a.key.empty() || a.key == key, WB_EINVAL, "ONNX: MatMul weight %s feeds two different biases (%s, %s)",
+                               a.w->name.c_str(), a.key.c_str(), key.c_str());
+                    a.key = key;
+                }
         }
     }
     return out;
@@ -210,17 +239,23 @@ void onnx_load_dir(const std::string& dir, const wb_model_cfg& c, std::map<std::
     struct Lin { std::string key; int64_t out, in; };
     auto take_linears = [&](const Model& m, const std::vector<std::string>& pre, const std::string& hf_prefix, const std::vector<Lin>& lins,
                             bool tied_tail) {
-        // (a) exports that kept nn.Linear names [out,in]; (b) anonymous transposed MatMul weights by graph order
-        std::vector<const Tensor*> anon = matmul_weights(m);
-        size_t cursor = 0;
-        for (const auto& L : lins) {
-            if (const Tensor* t = find_named(m, L.key + ".weight", pre)) {
-                WB_REQUIRE(t->dims.size() == 2 && t->dims[0] == L.out && t->dims[1] == L.in, WB_EINVAL, "ONNX initializer %s has an unexpected shape", t->name.c_str());
-                host[hf_prefix + L.key + ".weight"] = to_f32(*t);
-                continue;
-            }
-            WB_REQUIRE(cursor < anon.size(), WB_EINVAL, "ONNX graph has fewer MatMul weights than the architecture needs (at %s)", L.key.c_str());
-            const Tensor* t = anon[cursor++];
+        // (a) exports that kept nn.Linear names [out,in]; (b) anonymous transposed MatMul weights, identified by the named
+        // bias their output is added to; the bias-less ones (k_proj) must be the only unidentified MatMul between their
+        // identified neighbours in node order -- anything else is ambiguous and fails instead of loading silently wrong
+        std::vector<AnonLinear> anon = matmul_weights(m, pre);
+        auto by_key = [&](const std::string& key) -> int {
+            int found = -1;
+            for (size_t i = 0; i < anon.size(); ++i)
+                if (anon[i].key == key) {
+                    WB_REQUIRE(found < 0, WB_EINVAL, "ONNX: two MatMul weights resolve to %s", key.c_str());
+                    found = (int)i;
+                }
+            return found;
+        };
+        auto take_anon = [&](int idx, const Lin& L) {
+            AnonLinear& a = anon[(size_t)idx];
+            WB_REQUIRE(!a.used, WB_EINVAL, "ONNX MatMul weight %s would be used twice (at %s)", a.w->name.c_str(), L.key.c_str());
+            const Tensor* t = a.w;
             WB_REQUIRE(t->dims[0] == L.in && t->dims[1] == L.out, WB_EINVAL,
                        "ONNX MatMul weight %s is [%lld,%lld] but %s needs [%lld,%lld] (in,out): graph order does not match the HF module order",
                        t->name.c_str(), (long long)t->dims[0], (long long)t->dims[1], L.key.c_str(), (long long)L.in, (long long)L.out);
@@ -228,12 +263,48 @@ void onnx_load_dir(const std::string& dir, const wb_model_cfg& c, std::map<std::
             for (int64_t i = 0; i < L.in; ++i)
                 for (int64_t o = 0; o < L.out; ++o) wt[(size_t)(o * L.in + i)] = w[(size_t)(i * L.out + o)];
             host[hf_prefix + L.key + ".weight"] = std::move(wt);
+            a.used = true;
+        };
+        std::vector<int> slot(lins.size(), -2);                      // -2: named weight, -1: to be placed by position, >= 0: anon index
+        for (size_t li = 0; li < lins.size(); ++li) {
+            const Lin& L = lins[li];
+            if (const Tensor* t = find_named(m, L.key + ".weight", pre)) {
+                WB_REQUIRE(t->dims.size() == 2 && t->dims[0] == L.out && t->dims[1] == L.in, WB_EINVAL, "ONNX initializer %s has an unexpected shape", t->name.c_str());
+                host[hf_prefix + L.key + ".weight"] = to_f32(*t);
+                continue;
+            }
+            slot[li] = by_key(L.key);
         }
-        if (tied_tail && cursor < anon.size()) {
-            const Tensor* t = anon[cursor++];
-            WB_REQUIRE(t->dims[0] == d && t->dims[1] == c.vocab, WB_EINVAL, "ONNX: trailing MatMul weight is not the tied proj_out");
+        for (size_t li = 0; li < lins.size(); ++li)
+            if (slot[li] >= 0) take_anon(slot[li], lins[li]);
+        for (size_t li = 0; li < lins.size(); ++li) {
+            if (slot[li] != -1) continue;
+            // bias-less linear: the one unidentified MatMul after the previous linear's and before the next linear's weight
+            int lo = -1, hi = (int)anon.size();
+            for (size_t j = li; j-- > 0;) if (slot[j] >= 0) { lo = slot[j]; break; }
+            for (size_t j = li + 1; j < lins.size(); ++j) if (slot[j] >= 0) { hi = slot[j]; break; }
+            int pick = -1, n_free = 0;
+            for (int i = lo + 1; i < hi; ++i)
+                if (!anon[(size_t)i].used && anon[(size_t)i].key.empty() && anon[(size_t)i].w->dims[0] == lins[li].in && anon[(size_t)i].w->dims[1] == lins[li].out) {
+                    if (pick < 0) pick = i;
+                    ++n_free;
+                }
+            // several bias-less linears in a row (an export without any bias) fall back to graph order, one at a time
+            size_t run = 1;
+            for (size_t j = li + 1; j < lins.size() && slot[j] == -1; ++j) ++run;
+            WB_REQUIRE(pick >= 0 && (size_t)n_free == run, WB_EINVAL,
+                       "ONNX: cannot place the weight of %s: %d candidate MatMul weights between its neighbours, %zu expected "
+                       "(graph order does not match the HF module order)", lins[li].key.c_str(), n_free, run);
+            take_anon(pick, lins[li]);
+            slot[li] = pick;
         }
-        WB_REQUIRE(cursor == anon.size(), WB_EINVAL, "ONNX graph has %zu unassigned MatMul weights", anon.size() - cursor);
+        if (tied_tail) {
+            for (auto& a : anon)
+                if (!a.used && a.key.empty() && a.w->dims[0] == d && a.w->dims[1] == c.vocab) { a.used = true; break; }
+        }
+        size_t left = 0;
+        for (const auto& a : anon) left += a.used ? 0 : 1;
+        WB_REQUIRE(left == 0, WB_EINVAL, "ONNX graph has %zu unassigned MatMul weights", left);
     };
 
     {   // ---------------- encoder_model.onnx ----------------
