@@ -414,7 +414,12 @@ def run_ours(args, rank, world, local_rank):
     k_ms_plain, _ = m.bench_kernel("cross_attn", B, iters=30)      # serialised launches: the round-1 way of timing it
     os.environ["WB_BENCH_PDL"] = "1"              # replay the kernels the way the decode graph launches them (PDL)
     k_ms, k_bytes = m.bench_kernel("cross_attn", B, iters=30)
-    v_ms, v_bytes = m.bench_kernel("vocab_proj", B, iters=10)
+    try:                                                           # the tcgen05 vocabulary kernel where the model has it (d_model <= 512)
+        v_ms, v_bytes = m.bench_kernel("vocab_tc", B, iters=10)
+        v_name = "vocab_tc_kernel (final LN + vocabulary projection on tcgen05 + masked arg-max partials)"
+    except wb200.WbError:
+        v_ms, v_bytes = m.bench_kernel("vocab_proj", B, iters=10)
+        v_name = "skinny_mma_kernel (vocabulary projection, mma.sync)"
     peak, peak_src = measured_peaks()
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
     steps_dec = len(PROMPT) + MAX_NEW - 1
@@ -448,7 +453,7 @@ def run_ours(args, rank, world, local_rank):
                          "share_of_single_batch_step": share,
                          "without_pdl": {"ms_per_launch": k_ms_plain, "achieved": k_bytes / (k_ms_plain * 1e-3) / 1e9,
                                          "frac": k_bytes / (k_ms_plain * 1e-3) / 1e9 / peak},
-                         "also": {"vocab_proj": {"achieved": v_bytes / (v_ms * 1e-3) / 1e9, "ms_per_launch": v_ms, "bytes_per_launch": v_bytes}}},
+                         "also": {"vocab_proj": {"kernel": v_name, "achieved": v_bytes / (v_ms * 1e-3) / 1e9, "ms_per_launch": v_ms, "bytes_per_launch": v_bytes}}},
             "tokens_head": toks[0][0][:8],
         }
         if world == 1 and not args.no_other_configs and args.arch == "base":

@@ -80,12 +80,14 @@ int wb_get_tensor(wb_ctx* ctx, const char* name, float* out, int64_t n);
 
 /* ---- group 1: whisper_log_mel_80 (main.rs:407-509) + chunk slicing (:875-882, :895-905) ----
  * pcm: n_files mono 16 kHz files back to back; file i = pcm[offsets[i] .. offsets[i+1]).
- * Per file: reflect-pad 200, periodic Hann, 400-pt FFT hop 160, power, Slaney 80-mel, log10,
+ * Per file: reflect-pad 200, periodic Hann, 400-pt FFT hop 160, power, Slaney mel filterbank of cfg.n_mels
+ * triangles (80 = the reference's frontend; 128 = the large-v3 one, same function otherwise), log10,
  * clamp to FILE-GLOBAL max-8, (x+4)/4; then the file is cut into 30 s windows every 25 s
  * (chunk_len/step in samples; 0 = 480000/400000) zero-padded IN MEL SPACE to 3000 frames.
- * The chunk batch [n_chunks,80,3000] stays resident on the device for wb_encode.
- * mel_out (nullable, host): per-file [80][floor(N_i/160)] matrices back to back.
- * n_frames_out (nullable, host) [n_files].  Returns chunk count via n_chunks_out (nullable). */
+ * The chunk batch [n_chunks,n_mels,3000] stays resident on the device for wb_encode.
+ * mel_out (nullable, host): per-file [n_mels][floor(N_i/160)] matrices back to back.
+ * n_frames_out (nullable, host) [n_files].  Returns chunk count via n_chunks_out (nullable).
+ * With mel_out == NULL the call returns once the PCM is on the device and the kernels are enqueued. */
 int wb_log_mel(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_files,
                int64_t chunk_len, int64_t step, float* mel_out, int64_t* n_frames_out,
                int* n_chunks_out);
@@ -95,13 +97,15 @@ int wb_upload_pcm(wb_ctx* ctx, const float* pcm, const int64_t* offsets, int n_f
 int wb_run_log_mel(wb_ctx* ctx);
 /* Resident chunk metadata / data: file index + sample position of each chunk; mel windows. */
 int wb_get_chunks(wb_ctx* ctx, int32_t* file_idx, int64_t* sample_pos, int cap);
-int wb_get_chunk_mel(wb_ctx* ctx, int chunk_begin, int n, float* out /* [n,80,3000] */);
+int wb_get_chunk_mel(wb_ctx* ctx, int chunk_begin, int n, float* out /* [n,n_mels,3000] */);
 
 /* ---- group 2: run_encoder (main.rs:698-707; encoder.run at :703) ----
  * mel: host [B,n_mels,3000] f32, or NULL = use resident chunks [chunk_begin, chunk_begin+B).
  * hidden_out (nullable, host): [B,n_audio_ctx,d_model] f32 (the ONNX output 0).
  * Encoder states and the cross-attention K/V (the `present.*.encoder.*` outputs of
- * decoder_model.onnx, main.rs:786-787) stay resident for wb_greedy_decode. */
+ * decoder_model.onnx, main.rs:786-787) stay resident for wb_greedy_decode.
+ * With hidden_out == NULL the call only enqueues (no host wait): wb_greedy_decode runs right behind it on the
+ * context's stream, and wb_get_timing waits for whatever is still outstanding. */
 int wb_encode(wb_ctx* ctx, const float* mel, int chunk_begin, int B, float* hidden_out);
 /* Debug/test: intermediate activations of the last wb_encode. what: "stem" | "layer0". */
 int wb_get_encoder_debug(wb_ctx* ctx, const char* what, float* out, int64_t n);

@@ -87,3 +87,40 @@ def test_optional_kernels_free_running_decode_and_eot_bookkeeping(wb, env):
         n = len(row)
         assert row == full[:n] and (row[-1] == first_tok or n == 44)
     base.close(); opt.close()
+
+
+def test_tcgen05_vocabulary_projection_argmax(wb, oracle_run):
+    """vocab_tc.cu (default whenever a decode does not ask for logits): final LayerNorm + vocabulary projection on
+    tcgen05.mma (swap-AB) + masked arg-max partials.  Teacher-forced on the oracle's ids WITHOUT logits, so this kernel
+    (not the mma.sync one that also writes logits) produces the reported arg-max of every step: identical to the oracle
+    wherever its top-1 margin is clear of bf16 noise (begin-suppress at step 0, suppress everywhere, vocabulary tail of
+    the last 128-row tile excluded), identical between batch positions, and equal to the mma.sync kernel's on the same
+    margin-gated positions.  A batch of 32 (all TMEM columns) and a ragged one (7)."""
+    g, mel, forced, ref_l = oracle_run
+    sup = np.isin(np.arange(ref_l.shape[-1]), g["suppress"])
+    masked = np.where(sup, -np.inf, ref_l)
+    masked[:, 0, g["begin_suppress"]] = -np.inf
+    top2 = np.sort(masked, -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 0.1
+    want = masked.argmax(-1)
+    assert clear.mean() > 0.3
+    for n in (32, 7):
+        idx = np.arange(n) % 3
+        res = {}
+        for flag in ("1", "0"):
+            old = os.environ.get("WB_VOCAB_TC")
+            os.environ["WB_VOCAB_TC"] = flag
+            try:
+                m = make(wb, {}, n)
+            finally:
+                os.environ.pop("WB_VOCAB_TC", None)
+                if old is not None:
+                    os.environ["WB_VOCAB_TC"] = old
+            m.encode(mel[idx])
+            toks = m.greedy_decode(n, g["prompt"], forced.shape[1], EOT, g["suppress"], g["begin_suppress"], forced=forced[idx])
+            res[flag] = np.array([s[len(g["prompt"]):] for s in toks])
+            m.close()
+        for r, k in enumerate(idx):
+            assert np.all(res["1"][r][clear[k]] == want[k][clear[k]]), r
+            assert np.all(res["0"][r][clear[k]] == want[k][clear[k]]), r
+            assert np.array_equal(res["1"][r], res["1"][k])                 # same clip, other batch position: same ids

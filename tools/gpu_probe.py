@@ -130,7 +130,7 @@ def kernels(argv):
     m.encode(None, 0, B, want_hidden=False)
     m.greedy_decode(B, PROMPT, int(argv[0]) if argv else 64, EOT)
     out = {}
-    for k, it in (("cross_attn", 30), ("vocab_proj", 20), ("dec_vocab", 20), ("logmel", 10)):
+    for k, it in (("cross_attn", 30), ("vocab_proj", 20), ("vocab_tc", 20), ("dec_vocab", 20), ("logmel", 10)):
         try:
             ms, by = m.bench_kernel(k, B, it)
         except wb200.WbError as e:          # a path that is switched off in this process

@@ -271,6 +271,7 @@ void wb_destroy(wb_ctx* ctx) {
     for (auto& g : ctx->dec.graphs) cudaGraphExecDestroy(g.exec);
     if (ctx->dec.unfinished_host) cudaFreeHost(ctx->dec.unfinished_host);
     if (ctx->dec.stage_host) cudaFreeHost(ctx->dec.stage_host);
+    vocab_tc_free(ctx);
     if (ctx->mel_tables_dev) cudaFree(ctx->mel_tables_dev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -127,6 +127,7 @@ struct DecBufs {
     int self_attn_warps = 4;           // warps per (sequence, head) in the self-attention kernel (WB_SELF_ATTN_WARPS = 2 | 4 | 8)
     int* stage_host = nullptr;         // pinned staging of the per-decode control state (ids, bitmaps, lens): a pageable
     size_t stage_ints = 0;             //   source would make every cudaMemcpyAsync wait for the stream to drain first
+    void* vocab_tc = nullptr;          // vocab_tc.cu: tcgen05 vocabulary projection + arg-max (bf16 build, d_model <= 512)
     struct DecCluster* cluster = nullptr;   // dec_cluster.cu: all layers of a step in one launch (bf16, whisper-base widths)
 };
 
@@ -150,6 +151,13 @@ struct wb_ctx {
     CudaEvent marks[8];
     size_t esz() const { return cfg.precision == WB_PREC_BF16 ? 2 : 4; }
 };
+
+// vocab_tc.cu — final LayerNorm + vocabulary projection on tcgen05 with the masked arg-max fused (swap-AB: 128 weight rows x
+// <= 32 sequences per MMA); returns the number of per-CTA partials written for argmax_merge_kernel
+void vocab_tc_alloc(wb_ctx* ctx);
+void vocab_tc_free(wb_ctx* ctx);
+bool vocab_tc_ok(const wb_ctx* ctx, int B);
+int vocab_tc_launch(wb_ctx* ctx, cudaStream_t st, bool pdl, const int* state, const float* x, int B, float* amax_val, int* amax_idx);
 
 // api.cpp — waits for and publishes the stage timings whose events are still outstanding
 void timing_flush(wb_ctx* ctx);

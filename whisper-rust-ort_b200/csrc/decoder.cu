@@ -1179,7 +1179,12 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
         D.amax_val = D.amax_buf.p;                                           // [ctas][32] val | idx
         D.amax_idx = reinterpret_cast<int*>(D.amax_val + (size_t)32 * ctx->sm_count);
         D.amax_ctas = 0;
-        skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, (fuse && !D.want_logits) ? nullptr : D.logits.p, c.vocab, w.embed); ++n;
+        if (fuse && !D.want_logits && vocab_tc_ok(ctx, B)) {
+            // tcgen05 swap-AB kernel (vocab_tc.cu): final LN + projection + per-CTA masked arg-max partials, no logits
+            D.amax_ctas = vocab_tc_launch(ctx, st, pdl, state, x, B, D.amax_val, D.amax_idx); ++n;
+        } else {
+            skinny<WT>(ctx, x, B, d, dummy, &w.dec_ln, 0, nullptr, (fuse && !D.want_logits) ? nullptr : D.logits.p, c.vocab, w.embed); ++n;
+        }
         D.amax_state = nullptr;
         if (fuse && D.amax_ctas > 0) {
             launch_k(argmax_merge_kernel, dim3(B), dim3(32), 0, st, pdl, (const int*)state, (const float*)D.amax_val, (const int*)D.amax_idx,
@@ -1225,6 +1230,7 @@ void decoder_alloc(wb_ctx* ctx) {
     if (const char* e = getenv("WB_DEC_LEAN")) D.lean = e[0] == '1';
     D.self_attn_warps = 4;            // measured: 4 warps is the best of 2 / 4 / 8 both for one batch alone and for 8 in flight
     if (const char* e = getenv("WB_SELF_ATTN_WARPS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) D.self_attn_warps = v; }
+    vocab_tc_alloc(ctx);
     dec_cluster_alloc(ctx);           // bf16 build at whisper-base widths: all layers of a step in one launch
 }
 
@@ -1327,7 +1333,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     auto run_segment = [&](int n_steps, bool with_logits, int first_gi) {
         if (!use_graph) return enqueue_steps(n_steps, with_logits, first_gi);
         const int key[8] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
-                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0) + (cross_attn_tc_ok(ctx) ? 8 : 0),
+                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0) + (cross_attn_tc_ok(ctx) ? 8 : 0) + (vocab_tc_ok(ctx, B) ? 16 : 0),
                             n_steps, with_logits ? 1 : 0};
         DecGraph* g = nullptr;
         for (auto& e : D.graphs) {
@@ -1426,6 +1432,9 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
             WB_REQUIRE(bf && dec_cluster_vocab_ok(ctx, B) && D.last_T_total > 0, WB_EINVAL, "dec_vocab: the fused vocabulary kernel is not active for this context");
             dec_cluster_vocab(ctx, ctx->stream, bench_pdl, D.state.p, B, nullptr, nullptr, 1, -1, D.last_T_total,
                               D.tokens.p + (size_t)c.max_batch * D.last_T_total);
+        } else if (k == "vocab_tc") {
+            WB_REQUIRE(vocab_tc_ok(ctx, B), WB_ESTATE, "the tcgen05 vocabulary kernel is not available for this model");
+            vocab_tc_launch(ctx, ctx->stream, bench_pdl, D.state.p, D.x.p, B, D.amax_buf.p, reinterpret_cast<int*>(D.amax_buf.p + (size_t)32 * ctx->sm_count));
         } else if (k == "vocab_proj") {
             LinearW dummy;
             if (bf) skinny<bf16>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
@@ -1456,6 +1465,7 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
     } else
     if (k == "dec_layers") { *bytes = dec_cluster_bytes(ctx, B); dec_cluster_print_prof(ctx); }
     else if (k == "cross_attn") *bytes = (double)B * 2.0 * Tk * d * ctx->esz() + (double)B * d * 8.0;      // K+V stream, q in, out
+    else if (k == "vocab_tc") *bytes = (double)c.vocab * d * ctx->esz() + (double)B * d * 4.0;              // weights, activations in (no logits out)
     else *bytes = (double)c.vocab * d * ctx->esz() + (double)B * c.vocab * 4.0 + (double)B * d * 4.0;  // weights, logits out
 }
 
