@@ -161,6 +161,14 @@ vocab_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
         const int first = total_g < VT_STAGES ? total_g : VT_STAGES;
         for (; issued < first; ++issued) issue_load(issued);
     }
+    // LayerNorm parameters are weights too: fetch them under the predecessor's tail
+    float4 gw[4], gb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = i * 128 + lane * 4;
+        gw[i] = c < K ? __ldg(reinterpret_cast<const float4*>(ln_w + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gb[i] = c < K ? __ldg(reinterpret_cast<const float4*>(ln_b + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -216,9 +224,8 @@ vocab_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
                 if (c < K) {
                     uint2 pk = make_uint2(0u, 0u);
                     if (r < B) {
-                        const float4 gw = *reinterpret_cast<const float4*>(ln_w + c), gb = *reinterpret_cast<const float4*>(ln_b + c);
-                        pk.x = pack_bf16x2((xv[j][i].x - mean) * rs * gw.x + gb.x, (xv[j][i].y - mean) * rs * gw.y + gb.y);
-                        pk.y = pack_bf16x2((xv[j][i].z - mean) * rs * gw.z + gb.z, (xv[j][i].w - mean) * rs * gw.w + gb.w);
+                        pk.x = pack_bf16x2((xv[j][i].x - mean) * rs * gw[i].x + gb[i].x, (xv[j][i].y - mean) * rs * gw[i].y + gb[i].y);
+                        pk.y = pack_bf16x2((xv[j][i].z - mean) * rs * gw[i].z + gb[i].z, (xv[j][i].w - mean) * rs * gw[i].w + gb[i].w);
                     }
                     const int kb = c >> 6, chunk = (c & 63) >> 3;         // 16-byte chunk of the 128-byte row
                     *reinterpret_cast<uint2*>(sB + (size_t)kb * VT_BTILE_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4) + (c & 7) * 2) = pk;
@@ -298,16 +305,31 @@ vocab_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict
 #pragma unroll
         for (int s = 0; s < VT_N; ++s) { sv[row * 33 + s] = bestv[s]; si[row * 33 + s] = besti[s]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2) {
+        {   // thread (sequence = lane, quarter = q) scans 32 of the 128 rows; the four quarters meet in shared memory
             float bv = -INFINITY;
             int bi = 0x7fffffff;
-            for (int rr = 0; rr < 128; ++rr) {
+#pragma unroll 8
+            for (int rr = q * 32; rr < q * 32 + 32; ++rr) {
                 const float v = sv[rr * 33 + lane];
                 const int i = si[rr * 33 + lane];
                 if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
             }
-            amax_val[(size_t)blockIdx.x * 32 + lane] = bv;
-            amax_idx[(size_t)blockIdx.x * 32 + lane] = bi;
+            float* pv = reinterpret_cast<float*>(sA + 2 * 128 * 33 * 4);    // [4][32] values | indices
+            int* pi = reinterpret_cast<int*>(pv + 4 * 32);
+            pv[q * 32 + lane] = bv;
+            pi[q * 32 + lane] = bi;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2) {
+                bv = pv[lane]; bi = pi[lane];
+#pragma unroll
+                for (int k = 1; k < 4; ++k) {
+                    const float v = pv[k * 32 + lane];
+                    const int i = pi[k * 32 + lane];
+                    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+                }
+                amax_val[(size_t)blockIdx.x * 32 + lane] = bv;
+                amax_idx[(size_t)blockIdx.x * 32 + lane] = bi;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
