@@ -63,9 +63,9 @@ def decode(argv):
 
 def inflight(argv):
     counts = [int(x) for x in argv] or [1, 2, 4]
-    B = 32
+    B = int(os.environ.get("WB_PROBE_B", "32"))
     pcm = wb200.synth.fast_batch(B, seed=1)
-    out = {}
+    out = {"B": B}
     for S in counts:
         ctxs = [make(B) for _ in range(S)]
         for c in ctxs:
@@ -90,9 +90,9 @@ def inflight(argv):
 def stages(argv):
     """S contexts in flight, each looping ONE stage (decode only / encoder only): which stage saturates the GPU, and where?"""
     counts = [int(x) for x in argv] or [1, 8]
-    B = 32
+    B = int(os.environ.get("WB_PROBE_B", "32"))           # per-chain batch: how much of a decode is per-clip, how much per-step?
     pcm = wb200.synth.fast_batch(B, seed=1)
-    out = {}
+    out = {"B": B}
     ctxs = [make(B) for _ in range(max(counts))]
     for c in ctxs:
         c.upload_pcm(pcm)

@@ -322,6 +322,265 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Second generation of the same kernel (default; WB_ATTN_V=1 selects the first).  Same tiles, barriers and MMA order;
+// what changed is the softmax side, which bounded the first one (ncu: ex2 pipe 50 %, issue 52 %, tensor 24 %):
+//   * the 64 scores of a thread are read from TMEM ONCE and stay in registers between the maximum and the exponentials
+//     (the first version read S twice: tcgen05.ld + wait per 32 columns, 4 of them per block and thread);
+//   * O is accumulated by the tensor core in TMEM (accumulate flag on P.V) instead of being read back and folded into
+//     32 registers per thread every block;  the running maximum used for the exponentials is only moved when the true
+//     maximum has grown by more than 2^8 (exact: l and O carry the same stale maximum and the final O / l cancels it),
+//     so the TMEM read-modify-write of O happens a few times per tile instead of every block.
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// p = exp2(s * sc - m) of the 64 scores a thread holds in registers -> bf16 -> swizzled P row; returns their f32 sum.
+template <bool MASK>
+__device__ __forceinline__ float exp_store_regs(const uint32_t (&r)[64], int valid, float sc, float m, uint8_t* prow, int sw) {
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = c2 * 32 + 2 * i;
+            float p0 = ex2(fmaf(__uint_as_float(r[e]), sc, -m));
+            float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), sc, -m));
+            if (MASK) {
+                if (e >= valid) p0 = 0.f;
+                if (e + 1 >= valid) p1 = 0.f;
+            }
+            sum0 += p0;
+            sum1 += p1;
+            __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int chunk = c2 * 4 + c;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+    }
+    return sum0 + sum1;
+}
+
+constexpr float ATT_RESCALE_LOG2 = 8.0f;               // the stale maximum may lag the true one by 2^8 (p <= 256: exact in f32 sums, same relative precision in bf16)
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int d, int H, int n_qb) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + TILE_BYTES;                   // 2 buffers
+    uint8_t* sV = smem + 3 * TILE_BYTES;               // 1 buffer
+    uint8_t* sP = smem + 4 * TILE_BYTES;               // 2 halves of 64 keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+    uint64_t* bar_q = bars;
+    uint64_t* bar_k = bars + 1;        // 2
+    uint64_t* bar_kfree = bars + 3;    // 2
+    uint64_t* bar_s = bars + 5;
+    uint64_t* bar_p = bars + 6;
+    uint64_t* bar_o = bars + 7;        // P_j V_j retired == V tile and P tile free, O stable
+    uint64_t* bar_v = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    __shared__ float s_xmax[2][2][128];
+    __shared__ float s_xl[2][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x % n_qb, h = (blockIdx.x / n_qb) % H, b = blockIdx.x / (n_qb * H);
+    const int n_kb = (T + AK - 1) / AK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQKV)) : "memory");
+            mbar_init(bar_q, 1);
+            mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
+            mbar_init(&bar_kfree[0], 1); mbar_init(&bar_kfree[1], 1);
+            mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1); mbar_init(bar_v, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ATT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA + MMA control thread (as in the first version, except that P.V accumulates into O) =====
+            const uint32_t idesc_s = idesc_of(128, 0), idesc_o = idesc_of(64, 1);
+            mbar_expect_tx(bar_q, TILE_BYTES);
+            tma_load_3d(&tmQKV, bar_q, sQ, h * HD, qb * AQ, b);
+            mbar_expect_tx(&bar_k[0], TILE_BYTES);
+            tma_load_3d(&tmQKV, &bar_k[0], sK, d + h * HD, 0, b);
+            mbar_expect_tx(bar_v, TILE_BYTES);
+            tma_load_3d(&tmQKV, bar_v, sV, 2 * d + h * HD, 0, b);
+            mbar_wait(bar_q, 0);
+            const uint64_t dq = make_desc_sw128(smem_u32(sQ));
+            const uint64_t dv = make_desc_sw128(smem_u32(sV));
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&bar_k[s], (uint32_t)((j >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t dk = make_desc_sw128(smem_u32(sK + s * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma(tS, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+                umma_commit(bar_s);
+                umma_commit(&bar_kfree[s]);
+            };
+            auto load_k = [&](int j) {
+                const int s = j & 1;
+                if (j >= 2) mbar_wait(&bar_kfree[s], (uint32_t)(((j - 2) >> 1) & 1));
+                mbar_expect_tx(&bar_k[s], TILE_BYTES);
+                tma_load_3d(&tmQKV, &bar_k[s], sK + s * TILE_BYTES, d + h * HD, j * AK, b);
+            };
+            issue_s(0);
+            if (n_kb > 1) load_k(1);
+            for (int j = 0; j < n_kb; ++j) {
+                mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, S_j consumed, O rescaled if it had to be
+                if (j + 1 < n_kb) {
+                    issue_s(j + 1);
+                    if (j + 2 < n_kb) load_k(j + 2);
+                }
+                mbar_wait(bar_v, (uint32_t)(j & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < AK / 16; ++k) {                      // O += P_j V_j
+                    const uint64_t dp = make_desc_sw128(smem_u32(sP + (k >> 2) * TILE_BYTES)) + (uint64_t)((k & 3) * 2);
+                    umma(tO, dp, dv + (uint64_t)(k * 128), idesc_o, (uint32_t)((j | k) != 0));
+                }
+                umma_commit(bar_o);
+                if (j + 1 < n_kb) {
+                    mbar_wait(bar_o, (uint32_t)(j & 1));
+                    mbar_expect_tx(bar_v, TILE_BYTES);
+                    tma_load_3d(&tmQKV, bar_v, sV, 2 * d + h * HD, (j + 1) * AK, b);
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 1) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;
+        float m_used = -INFINITY, l = 0.f;                               // l: this thread's half of the row sum, in units of 2^m_used
+        uint8_t* prow = sP + half * TILE_BYTES + row * 128;
+        const int sw = row & 7;
+
+        for (int j = 0; j < n_kb; ++j) {
+            mbar_wait(bar_s, (uint32_t)(j & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int valid = T - j * AK - half * 64;                    // keys of this thread's half that exist (may be <= 0)
+            uint32_t r[64];
+            tmem_ld32_nowait(tS + lane_off + half * 64, r);
+            tmem_ld32_nowait(tS + lane_off + half * 64 + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float mx = -INFINITY;
+            if (valid >= 64) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+            s_xmax[j & 1][half][row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]);
+            const float m_cand = mx * sc;
+            // P is single-buffered and O must be stable: P_{j-1} V_{j-1} has to retire before either is touched
+            if (j > 0) mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+            if (j == 0) {
+                m_used = m_cand;
+            } else {
+                const bool grow = m_cand > m_used + ATT_RESCALE_LOG2;
+                if (__any_sync(0xffffffffu, grow)) {                     // rare after the first blocks
+                    const float alpha = grow ? ex2(m_used - m_cand) : 1.0f;
+                    if (grow) m_used = m_cand;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {                        // 8 columns at a time: the 64 scores stay in registers
+                        uint32_t o[8];
+                        const uint32_t ta = tO + lane_off + half * 32 + c * 8;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(ta));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                     ::"r"(ta), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    l *= alpha;
+                }
+            }
+            const float sum = valid >= 64 ? exp_store_regs<false>(r, valid, sc, m_used, prow, sw) : exp_store_regs<true>(r, valid, sc, m_used, prow, sw);
+            l += sum;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_p);
+        }
+        mbar_wait(bar_o, (uint32_t)((n_kb - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        s_xl[half][row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float inv = 1.0f / (l + s_xl[half ^ 1][row]);
+        const int gq = qb * AQ + row;
+        {
+            uint32_t o[32];
+            tmem_ld32(tO + lane_off + half * 32, o);
+            if (gq < T) {
+                uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * T + gq) * d + h * HD + half * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = c * 8 + 2 * i;
+                        __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv);
+                        w[i] = *reinterpret_cast<uint32_t*>(&v);
+                    }
+                    dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ATT_TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -336,6 +595,7 @@ bool attn_tc_enabled() {
 
 void attn_tc_set_attrs() {           // per context / device, from wb_create (see mel_set_attrs)
     CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
 }
 
 // qkv: [B][T][3d] bf16 (q | k | v), out: [B][T][d] bf16.
@@ -357,6 +617,9 @@ void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WB_REQUIRE(r == CUDA_SUCCESS, WB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     const int n_qb = ceil_div(T, AQ);
-    attn_tc_kernel<<<B * H * n_qb, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, (__nv_bfloat16*)out, T, d, H, n_qb);
+    static int version = 0;
+    if (!version) { const char* e = getenv("WB_ATTN_V"); version = (e && e[0] == '1') ? 1 : 2; }
+    if (version == 1) attn_tc_kernel<<<B * H * n_qb, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, (__nv_bfloat16*)out, T, d, H, n_qb);
+    else attn_tc2_kernel<<<B * H * n_qb, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, (__nv_bfloat16*)out, T, d, H, n_qb);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -157,7 +157,11 @@ struct wb_ctx {
 void vocab_tc_alloc(wb_ctx* ctx);
 void vocab_tc_free(wb_ctx* ctx);
 bool vocab_tc_ok(const wb_ctx* ctx, int B);
+int vocab_tc_stride(int B);          // sequences per partial row ([cta][stride] values | indices)
 int vocab_tc_launch(wb_ctx* ctx, cudaStream_t st, bool pdl, const int* state, const float* x, int B, float* amax_val, int* amax_idx);
+// the per-layer decode GEMMs on the same kernel family; false = shape / weight not served, caller falls back
+bool skinny_tc_launch(wb_ctx* ctx, cudaStream_t st, bool pdl, const float* X, int B, int K, const void* W, int N, const float* bias,
+                      const float* ln_w, const float* ln_b, int act, const float* residual, float* Y);
 
 // api.cpp — waits for and publishes the stage timings whose events are still outstanding
 void timing_flush(wb_ctx* ctx);

@@ -602,7 +602,7 @@ argmax_kernel(const int* __restrict__ state, const float* __restrict__ logits, i
 
 // Second half of the fused arg-max: combine the per-CTA partials of the vocabulary projection.
 __global__ void __launch_bounds__(32)
-argmax_merge_kernel(const int* __restrict__ state, const float* __restrict__ pval, const int* __restrict__ pidx, int n_part,
+argmax_merge_kernel(const int* __restrict__ state, const float* __restrict__ pval, const int* __restrict__ pidx, int n_part, int pstride,
                     const int* __restrict__ forced, int max_new, int eot, int T_total, int* __restrict__ tokens,
                     int* __restrict__ lens, int* __restrict__ finished, int* __restrict__ cur_tok) {
     pdl_sync();
@@ -611,8 +611,8 @@ argmax_merge_kernel(const int* __restrict__ state, const float* __restrict__ pva
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int p = lane; p < n_part; p += 32) {
-        const float v = pval[p * 32 + b];
-        const int i = pidx[p * 32 + b];
+        const float v = pval[p * pstride + b];
+        const int i = pidx[p * pstride + b];
         if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
     }
 #pragma unroll
@@ -685,7 +685,10 @@ void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv,
 
 constexpr int MM_THREADS = 256;
 // One skinny GEMM executed by CTA `cta` of the `ncta` CTAs of the grid.
-template <int RW, int KS, int NCH, int NP>   // K = KS slices x NP passes x NCH chunks of 32
+// Sequences are processed in groups of GS = 8 * NT (NT n-tiles of 8): batches up to GS take one pass as before; a wider
+// batch walks its groups with the SAME register-resident weight fragments (one weight read per step for 64 or 128
+// sequences: the per-step cost of a decode chain is weight- and latency-bound, so it is shared by more clips).
+template <int RW, int KS, int NCH, int NP, int NT>   // K = KS slices x NP passes x NCH chunks of 32
 __device__ __forceinline__ void
 mma_stage(unsigned char* mm_smem, int cta, int ncta,
           const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
@@ -699,20 +702,21 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
     // streams that pass through it (cross-attention K/V is evict-first, encoder activations are untagged)
     const uint64_t wpol = l2_evict_last_policy();
 #define WB_WLOAD(ptr) ldg_hint((ptr), wpol)
+    constexpr int GS = NT * 8, PS = GS + 1;                          // sequences per pass, pitch of the k-slice partials
     const int xstride = K * 2 + 64;                                  // bytes per activation row
-    const int rows_st = ((B + 7) >> 3) << 3;                         // staged sequences: whole n-tiles of 8
-    unsigned char* xs = mm_smem;                                     // [rows_st][K] bf16 (padded rows)
-    float* part = reinterpret_cast<float*>(mm_smem + rows_st * xstride);  // [KS][RW*16][33]
+    const int rows_max = (((B < GS ? B : GS) + 7) >> 3) << 3;        // staged sequences of the widest pass: whole n-tiles of 8
+    unsigned char* xs = mm_smem;                                     // [rows_max][K] bf16 (padded rows)
+    float* part = reinterpret_cast<float*>(mm_smem + rows_max * xstride);  // [KS][RW*16][PS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int rt = warp / KS, ks = warp % KS;
     const int rows_cta = RW * 16;
     const int n_tiles = (N + rows_cta - 1) / rows_cta;
     const int kbase = ks * NP * NCH * 32;
-    bool synced = false;
-    float bestv[8];
-    int besti[8];
+    bool synced = false, staged = false;
+    float bestv[2 * NT];
+    int besti[2 * NT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { bestv[i] = -INFINITY; besti[i] = 0x7fffffff; }
+    for (int i = 0; i < 2 * NT; ++i) { bestv[i] = -INFINITY; besti[i] = 0x7fffffff; }
     const unsigned* sup = nullptr;
 
     for (int tile = cta; tile < n_tiles; tile += ncta) {
@@ -733,7 +737,13 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             pdl_sync();
             synced = true;
             if (amax_val) sup = (state[0] - (state[1] - 1) == 0) ? sup_first : sup_base;   // first generated token?
-            // ---- stage (and LayerNorm) the activations once per CTA: warp w owns rows w, w+8, .. ----
+        }
+        for (int b0 = 0; b0 < B; b0 += GS) {                         // one pass per group of GS sequences
+        const int rows_st = (((B - b0 < GS ? B - b0 : GS) + 7) >> 3) << 3;
+        if (!staged || B > GS) {
+            if (staged) __syncthreads();                             // every warp is done reading the previous group's rows
+            staged = true;
+            // ---- stage (and LayerNorm) the activations, once per CTA when the batch fits one pass: warp w owns rows w, w+8, .. ----
             constexpr int KT = KS * NP * NCH * 32;                   // == K (checked at launch): prunes the unused LayerNorm path
             if (KT > 512 && ln_w) {
                 // wide rows (d_model 1280): one row at a time, the whole row in registers (K <= 1280)
@@ -744,7 +754,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
 #pragma unroll
                     for (int i = 0; i < LNV; ++i) {
                         const int c = i * 128 + lane * 4;
-                        xv[i] = (bb < B && c < K) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)bb * K + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xv[i] = (b0 + bb < B && c < K) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)(b0 + bb) * K + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         s1 += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
                     }
 #pragma unroll
@@ -768,23 +778,24 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                             uint2 pk;
                             pk.x = pack_bf16((xv[i].x - mean) * rs * gw.x + gb.x, (xv[i].y - mean) * rs * gw.y + gb.y);
                             pk.y = pack_bf16((xv[i].z - mean) * rs * gw.z + gb.z, (xv[i].w - mean) * rs * gw.w + gb.w);
-                            if (bb >= B) pk = make_uint2(0u, 0u);
+                            if (b0 + bb >= B) pk = make_uint2(0u, 0u);
                             *reinterpret_cast<uint2*>(xs + bb * xstride + c * 2) = pk;
                         }
                     }
                 }
             } else
+            for (int r4 = 0; r4 * 32 < rows_st; ++r4)                // 32 staged rows (4 per warp) at a time
             for (int k0 = 0; k0 < K; k0 += 512) {
                 const int kc = min(512, K - k0);
                 float4 xv[4][4];
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
-                    const int bb = warp + rr * 8;
+                    const int bb = r4 * 32 + warp + rr * 8;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = i * 128 + lane * 4;
-                        xv[rr][i] = (bb < B && c < kc) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)bb * K + k0 + c))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xv[rr][i] = (b0 + bb < B && c < kc) ? __ldcg(reinterpret_cast<const float4*>(X + (size_t)(b0 + bb) * K + k0 + c))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
                 if (KT <= 512 && ln_w) {                              // wider rows took the branch above
@@ -836,7 +847,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                 }
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
-                    const int bb = warp + rr * 8;
+                    const int bb = r4 * 32 + warp + rr * 8;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = i * 128 + lane * 4;
@@ -851,10 +862,10 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
             }
             __syncthreads();
         }
-        // ---- 16 rows x 32 sequences x (K / KS) on the tensor cores ----
-        float acc[4][4];
+        // ---- 16 rows x GS sequences x (K / KS) on the tensor cores ----
+        float acc[NT][4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
 #pragma unroll
@@ -873,7 +884,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
+                for (int nt = 0; nt < NT; ++nt) {
                     if (nt * 8 < rows_st) {
                         const uint4 xb = *reinterpret_cast<const uint4*>(xs + (nt * 8 + g) * xstride + (kbase + (p * NCH + c) * 32 + 8 * t) * 2);
                         mma_bf16(acc[nt], wa[c].x, wb[c].x, wa[c].y, wb[c].y, xb.x, xb.y);
@@ -886,25 +897,35 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                 for (int c = 0; c < NCH; ++c) { wa[c] = na[c]; wb[c] = nb[c]; }
             }
         }
+        if (NP > 1 && b0 + GS < B) {                                 // multi-pass weights: the next group starts from the first pass again
+            const int r0 = min(n0 + g, N - 1), r1 = min(n0 + g + 8, N - 1);
+            const bf16* p0 = W + (size_t)r0 * K + kbase + 8 * t;
+            const bf16* p1 = W + (size_t)r1 * K + kbase + 8 * t;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                wa[c] = WB_WLOAD(p0 + c * 32);
+                wb[c] = WB_WLOAD(p1 + c * 32);
+            }
+        }
         // ---- combine k-slices, epilogue ----
         if (KS > 1) {
-            __syncthreads();                                         // previous tile's readers are done
+            __syncthreads();                                         // previous tile's / group's readers are done
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                float* pr = part + ((size_t)ks * rows_cta + rt * 16) * 33;
-                pr[(g) * 33 + nt * 8 + 2 * t] = acc[nt][0];
-                pr[(g) * 33 + nt * 8 + 2 * t + 1] = acc[nt][1];
-                pr[(g + 8) * 33 + nt * 8 + 2 * t] = acc[nt][2];
-                pr[(g + 8) * 33 + nt * 8 + 2 * t + 1] = acc[nt][3];
+            for (int nt = 0; nt < NT; ++nt) {
+                float* pr = part + ((size_t)ks * rows_cta + rt * 16) * PS;
+                pr[(g) * PS + nt * 8 + 2 * t] = acc[nt][0];
+                pr[(g) * PS + nt * 8 + 2 * t + 1] = acc[nt][1];
+                pr[(g + 8) * PS + nt * 8 + 2 * t] = acc[nt][2];
+                pr[(g + 8) * PS + nt * 8 + 2 * t + 1] = acc[nt][3];
             }
             __syncthreads();
-            for (int idx = tid; idx < rows_cta * 32; idx += MM_THREADS) {
-                const int nl = idx % rows_cta, b = idx / rows_cta;
+            for (int idx = tid; idx < rows_cta * GS; idx += MM_THREADS) {
+                const int nl = idx % rows_cta, bl = idx / rows_cta, b = b0 + bl;
                 const int n = tile * rows_cta + nl;
                 if (b < B && n < N) {
                     float v = 0.f;
 #pragma unroll
-                    for (int k2 = 0; k2 < KS; ++k2) v += part[((size_t)k2 * rows_cta + nl) * 33 + b];
+                    for (int k2 = 0; k2 < KS; ++k2) v += part[((size_t)k2 * rows_cta + nl) * PS + bl];
                     if (bias) v += bias[n];
                     if (act == 1) v = gelu_erf(v);
                     if (residual) v += __ldcg(residual + (size_t)b * N + n);
@@ -921,10 +942,10 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                 }
             }
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int n = n0 + g + (i >> 1) * 8, b = nt * 8 + 2 * t + (i & 1);
+                    const int n = n0 + g + (i >> 1) * 8, b = b0 + nt * 8 + 2 * t + (i & 1);
                     float v = acc[nt][i];
                     if (bias && n < N) v += bias[n];
                     if (act == 1) v = gelu_erf(v);
@@ -938,10 +959,11 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                     }
                 }
         }
+        }                                                            // sequence groups
     }
-    if (KS == 1 && amax_val) {
+    if (KS == 1 && amax_val) {                                       // (the host fuses the arg-max only when the batch is one group)
         // reduce over the 8 row lanes (g) that share a sequence, then over the 8 warps, one partial per CTA
-        float* sv = reinterpret_cast<float*>(mm_smem + rows_st * xstride); // [8 warps][32] (+ indices)
+        float* sv = reinterpret_cast<float*>(mm_smem + rows_max * xstride); // [8 warps][32] (+ indices)
         int* si = reinterpret_cast<int*>(sv + 8 * 32);
 #pragma unroll
         for (int slot = 0; slot < 8; ++slot) {
@@ -978,7 +1000,7 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
     if (!synced) pdl_sync();                        // a CTA without tiles still releases its dependents
 }
 
-template <int RW, int KS, int NCH, int NP>
+template <int RW, int KS, int NCH, int NP, int NT>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restrict__ W, int N,
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -986,8 +1008,8 @@ skinny_mma_kernel(const float* __restrict__ X, int B, int K, const bf16* __restr
                   const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
                   float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     extern __shared__ __align__(16) unsigned char mm_smem[];
-    mma_stage<RW, KS, NCH, NP>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
-                                     state, sup_base, sup_first, amax_val, amax_idx);
+    mma_stage<RW, KS, NCH, NP, NT>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
+                                         state, sup_base, sup_first, amax_val, amax_idx);
 }
 
 // The same kernel capped at 192 registers ("lean").  A 256-thread CTA then takes 48 K of the SM's 64 K registers, which
@@ -1001,24 +1023,26 @@ skinny_mma_lean_kernel(const float* __restrict__ X, int B, int K, const bf16* __
                        const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
                        float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     extern __shared__ __align__(16) unsigned char mm_smem[];
-    mma_stage<RW, KS, NCH, NP>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
-                                     state, sup_base, sup_first, amax_val, amax_idx);
+    mma_stage<RW, KS, NCH, NP, 4>(mm_smem, blockIdx.x, gridDim.x, X, B, K, W, N, bias, ln_w, ln_b, act, residual, Y,
+                                        state, sup_base, sup_first, amax_val, amax_idx);
 }
 
-template <int RW, int KS, int NCH, int NP = 1>
+template <int RW, int KS, int NCH, int NP = 1, int NT = 4>
 void skinny_mma_launch(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
                        const float* lb, int act, const float* residual, float* Y, bool fused_argmax = false) {
     static_assert(RW * KS == 8, "8 warps");
     WB_REQUIRE(K == KS * NP * NCH * 32, WB_EINVAL, "skinny_mma: K=%d does not match the <%d,%d,%d> instantiation", K, KS, NCH, NP);
-    const size_t smem = (size_t)(((B + 7) / 8) * 8) * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * 33 : 8 * 32 * 8);
+    constexpr int GS = NT * 8;                                           // sequences per pass (wider batches walk groups of GS)
+    WB_REQUIRE(!fused_argmax || B <= 32, WB_EINVAL, "skinny_mma: the fused arg-max serves one group of 32 sequences (B=%d)", B);
+    const size_t smem = (size_t)(((std::min(B, GS) + 7) / 8) * 8) * (K * 2 + 64) + (KS > 1 ? sizeof(float) * KS * RW * 16 * (GS + 1) : 8 * 32 * 8);
     const int tiles = ceil_div(N, RW * 16);
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     DecBufs& D = ctx->dec;
-    if (D.lean && !fused_argmax)
+    if (D.lean && !fused_argmax && NT == 4)
         launch_k(skinny_mma_lean_kernel<RW, KS, NCH, NP>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
                  act, residual, Y, (const int*)nullptr, (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p, (float*)nullptr, (int*)nullptr);
     else
-    launch_k(skinny_mma_kernel<RW, KS, NCH, NP>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
+    launch_k(skinny_mma_kernel<RW, KS, NCH, NP, NT>, dim3(grid), dim3(MM_THREADS), smem, ctx->stream, D.pdl, X, B, K, W, N, bias, lw, lb,
              act, residual, Y, (const int*)(fused_argmax ? D.amax_state : nullptr), (const unsigned*)D.sup_base.p,
              (const unsigned*)D.sup_first.p, fused_argmax ? D.amax_val : (float*)nullptr, fused_argmax ? D.amax_idx : (int*)nullptr);
     if (fused_argmax) D.amax_ctas = grid;
@@ -1032,9 +1056,10 @@ inline bool skinny_mma_enabled() {
 }
 inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W, int N, const float* bias, const float* lw,
                        const float* lb, int act, const float* residual, float* Y) {
-    if (!skinny_mma_enabled() || B > 32 || (lw && K > 1280)) return false;
+    if (!skinny_mma_enabled() || (lw && K > 1280)) return false;
+    const bool wide = B > 32;                      // 64 sequences per pass where the staged rows fit shared memory (K <= 512)
     if (K == 1280) {                               // large-v3 widths: d_model 1280 as the contraction
-        if (N >= 8192) { skinny_mma_launch<8, 1, 5, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, ctx->dec.amax_state != nullptr); return true; }
+        if (N >= 8192) { skinny_mma_launch<8, 1, 5, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, ctx->dec.amax_state != nullptr && B <= 32); return true; }
         if (N >= 2560) { skinny_mma_launch<2, 4, 10>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // qkv / fc1
         skinny_mma_launch<1, 8, 5>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true;                       // o / cq / co
     }
@@ -1044,34 +1069,44 @@ inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W,
     }
     if (lw && K > 512) return false;
     if (N >= 8192) {                               // vocabulary projection: 128 rows per CTA pass, grid-stride
-        const bool fa = ctx->dec.amax_state != nullptr;
+        const bool fa = ctx->dec.amax_state != nullptr && B <= 32;
         if (K == 512) { skinny_mma_launch<8, 1, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
         if (K == 128) { skinny_mma_launch<8, 1, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
         return false;
     }
     if (N > 1024) {                                // qkv / fc1: 64 rows per CTA, 2 k-slices
+        if (K == 512 && wide) { skinny_mma_launch<4, 2, 8, 1, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
         if (K == 512) { skinny_mma_launch<4, 2, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
         return false;
     }
+    if (wide) {
+        if (K == 512) { skinny_mma_launch<2, 4, 4, 1, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+        if (K == 128) { skinny_mma_launch<2, 4, 1, 1, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+        if (K == 256) { skinny_mma_launch<2, 4, 2, 1, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+    }
     if (K == 512) { skinny_mma_launch<2, 4, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // o / cq / co
-    if (K == 2048) { skinny_mma_launch<2, 4, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }  // fc2
+    if (K == 2048) { skinny_mma_launch<2, 4, 16>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }  // fc2: 64 staged rows of 2048 exceed shared memory, groups of 32
     if (K == 128) { skinny_mma_launch<2, 4, 1>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // toy
     if (K == 256) { skinny_mma_launch<2, 4, 2>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }    // toy ffn
     return false;
 }
 void skinny_mma_set_attrs() {       // once per process, outside any stream capture
     const int smem = 16 * (5120 * 2 + 64) + (int)sizeof(float) * 8 * 16 * 33;      // largest: fc2 of the large-v3 widths
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 5, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 10, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 5, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 5, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 16, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<8, 1, 4, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<8, 1, 5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<2, 4, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_lean_kernel<1, 8, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1109,6 +1144,8 @@ void skinny(wb_ctx* ctx, const float* X, int B, int K, const LinearW& L, const L
     const float* lw = ln ? ln->w : nullptr;
     const float* lb = ln ? ln->b : nullptr;
     const float* bias = (L.b && !W_override) ? L.b : nullptr;
+    if (sizeof(WT) == 2 &&
+        skinny_tc_launch(ctx, ctx->stream, ctx->dec.pdl, X, B, K, W, N, bias, lw, lb, act, residual, Y)) return;       // tcgen05 (vocab_tc.cu)
     if (skinny_mma(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y)) { CUDA_CHECK(cudaGetLastError()); return; }
     WB_REQUIRE(Y != nullptr, WB_EINVAL, "skinny gemm: no output buffer on the SIMT path (N=%d K=%d)", N, K);
     // rows per warp: enough CTAs to cover the chip for the per-layer GEMMs, register blocking for the vocab one
@@ -1174,12 +1211,15 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
         LinearW dummy;
         // bf16 build: arg-max partials are produced by the vocabulary projection itself (no logits round trip
         // unless the caller asked for logits); fp32 build: separate full arg-max over the logits.
-        const bool fuse = sizeof(WT) == 2 && B <= 32 && D.fuse_argmax && skinny_mma_enabled() && c.vocab >= 8192 && (d == 512 || d == 128 || d == 1280);   // shapes with an mma vocab kernel
+        const bool shapes = sizeof(WT) == 2 && D.fuse_argmax && skinny_mma_enabled() && c.vocab >= 8192 && (d == 512 || d == 128 || d == 1280);   // shapes with an mma vocab kernel
+        const bool tc = shapes && !D.want_logits && vocab_tc_ok(ctx, B);     // tcgen05 kernel: up to 64 sequences
+        const bool fuse = shapes && (B <= 32 || tc);                         // the mma.sync kernel carries partials for one group of 32
+        const int pstride = tc ? vocab_tc_stride(B) : 32;
         D.amax_state = fuse ? state : nullptr;
-        D.amax_val = D.amax_buf.p;                                           // [ctas][32] val | idx
-        D.amax_idx = reinterpret_cast<int*>(D.amax_val + (size_t)32 * ctx->sm_count);
+        D.amax_val = D.amax_buf.p;                                           // [ctas][pstride] val | idx
+        D.amax_idx = reinterpret_cast<int*>(D.amax_val + (size_t)pstride * ctx->sm_count);
         D.amax_ctas = 0;
-        if (fuse && !D.want_logits && vocab_tc_ok(ctx, B)) {
+        if (tc) {
             // tcgen05 swap-AB kernel (vocab_tc.cu): final LN + projection + per-CTA masked arg-max partials, no logits
             D.amax_ctas = vocab_tc_launch(ctx, st, pdl, state, x, B, D.amax_val, D.amax_idx); ++n;
         } else {
@@ -1188,7 +1228,7 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
         D.amax_state = nullptr;
         if (fuse && D.amax_ctas > 0) {
             launch_k(argmax_merge_kernel, dim3(B), dim3(32), 0, st, pdl, (const int*)state, (const float*)D.amax_val, (const int*)D.amax_idx,
-                     D.amax_ctas, forced_dev, max_new, eot, T_total, D.tokens.p, D.lens.p, D.finished.p, cur_tok); ++n;
+                     D.amax_ctas, pstride, forced_dev, max_new, eot, T_total, D.tokens.p, D.lens.p, D.finished.p, cur_tok); ++n;
         } else {
             launch_k(argmax_kernel, dim3(B), dim3(1024), 0, st, pdl, (const int*)state, (const float*)D.logits.p, c.vocab,
                      (const unsigned*)D.sup_base.p, (const unsigned*)D.sup_first.p, forced_dev, max_new, eot, T_total,
@@ -1219,7 +1259,7 @@ void decoder_alloc(wb_ctx* ctx) {
     D.lens.reserve(B);
     D.finished.reserve(B);
     D.state.reserve(16);
-    D.amax_buf.reserve((size_t)64 * ctx->sm_count);
+    D.amax_buf.reserve((size_t)2 * 64 * ctx->sm_count);                      // [ctas][<= 64 sequences] values | indices
     CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&D.unfinished_host), sizeof(int), cudaHostAllocMapped));
     CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&D.unfinished_dev), D.unfinished_host, 0));
     const size_t words = ((size_t)c.vocab + 31) / 32;
@@ -1434,7 +1474,7 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
                               D.tokens.p + (size_t)c.max_batch * D.last_T_total);
         } else if (k == "vocab_tc") {
             WB_REQUIRE(vocab_tc_ok(ctx, B), WB_ESTATE, "the tcgen05 vocabulary kernel is not available for this model");
-            vocab_tc_launch(ctx, ctx->stream, bench_pdl, D.state.p, D.x.p, B, D.amax_buf.p, reinterpret_cast<int*>(D.amax_buf.p + (size_t)32 * ctx->sm_count));
+            vocab_tc_launch(ctx, ctx->stream, bench_pdl, D.state.p, D.x.p, B, D.amax_buf.p, reinterpret_cast<int*>(D.amax_buf.p + (size_t)vocab_tc_stride(B) * ctx->sm_count));
         } else if (k == "vocab_proj") {
             LinearW dummy;
             if (bf) skinny<bf16>(ctx, D.x.p, B, d, dummy, &ctx->w.dec_ln, 0, nullptr, D.logits.p, c.vocab, ctx->w.embed);
