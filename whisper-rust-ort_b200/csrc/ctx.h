@@ -123,7 +123,7 @@ struct DecBufs {
     int* unfinished_host = nullptr;    // mapped: sequences still running, written at the end of a segment
     int* unfinished_dev = nullptr;
     bool pdl = false;                  // programmatic dependent launch for the decode chain
-    bool lean = false;                 // register-capped skinny GEMMs + 4-warp cross-attention (see decoder.cu)
+    int lean = 0;                      // 1: register-capped skinny GEMMs + 4-warp cross-attention (see decoder.cu)
     int self_attn_warps = 4;           // warps per (sequence, head) in the self-attention kernel (WB_SELF_ATTN_WARPS = 2 | 4 | 8)
     int* stage_host = nullptr;         // pinned staging of the per-decode control state (ids, bitmaps, lens): a pageable
     size_t stage_ints = 0;             //   source would make every cudaMemcpyAsync wait for the stream to drain first

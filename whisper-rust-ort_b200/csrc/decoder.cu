@@ -1175,6 +1175,9 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
     int* cur_tok = D.tokens.p + (size_t)c.max_batch * T_total;
     int n = 0;
     const bool pdl = D.pdl;
+    // timing experiments only (results are wrong): WB_DEC_SKIP=cross drops the cross-attention launches, =rest everything else of a layer
+    static int skip = -1;
+    if (skip < 0) { const char* e = getenv("WB_DEC_SKIP"); skip = !e ? 0 : e[0] == 'c' ? 1 : e[0] == 'r' ? 2 : e[0] == 'v' ? 3 : 0; }
     if (sizeof(WT) == 2 && dec_cluster_enabled(ctx)) {
         // bf16 build at whisper-base widths: embedding + all decoder layers in ONE launch (dec_cluster.cu).
         // The first kernel of a graph follows memcpy nodes, not a kernel: plain launch.
@@ -1185,6 +1188,10 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
             const DecLayerW& L = w.dec[l];
             WT* skv = reinterpret_cast<WT*>(D.self_kv.p) + (size_t)l * c.max_batch * D.T_max * 2 * d;
             const WT* ckv = reinterpret_cast<const WT*>(ctx->enc.ckv.p) + (size_t)l * c.max_batch * Tk * 2 * d;
+            if (skip == 2) {
+                launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean == 1); ++n;
+                continue;
+            }
             skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, D.qkv.p); ++n;                                             // K3c
             if (D.self_attn_warps == 2) launch_k(self_attn_kernel<WT, 2>, dim3(H, B), dim3(64), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);   // K3d
             else if (D.self_attn_warps == 4) launch_k(self_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);
@@ -1192,8 +1199,9 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
             ++n;
             skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, x, x); ++n;                                                      // K3f
             skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
-            if (sizeof(WT) == 2 && cross_attn_tc_ok(ctx)) cross_attn_tc(ctx, st, pdl, l, D.q.p, D.att.p, B);                // K3e
-            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean);
+            if (skip == 1) {}
+            else if (sizeof(WT) == 2 && cross_attn_tc_ok(ctx)) cross_attn_tc(ctx, st, pdl, l, D.q.p, D.att.p, B);           // K3e
+            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean == 1);
             ++n;
             skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, x, x); ++n;
             skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                                               // K3g
@@ -1219,7 +1227,8 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
         D.amax_val = D.amax_buf.p;                                           // [ctas][pstride] val | idx
         D.amax_idx = reinterpret_cast<int*>(D.amax_val + (size_t)pstride * ctx->sm_count);
         D.amax_ctas = 0;
-        if (tc) {
+        if (skip == 3) {
+        } else if (tc) {
             // tcgen05 swap-AB kernel (vocab_tc.cu): final LN + projection + per-CTA masked arg-max partials, no logits
             D.amax_ctas = vocab_tc_launch(ctx, st, pdl, state, x, B, D.amax_val, D.amax_idx); ++n;
         } else {
@@ -1266,8 +1275,8 @@ void decoder_alloc(wb_ctx* ctx) {
     D.sup_base.reserve(words);
     D.sup_first.reserve(words);
     if (c.precision == WB_PREC_BF16) { set_func_attrs<bf16>(); skinny_mma_set_attrs(); } else set_func_attrs<float>();
-    D.lean = false;                    // WB_DEC_LEAN=1: 192-register GEMM kernels + 4-warp cross-attention CTAs (co-residency across batches in flight)
-    if (const char* e = getenv("WB_DEC_LEAN")) D.lean = e[0] == '1';
+    D.lean = 0;                        // WB_DEC_LEAN=1: register-capped GEMM kernels + 4-warp cross-attention CTAs (co-residency across batches in flight); 2: the GEMM kernels only
+    if (const char* e = getenv("WB_DEC_LEAN")) D.lean = e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0;
     D.self_attn_warps = 4;            // measured: 4 warps is the best of 2 / 4 / 8 both for one batch alone and for 8 in flight
     if (const char* e = getenv("WB_SELF_ATTN_WARPS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) D.self_attn_warps = v; }
     vocab_tc_alloc(ctx);
@@ -1460,7 +1469,7 @@ void decoder_bench(wb_ctx* ctx, const char* kernel, int B, int iters, float* avg
         if (k == "cross_attn") {
             const char* ckv = (const char*)ctx->enc.ckv.p + (size_t)l * c.max_batch * c.n_audio_ctx * 2 * d * ctx->esz();
             if (bf && cross_attn_tc_ok(ctx) && Tk == c.n_audio_ctx) cross_attn_tc(ctx, ctx->stream, bench_pdl, l, D.q.p, D.att.p, B);
-            else if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk, D.lean);
+            else if (bf) launch_cross_attn<bf16>(ctx->stream, bench_pdl, D.q.p, (const bf16*)ckv, D.att.p, H, B, d, Tk, D.lean == 1);
             else launch_cross_attn<float>(ctx->stream, bench_pdl, D.q.p, (const float*)ckv, D.att.p, H, B, d, Tk);
         } else if (k == "dec_layers") {
             WB_REQUIRE(bf && dec_cluster_enabled(ctx), WB_EINVAL, "dec_layers: the cluster-chained layer kernel is not active for this context");
