@@ -19,7 +19,7 @@ constexpr int AQ = 128, AK = 128, HD = 64;
 constexpr int ATT_THREADS = 288;                       // warp 0: TMA + MMA issue; warps 1-8: softmax / epilogue
 constexpr uint32_t TILE_BYTES = 128 * 64 * 2;          // one [128 x 64] bf16 tile, 128-byte rows
 constexpr uint32_t ATT_TMEM_COLS = 256;                // S: [0,128)  O_j: [128,192)
-constexpr size_t ATT_SMEM = 6 * TILE_BYTES + 1024 + 128;   // Q, K[2], V, P[2 halves]: 97 KB -> two CTAs per SM
+constexpr size_t ATT_SMEM = 6 * TILE_BYTES + 1024 + 128;   // Q, K[2], V, P[2 halves] + barriers: 97 KB -> two CTAs per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -356,8 +356,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 2^x on the FMA pipe: round-to-nearest split x = xi + f (|f| <= 0.5) with the 1.5 * 2^23 trick, minimax cubic for 2^f
+// (relative error 7.5e-5, below the bf16 rounding of P: 2e-3), xi added straight into the exponent field.  The MUFU unit
+// does 16 ex2 per clock and SM, the FMA pipe 128 lanes: moving a fraction of the exponentials here lifts the softmax
+// bound of a head-dim-64 attention (one exponential per 128 tensor-core flops).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -120.0f);
+    const float r = x + 12582912.0f;
+    const float f = x - (r - 12582912.0f);
+    float p = fmaf(f, 0.05517167f, 0.24261112f);
+    p = fmaf(p, f, 0.69326099f);
+    p = fmaf(p, f, 0.99992807f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+// PF of every 8 exponentials go to the polynomial, evenly spread
+__device__ __forceinline__ constexpr bool poly_slot(int i, int PF) { return ((i + 1) * PF) / 8 != (i * PF) / 8; }
+
 // p = exp2(s * sc - m) of the 64 scores a thread holds in registers -> bf16 -> swizzled P row; returns their f32 sum.
-template <bool MASK>
+template <bool MASK, int PF>
 __device__ __forceinline__ float exp_store_regs(const uint32_t (&r)[64], int valid, float sc, float m, uint8_t* prow, int sw) {
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
@@ -366,8 +382,9 @@ __device__ __forceinline__ float exp_store_regs(const uint32_t (&r)[64], int val
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = c2 * 32 + 2 * i;
-            float p0 = ex2(fmaf(__uint_as_float(r[e]), sc, -m));
-            float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), sc, -m));
+            const float x0 = fmaf(__uint_as_float(r[e]), sc, -m), x1 = fmaf(__uint_as_float(r[e + 1]), sc, -m);
+            float p0 = poly_slot(e & 7, PF) ? ex2_poly(x0) : ex2(x0);
+            float p1 = poly_slot((e + 1) & 7, PF) ? ex2_poly(x1) : ex2(x1);
             if (MASK) {
                 if (e >= valid) p0 = 0.f;
                 if (e + 1 >= valid) p1 = 0.f;
@@ -386,8 +403,15 @@ __device__ __forceinline__ float exp_store_regs(const uint32_t (&r)[64], int val
     return sum0 + sum1;
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 constexpr float ATT_RESCALE_LOG2 = 8.0f;               // the stale maximum may lag the true one by 2^8 (p <= 256: exact in f32 sums, same relative precision in bf16)
 
+template <int PF>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int d, int H, int n_qb) {
     extern __shared__ uint8_t smem_raw[];
@@ -405,7 +429,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     uint64_t* bar_p = bars + 6;
     uint64_t* bar_o = bars + 7;        // P_j V_j retired == V tile and P tile free, O stable
     uint64_t* bar_v = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* bar_sfree = bars + 9;    // all 256 softmax threads hold S_j in registers: the S columns may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     __shared__ float s_xmax[2][2][128];
     __shared__ float s_xl[2][128];
@@ -419,7 +444,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             mbar_init(bar_q, 1);
             mbar_init(&bar_k[0], 1); mbar_init(&bar_k[1], 1);
             mbar_init(&bar_kfree[0], 1); mbar_init(&bar_kfree[1], 1);
-            mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1); mbar_init(bar_v, 1);
+            mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1); mbar_init(bar_v, 1); mbar_init(bar_sfree, 256);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -465,11 +490,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             issue_s(0);
             if (n_kb > 1) load_k(1);
             for (int j = 0; j < n_kb; ++j) {
-                mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, S_j consumed, O rescaled if it had to be
+                // S_{j+1} is issued as soon as S_j sits in the softmax threads' registers, i.e. under the exponentials of
+                // block j (ncu on the first cut of this kernel: 20 % of all warp samples were softmax warps waiting for S)
                 if (j + 1 < n_kb) {
+                    mbar_wait(bar_sfree, (uint32_t)(j & 1));
                     issue_s(j + 1);
                     if (j + 2 < n_kb) load_k(j + 2);
                 }
+                mbar_wait(bar_p, (uint32_t)(j & 1));                     // P_j in smem, O rescaled if it had to be
                 mbar_wait(bar_v, (uint32_t)(j & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -503,10 +531,17 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             tmem_ld32_nowait(tS + lane_off + half * 64, r);
             tmem_ld32_nowait(tS + lane_off + half * 64 + 32, r + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_sfree);                                      // S_j is in registers
             float mx = -INFINITY;
             if (valid >= 64) {
+                float mx2 = -INFINITY;                                   // two chains of 3-input maxima (FMNMX3): 32 instructions for 64 scores
 #pragma unroll
-                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                for (int i = 0; i < 64; i += 4) {
+                    mx = max3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                    mx2 = max3(mx2, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
+                mx = fmaxf(mx, mx2);
             } else {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
@@ -542,7 +577,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
                     l *= alpha;
                 }
             }
-            const float sum = valid >= 64 ? exp_store_regs<false>(r, valid, sc, m_used, prow, sw) : exp_store_regs<true>(r, valid, sc, m_used, prow, sw);
+            const float sum = valid >= 64 ? exp_store_regs<false, PF>(r, valid, sc, m_used, prow, sw) : exp_store_regs<true, PF>(r, valid, sc, m_used, prow, sw);
             l += sum;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -595,7 +630,11 @@ bool attn_tc_enabled() {
 
 void attn_tc_set_attrs() {           // per context / device, from wb_create (see mel_set_attrs)
     CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
 }
 
 // qkv: [B][T][3d] bf16 (q | k | v), out: [B][T][d] bf16.
@@ -617,9 +656,21 @@ void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WB_REQUIRE(r == CUDA_SUCCESS, WB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     const int n_qb = ceil_div(T, AQ);
-    static int version = 0;
-    if (!version) { const char* e = getenv("WB_ATTN_V"); version = (e && e[0] == '1') ? 1 : 2; }
-    if (version == 1) attn_tc_kernel<<<B * H * n_qb, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, (__nv_bfloat16*)out, T, d, H, n_qb);
-    else attn_tc2_kernel<<<B * H * n_qb, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, (__nv_bfloat16*)out, T, d, H, n_qb);
+    static int version = 0, poly = 0;
+    if (!version) {
+        const char* e = getenv("WB_ATTN_V");
+        version = (e && e[0] == '1') ? 1 : 2;
+        const char* pe = getenv("WB_ATTN_POLY");            // exponentials per 8 that go to the FMA-pipe polynomial (0 .. 4)
+        poly = pe ? atoi(pe) : 0;
+        if (poly < 0 || poly > 4) poly = 0;
+    }
+    const dim3 grid(B * H * n_qb);
+    __nv_bfloat16* o = (__nv_bfloat16*)out;
+    if (version == 1) attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 1) attn_tc2_kernel<1><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 2) attn_tc2_kernel<2><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 3) attn_tc2_kernel<3><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 4) attn_tc2_kernel<4><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else attn_tc2_kernel<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
     CUDA_CHECK(cudaGetLastError());
 }
