@@ -493,6 +493,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[1] / configs[2] side measurements")
     args = ap.parse_args()
+    # timing probes that drop work from a decode step (tools/gpu_probe.py) must never reach a bench line
+    for probe in ("WB_DEC_SKIP",):
+        if os.environ.get(probe):
+            raise SystemExit(f"bench.py: refusing to run with {probe} set (it skips kernels inside the timed region)")
     if args.batch is None:
         args.batch = ARCHS[args.arch]["batch"]
     rank = int(os.environ.get("RANK", "0"))
