@@ -43,7 +43,6 @@ struct TcArgs {
     const float* residual;
     int tiles_m, tiles_n, num_tiles, num_kb;
     int tma_store;              // bf16 output without residual: tiles leave through shared memory + TMA (coalesced)
-    int res_prefetch;           // f32 residual fetched ahead of the accumulator wait (WB_TC_RESPRE)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -219,21 +218,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nb = t % a.tiles_n, rest = t / a.tiles_n, mb = rest % a.tiles_m, z = rest / a.tiles_m;
             const int acc = it & 1;
             const uint32_t use = (uint32_t)(it >> 1);
+            mbar_wait(&tfull[acc], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int gm = mb * BM + row_in_tile;
             const bool row_ok = gm < a.M;
             const long long crow = (long long)z * a.sC + (long long)gm * a.ldc;
-            // the residual does not depend on the accumulator: the first chunk's 128 bytes per row leave before the wait for
-            // the MMAs, the next chunk's while the current one is processed (8 warps x 8 loads in flight could not hide a
-            // DRAM round trip per chunk: the N = 512 GEMMs with an f32 residual were epilogue-bound)
-            float4 res[8];
-            const bool pre = a.res_prefetch && a.residual != nullptr && row_ok && !a.tma_store;
-            if (pre) {
-                const float4* p = reinterpret_cast<const float4*>(a.residual + crow + nb * BN + chalf * NCH * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) res[j] = p[j];
-            }
-            mbar_wait(&tfull[acc], use & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (a.tma_store) {
                 // bf16 tile out through shared memory: a thread owns one row x 64 columns = eight 16-byte chunks, written
                 // in the 128B-swizzle pattern (conflict-free), then one TMA store per 128x64 half; rows >= M are clipped
@@ -300,12 +289,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(q * 32) << 16), r);
                 const int gn0 = nb * BN + ch * 32;
-                float4 nxt[8];
-                if (pre && ch + 1 < (chalf + 1) * NCH) {
-                    const float4* p = reinterpret_cast<const float4*>(a.residual + crow + gn0 + 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) nxt[j] = p[j];
-                }
                 if (row_ok) {
                     float v[32];
 #pragma unroll
@@ -332,13 +315,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 8; ++j) { float4 t4 = __ldg(p + j); v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
                     }
                     if (a.residual) {
-                        if (!pre) {
-                            const float4* p = reinterpret_cast<const float4*>(a.residual + crow + gn0);
+                        const float4* p = reinterpret_cast<const float4*>(a.residual + crow + gn0);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) res[j] = p[j];
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w; }
+                        for (int j = 0; j < 8; ++j) { float4 t4 = p[j]; v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w; }
                     }
                     if (a.tc == WB_F32) {
                         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.C) + crow + gn0);
@@ -357,8 +336,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) res[j] = nxt[j];
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty[acc]);                                    // 256 arrivals release the accumulator
@@ -448,9 +425,6 @@ void gemm_tc(wb_ctx* ctx, const GemmArgs& g) {
     }
     TcArgs a{};
     a.tma_store = tma_store ? 1 : 0;
-    static int respre = -1;
-    if (respre < 0) { const char* e = getenv("WB_TC_RESPRE"); respre = (e && e[0] == '1') ? 1 : 0; }
-    a.res_prefetch = respre;
     a.C = g.C; a.tc = g.tc; a.M = g.M; a.N = g.N; a.K = g.K; a.ldc = g.ldc; a.sC = g.sCo;
     a.bias = g.bias; a.act = g.act; a.rowadd = g.rowadd; a.ld_rowadd = g.ld_rowadd; a.residual = g.residual;
     a.tiles_m = ceil_div(g.M, BM); a.tiles_n = g.N / BN; a.num_tiles = a.tiles_m * a.tiles_n * g.batch;
