@@ -10,8 +10,10 @@ One "step" = one pass of the hot path over one batch of 32 synthetic 30 s clips 
 chain of small dependent kernels that leaves most SMs idle (`single_batch_in_flight` reports S = 1; one B200:
 S = 1 / 2 / 4 / 6 / 8 -> 18.1 / 26.6 / 32.6 / 34.6 / 35.8 k audio-s/s, profiles/r2_inflight.json).
 `value`  : whole-job audio-s/s with the PCM already resident in HBM (device-timed, max over ranks).
-`e2e`    : same metric through the reference-facing C ABI call wb_transcribe_batch with HOST
-           (pinned) PCM buffers — H2D of the PCM and D2H of the token ids inside the timed region.
+`e2e`    : same metric through the reference-facing C ABI with HOST (pinned) PCM buffers — H2D of the PCM and D2H of
+           the token ids inside the timed region — driven the way the reference's single-threaded main would: ONE host
+           thread, ONE wb_pool handle with S slots (wb_pool_submit / wb_pool_wait);  `e2e.per_context_host_threads` is
+           the same with S host threads calling wb_transcribe_batch on a wb_ctx each (p95 per-clip latency comes from there).
 `roofline`: dominant kernel (decoder cross-attention, HBM-bound) against MEASURED_PEAKS.json, replayed on live
            buffers the way the product launches it (programmatic dependent launch).
 `cpu_baseline`: the CPU oracle port (C log-mel + numpy Whisper) on a bounded sample, rank 0, N=1.
@@ -401,6 +403,27 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = audio_s / e2e_s
     p95 = dist_max(float(np.percentile(lat, 95)), dist, dev)
 
+    # ---- the same through ONE handle driven by ONE host thread (wb_pool: S slots, worker threads inside the library) ----
+    pool_value = None
+    if not args.no_pool:
+        pool = wb200.Pool(wb200.default_cfg(A["cfg"], precision=prec, max_batch=B, max_chunks=B), S, device=local_rank)
+        def pool_steps(n_steps):
+            tickets = []
+            for k in range(n_steps):
+                if len(tickets) >= 2 * S:                        # a bounded window of tickets, collected in order
+                    pool.wait(tickets.pop(0))
+                tickets.append(pool.submit_ptr(pinned[k % S].data_ptr(), B, n_clip, PROMPT, MAX_NEW, EOT, sup, bsup))
+            for t in tickets:
+                pool.wait(t)
+        pool_steps(max(1, args.warmup // 2) * S)
+        barrier()
+        t0 = time.perf_counter()
+        pool_steps(args.steps)
+        barrier()
+        pool_s = dist_max(time.perf_counter() - t0, dist, dev)
+        pool_value = audio_s / pool_s
+        pool.close()
+
     # ---- one batch at a time on an otherwise idle GPU: the latency-optimal operating point ----
     barrier()
     t0 = time.perf_counter()
@@ -436,8 +459,16 @@ def run_ours(args, rank, world, local_rank):
                        "weights": f"seeded random-init {A['name']} (no checkpoint offline)",
                        "l2": "working set per step (PCM 1.9 MB/clip + weights >= 145 MB + cross-K/V >= 18 MB/clip) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"clips sharded over {world} GPU(s), one process per GPU, no collective on the data path"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned[0].numel() * 4) * world,
-                    "d2h_bytes_per_step": int(B * (len(PROMPT) + MAX_NEW) * 8 + B * 4) * world, "p95_latency_s_per_clip": p95},
+            # headline e2e = what a single-threaded host (the reference's fn main) gets from ONE handle: wb_pool with S slots;
+            # the S-host-threads figure (one wb_ctx each, where p95 per-clip latency is taken) is kept beside it
+            "e2e": {"value": pool_value if pool_value is not None else e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(pinned[0].numel() * 4) * world,
+                    "d2h_bytes_per_step": int(B * (len(PROMPT) + MAX_NEW) * 8 + B * 4) * world,
+                    "driver": (f"one host thread, one wb_pool handle with {S} slots (wb_pool_submit / wb_pool_wait)" if pool_value is not None
+                               else f"{S} host threads, one wb_ctx each (wb_transcribe_batch)"),
+                    "p95_latency_s_per_clip": p95,
+                    "per_context_host_threads": {"value": e2e_value, "unit": UNIT, "driver": f"{S} host threads, one wb_ctx each (wb_transcribe_batch)",
+                                                 "p95_latency_s_per_clip": p95}},
             "single_batch_in_flight": {"value": B * CLIP_S / single_s, "unit": UNIT, "latency_s_per_clip": single_s,
                                        "stage_ms": {k: tm1[k] for k in ("mel_ms", "encoder_ms", "cross_kv_ms", "decode_ms")}},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -491,6 +522,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("WB_BENCH_IN_FLIGHT", "8")),
                     help="independent batches of --batch clips in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pool", action="store_true", help="skip the single-host-thread wb_pool leg of e2e")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[1] / configs[2] side measurements")
     args = ap.parse_args()
     # timing probes that drop work from a decode step (tools/gpu_probe.py) must never reach a bench line

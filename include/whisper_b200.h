@@ -141,6 +141,28 @@ int wb_transcribe_resident(wb_ctx* ctx, const int64_t* prompt, int prompt_len, i
                            const int64_t* begin_suppress, int n_begin_suppress,
                            int64_t* tokens_out, int32_t* lens_out, int cap_chunks);
 
+/* ---- batch scheduler behind one handle (north_star (4); replaces the serial per-file loop main.rs:1161-1210) ----
+ * A decode is a chain of small dependent kernels, so a GPU reaches its throughput only with several independent
+ * batches in flight.  A wb_ctx is ONE batch slot and its calls block; a wb_pool owns n_slots contexts on one device
+ * (one shared copy of the weights) plus a worker thread per slot, so that a single-threaded host submits batches
+ * without blocking and collects them by ticket.
+ * wb_pool_submit: arguments as wb_transcribe_batch; returns a ticket >= 0 (or a negative WB_E* code), blocks only while
+ *   n_slots tickets are already waiting for a slot.  pcm / offsets / the output arrays must stay valid until the ticket
+ *   has been collected; prompt and suppress lists are copied.
+ * wb_pool_wait: blocks until that batch is done, returns its status (the message of a failed batch is then in
+ *   wb_last_error() of the calling thread) and the chunks it produced.  Each ticket is collected exactly once, in any order.
+ * wb_pool_destroy completes queued work first. */
+typedef struct wb_pool wb_pool;
+int wb_pool_create(wb_pool** out, int device, const wb_model_cfg* cfg, const char* weights_path, int n_slots);
+void wb_pool_destroy(wb_pool* pool);
+int wb_pool_slots(const wb_pool* pool);
+int wb_pool_submit(wb_pool* pool, const float* pcm, const int64_t* offsets, int n_files,
+                   const int64_t* prompt, int prompt_len, int max_new_tokens, int64_t eot,
+                   const int64_t* suppress, int n_suppress,
+                   const int64_t* begin_suppress, int n_begin_suppress,
+                   int64_t* tokens_out, int32_t* lens_out, int32_t* file_idx_out, int cap_chunks);
+int wb_pool_wait(wb_pool* pool, int ticket, int* n_chunks_out);
+
 /* ---- measurement hooks (bench.py): CUDA events on the library's own stream ---- */
 int wb_mark(wb_ctx* ctx, int slot /* 0..7 */);
 int wb_elapsed_ms(wb_ctx* ctx, int slot_a, int slot_b, float* ms_out);   /* syncs on slot_b */

@@ -72,6 +72,10 @@ def lib():
         "wb_greedy_decode": [vp, ci, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, i64p, f32p],
         "wb_transcribe_batch": [vp, f32p, i64p, ci, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, i32p, ci, C.POINTER(ci)],
         "wb_transcribe_resident": [vp, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, ci],
+        "wb_pool_create": [C.POINTER(vp), ci, C.POINTER(wb_model_cfg), cp, ci],
+        "wb_pool_slots": [vp],
+        "wb_pool_submit": [vp, f32p, i64p, ci, i64p, ci, ci, C.c_int64, i64p, ci, i64p, ci, i64p, i32p, i32p, ci],
+        "wb_pool_wait": [vp, ci, C.POINTER(ci)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -79,6 +83,8 @@ def lib():
         fn.restype = ci
     L.wb_destroy.argtypes = [vp]
     L.wb_destroy.restype = None
+    L.wb_pool_destroy.argtypes = [vp]
+    L.wb_pool_destroy.restype = None
     _lib = L
     return L
 
@@ -318,3 +324,64 @@ class Whisper:
         out = np.empty(shape, np.float32)
         _chk(self.L.wb_get_tensor(self.h, name.encode(), out.ctypes.data_as(f32p), out.size))
         return out
+
+
+class Pool:
+    """wb_pool: one handle, n_slots batches in flight on one GPU, driven from a single host thread.
+
+    submit() returns a ticket at once (it blocks only while n_slots batches are already queued); wait(ticket) returns
+    that batch's token lists.  The PCM of a submitted batch must stay alive until its ticket has been collected: the
+    pool keeps a reference to whatever array / pointer owner was passed."""
+
+    def __init__(self, cfg: wb_model_cfg, n_slots: int, device: int = 0, weights_path: str | None = None):
+        self.L = lib()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        self._live = {}
+        _chk(self.L.wb_pool_create(C.byref(self.h), device, C.byref(self.cfg), weights_path.encode() if weights_path else None, n_slots))
+
+    @property
+    def slots(self) -> int:
+        return int(self.L.wb_pool_slots(self.h))
+
+    def submit_ptr(self, pcm_ptr: int, n_clips: int, clip_len: int, prompt, max_new_tokens, eot, suppress=(), begin_suppress=(), keep=None) -> int:
+        """Equal-length clips in caller memory (e.g. a pinned host buffer); `keep` is held until the ticket is collected."""
+        offs = np.arange(n_clips + 1, dtype=np.int64) * clip_len
+        prompt, pp = _i64(prompt)
+        sup, sp = _i64(list(suppress))
+        bsup, bp = _i64(list(begin_suppress))
+        cap = self.cfg.max_chunks
+        stride = len(prompt) + max(1, max_new_tokens)
+        toks = np.full((cap, stride), -1, np.int64)
+        lens, fidx = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        t = self.L.wb_pool_submit(self.h, C.cast(pcm_ptr, f32p), offs.ctypes.data_as(i64p), n_clips, pp, len(prompt), max_new_tokens, eot,
+                                  sp, len(sup), bp, len(bsup), toks.ctypes.data_as(i64p), lens.ctypes.data_as(i32p),
+                                  fidx.ctypes.data_as(i32p), cap)
+        if t < 0:
+            _chk(t)
+        self._live[t] = (keep, offs, toks, lens, fidx)
+        return t
+
+    def submit(self, clips, prompt, max_new_tokens, eot, suppress=(), begin_suppress=()) -> int:
+        flat = np.ascontiguousarray(np.stack([np.asarray(c, np.float32) for c in clips]))
+        return self.submit_ptr(flat.ctypes.data, flat.shape[0], flat.shape[1], prompt, max_new_tokens, eot, suppress, begin_suppress, keep=flat)
+
+    def wait(self, ticket: int):
+        """-> (token lists per chunk, file index per chunk)"""
+        n = C.c_int(0)
+        rc = self.L.wb_pool_wait(self.h, ticket, C.byref(n))
+        _, _, toks, lens, fidx = self._live.pop(ticket, (None, None, None, None, None))
+        _chk(rc)
+        return [toks[i, :lens[i]].tolist() for i in range(n.value)], fidx[:n.value].copy()
+
+    def close(self):
+        if self.h:
+            self.L.wb_pool_destroy(self.h)
+            self.h = C.c_void_p()
+            self._live.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
