@@ -102,3 +102,24 @@ def test_wide_batch_toy_widths(wb):
     hi = m.greedy_decode(16, [1, 2, 3, 4], 20, 1030, [5], [6, 7])
     assert lo + hi == a
     m.close()
+
+
+def test_batch_above_64_falls_back_to_the_logits_path(wb):
+    """Above 64 sequences the tcgen05 vocabulary kernel does not apply: the GEMMs walk two groups of 64 (fc2: three of
+    32) and the arg-max runs over written logits.  Same tokens as the first 32 sequences decoded on their own wherever
+    the top-1 margin is clear."""
+    B = 72
+    m = wb.Whisper(wb.default_cfg("base", precision=wb.WB_PREC_BF16, max_batch=B, max_chunks=B))
+    mel = np.random.default_rng(21).normal(0.0, 0.6, (B, 80, 3000)).astype(np.float32)
+    m.encode(mel, want_hidden=False)
+    n_new = 6
+    a = m.greedy_decode(B, PROMPT, n_new, EOT)
+    forced = np.array([s[4:] for s in a])
+    _, big = m.greedy_decode(B, PROMPT, n_new, EOT, forced=forced, want_logits=True)
+    top2 = np.sort(np.partition(big, -2, axis=-1)[..., -2:], -1)
+    clear = (top2[..., 1] - top2[..., 0]) > 2e-2
+    assert np.all(big.argmax(-1)[clear] == forced[clear])
+    m.encode(mel[:32], want_hidden=False)
+    _, small = m.greedy_decode(32, PROMPT, n_new, EOT, forced=forced[:32], want_logits=True)
+    assert np.abs(small - big[:32]).max() <= 2e-2
+    m.close()

@@ -372,33 +372,25 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // PF of every 8 exponentials go to the polynomial, evenly spread
 __device__ __forceinline__ constexpr bool poly_slot(int i, int PF) { return ((i + 1) * PF) / 8 != (i * PF) / 8; }
 
-// p = exp2(s * sc - m) of the 64 scores a thread holds in registers -> bf16 -> swizzled P row; returns their f32 sum.
+// p = exp2(s * sc - m) of the 64 scores a thread holds in registers -> bf16 pairs in pk[32]; returns their f32 sum.
+// (Packing first and storing later lets the caller wait for the P tile to become free AFTER the exponentials.)
 template <bool MASK, int PF>
-__device__ __forceinline__ float exp_store_regs(const uint32_t (&r)[64], int valid, float sc, float m, uint8_t* prow, int sw) {
+__device__ __forceinline__ float exp_pack_regs(const uint32_t (&r)[64], int valid, float sc, float m, uint32_t (&pk)[32]) {
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int e = c2 * 32 + 2 * i;
-            const float x0 = fmaf(__uint_as_float(r[e]), sc, -m), x1 = fmaf(__uint_as_float(r[e + 1]), sc, -m);
-            float p0 = poly_slot(e & 7, PF) ? ex2_poly(x0) : ex2(x0);
-            float p1 = poly_slot((e + 1) & 7, PF) ? ex2_poly(x1) : ex2(x1);
-            if (MASK) {
-                if (e >= valid) p0 = 0.f;
-                if (e + 1 >= valid) p1 = 0.f;
-            }
-            sum0 += p0;
-            sum1 += p1;
-            __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&pb);
+    for (int i = 0; i < 32; ++i) {
+        const int e = 2 * i;
+        const float x0 = fmaf(__uint_as_float(r[e]), sc, -m), x1 = fmaf(__uint_as_float(r[e + 1]), sc, -m);
+        float p0 = poly_slot(e & 7, PF) ? ex2_poly(x0) : ex2(x0);
+        float p1 = poly_slot((e + 1) & 7, PF) ? ex2_poly(x1) : ex2(x1);
+        if (MASK) {
+            if (e >= valid) p0 = 0.f;
+            if (e + 1 >= valid) p1 = 0.f;
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int chunk = c2 * 4 + c;
-            *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        }
+        sum0 += p0;
+        sum1 += p1;
+        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&pb);
     }
     return sum0 + sum1;
 }
@@ -411,7 +403,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 
 constexpr float ATT_RESCALE_LOG2 = 8.0f;               // the stale maximum may lag the true one by 2^8 (p <= 256: exact in f32 sums, same relative precision in bf16)
 
-template <int PF>
+template <int PF, bool LATE>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int d, int H, int n_qb) {
     extern __shared__ uint8_t smem_raw[];
@@ -551,18 +543,27 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]);
             const float m_cand = mx * sc;
-            // P is single-buffered and O must be stable: P_{j-1} V_{j-1} has to retire before either is touched
-            if (j > 0) mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+            // the maximum the exponentials use: moved only when the true one has grown by more than 2^8 (decided here, the
+            // matching rescale of O in TMEM waits until P_{j-1} V_{j-1} has retired, below)
+            float alpha = 1.0f;
+            bool grow = false;
             if (j == 0) {
                 m_used = m_cand;
             } else {
-                const bool grow = m_cand > m_used + ATT_RESCALE_LOG2;
+                grow = m_cand > m_used + ATT_RESCALE_LOG2;
+                if (grow) { alpha = ex2(m_used - m_cand); m_used = m_cand; l *= alpha; }
+            }
+            uint32_t pk[32];
+            float sum = 0.f;
+            if (LATE) sum = valid >= 64 ? exp_pack_regs<false, PF>(r, valid, sc, m_used, pk) : exp_pack_regs<true, PF>(r, valid, sc, m_used, pk);
+            // P is single-buffered and O must be stable: P_{j-1} V_{j-1} has to retire before either is touched -- by now it
+            // has had the 64 exponentials of this block to do so (ncu before this reordering: 9.5 % of the samples here)
+            if (j > 0) {
+                mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
                 if (__any_sync(0xffffffffu, grow)) {                     // rare after the first blocks
-                    const float alpha = grow ? ex2(m_used - m_cand) : 1.0f;
-                    if (grow) m_used = m_cand;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {                        // 8 columns at a time: the 64 scores stay in registers
+                    for (int c = 0; c < 4; ++c) {                        // 8 columns at a time: few live registers
                         uint32_t o[8];
                         const uint32_t ta = tO + lane_off + half * 32 + c * 8;
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -574,10 +575,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
                                      ::"r"(ta), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    l *= alpha;
                 }
             }
-            const float sum = valid >= 64 ? exp_store_regs<false, PF>(r, valid, sc, m_used, prow, sw) : exp_store_regs<true, PF>(r, valid, sc, m_used, prow, sw);
+            if (!LATE) sum = valid >= 64 ? exp_pack_regs<false, PF>(r, valid, sc, m_used, pk) : exp_pack_regs<true, PF>(r, valid, sc, m_used, pk);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             l += sum;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -630,11 +633,12 @@ bool attn_tc_enabled() {
 
 void attn_tc_set_attrs() {           // per context / device, from wb_create (see mel_set_attrs)
     CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
 }
 
 // qkv: [B][T][3d] bf16 (q | k | v), out: [B][T][d] bf16.
@@ -656,21 +660,24 @@ void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WB_REQUIRE(r == CUDA_SUCCESS, WB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     const int n_qb = ceil_div(T, AQ);
-    static int version = 0, poly = 0;
+    static int version = 0, poly = 0, late = 0;
     if (!version) {
         const char* e = getenv("WB_ATTN_V");
         version = (e && e[0] == '1') ? 1 : 2;
         const char* pe = getenv("WB_ATTN_POLY");            // exponentials per 8 that go to the FMA-pipe polynomial (0 .. 4)
         poly = pe ? atoi(pe) : 0;
         if (poly < 0 || poly > 4) poly = 0;
+        const char* le = getenv("WB_ATTN_LATE");            // 1: exponentials before the wait for the P tile
+        late = (le && le[0] == '1') ? 1 : 0;
     }
     const dim3 grid(B * H * n_qb);
     __nv_bfloat16* o = (__nv_bfloat16*)out;
     if (version == 1) attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
-    else if (poly == 1) attn_tc2_kernel<1><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
-    else if (poly == 2) attn_tc2_kernel<2><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
-    else if (poly == 3) attn_tc2_kernel<3><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
-    else if (poly == 4) attn_tc2_kernel<4><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
-    else attn_tc2_kernel<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 1) attn_tc2_kernel<1, false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 2) attn_tc2_kernel<2, false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 3) attn_tc2_kernel<3, false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (poly == 4) attn_tc2_kernel<4, false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else if (late) attn_tc2_kernel<0, true><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
+    else attn_tc2_kernel<0, false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);
     CUDA_CHECK(cudaGetLastError());
 }
