@@ -1,7 +1,10 @@
-"""GPU: the optional decode kernels of dec_cluster.cu (switched on per context through the environment at wb_create):
-  WB_DEC_CLUSTER=1  all decoder layers of a step in one cluster-chained launch (dec_layers_kernel)
+"""GPU: the optional decode kernels (switched on per context through the environment at wb_create):
+  WB_DEC_CLUSTER=1  all decoder layers of a step in one cluster-chained launch (dec_layers_kernel, dec_cluster.cu)
   WB_DEC_VOCAB=1    final LayerNorm + vocabulary projection + masked arg-max + token bookkeeping in one launch
   WB_XATTN_TC=1     stand-alone cross-attention on the TMA ring + tensor cores
+  WB_SKINNY_TC=1    per-layer decode GEMMs on tcgen05 (skinny_tc_kernel, vocab_tc.cu)
+  WB_DEC_LEAN=2     register-capped mma.sync decode GEMMs
+Process-wide switches (read once per process) are covered by tests/test_gpu_switches.py in subprocesses.
 Each is held to the same bar as the default bf16 path: teacher-forced logits within 5e-2 of the fp32 oracle
 (/root/reference/src/main.rs:753-829 restated in oracle/whisper_ref.py), arg-max identical wherever the oracle's margin is
 clear of bf16 noise, results independent of the batch position, eos / suppress bookkeeping identical to the default path."""
@@ -15,11 +18,14 @@ import whisper_ref as wr
 
 pytestmark = pytest.mark.gpu
 EOT = 50257
-VARIANTS = [{"WB_DEC_CLUSTER": "1", "WB_DEC_VOCAB": "1"}, {"WB_DEC_VOCAB": "1"}, {"WB_XATTN_TC": "1"}, {"WB_DEC_CLUSTER": "1"}]
+VARIANTS = [{"WB_DEC_CLUSTER": "1", "WB_DEC_VOCAB": "1"}, {"WB_DEC_VOCAB": "1"}, {"WB_XATTN_TC": "1"}, {"WB_DEC_CLUSTER": "1"},
+            {"WB_SKINNY_TC": "1"},          # vocab_tc.cu: the per-layer decode GEMMs on tcgen05 (measured slower, kept as a record)
+            {"WB_DEC_LEAN": "2"}]           # register-capped decode GEMM kernels
+SWITCHES = ("WB_DEC_CLUSTER", "WB_DEC_VOCAB", "WB_XATTN_TC", "WB_SKINNY_TC", "WB_DEC_LEAN")
 
 
 def make(wb, env, batch):
-    old = {k: os.environ.get(k) for k in ("WB_DEC_CLUSTER", "WB_DEC_VOCAB", "WB_XATTN_TC")}
+    old = {k: os.environ.get(k) for k in SWITCHES}
     for k in old:
         os.environ.pop(k, None)
     os.environ.update(env)
