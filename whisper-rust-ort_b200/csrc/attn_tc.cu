@@ -660,16 +660,20 @@ void attn_tc(wb_ctx* ctx, const void* qkv, void* out, int B, int T, int d, int H
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     WB_REQUIRE(r == CUDA_SUCCESS, WB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     const int n_qb = ceil_div(T, AQ);
-    static int version = 0, poly = 0, late = 0;
-    if (!version) {
+    // process-wide switches, read once (initialisation of a function-local static is thread-safe)
+    struct Sw { int version, poly, late; };
+    static const Sw sw = [] {
+        Sw r{2, 0, 0};
         const char* e = getenv("WB_ATTN_V");
-        version = (e && e[0] == '1') ? 1 : 2;
+        if (e && e[0] == '1') r.version = 1;
         const char* pe = getenv("WB_ATTN_POLY");            // exponentials per 8 that go to the FMA-pipe polynomial (0 .. 4)
-        poly = pe ? atoi(pe) : 0;
-        if (poly < 0 || poly > 4) poly = 0;
+        r.poly = pe ? atoi(pe) : 0;
+        if (r.poly < 0 || r.poly > 4) r.poly = 0;
         const char* le = getenv("WB_ATTN_LATE");            // 1: exponentials before the wait for the P tile
-        late = (le && le[0] == '1') ? 1 : 0;
-    }
+        r.late = (le && le[0] == '1') ? 1 : 0;
+        return r;
+    }();
+    const int version = sw.version, poly = sw.poly, late = sw.late;
     const dim3 grid(B * H * n_qb);
     __nv_bfloat16* o = (__nv_bfloat16*)out;
     if (version == 1) attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(tm, o, T, d, H, n_qb);

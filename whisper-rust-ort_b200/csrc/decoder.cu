@@ -1200,8 +1200,7 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
     int n = 0;
     const bool pdl = D.pdl;
     // timing experiments only (results are wrong): WB_DEC_SKIP=cross drops the cross-attention launches, =rest everything else of a layer
-    static int skip = -1;
-    if (skip < 0) { const char* e = getenv("WB_DEC_SKIP"); skip = !e ? 0 : e[0] == 'c' ? 1 : e[0] == 'r' ? 2 : e[0] == 'v' ? 3 : 0; }
+    static const int skip = [] { const char* e = getenv("WB_DEC_SKIP"); return !e ? 0 : e[0] == 'c' ? 1 : e[0] == 'r' ? 2 : e[0] == 'v' ? 3 : 0; }();
     if (sizeof(WT) == 2 && dec_cluster_enabled(ctx)) {
         // bf16 build at whisper-base widths: embedding + all decoder layers in ONE launch (dec_cluster.cu).
         // The first kernel of a graph follows memcpy nodes, not a kernel: plain launch.

@@ -715,14 +715,13 @@ int vocab_tc_launch(wb_ctx* ctx, cudaStream_t st, bool pdl, const int* state, co
     // need every SM, and with several batches in flight the SM-time a launch holds is what it costs the other batches.
     // Measured (decode only, B = 32; 8 in flight / alone, ms per batch): 148 CTAs 18.78 / 44.5, 74: 18.48 / 44.8,
     // 50: 18.3 / 45.3, 37: 18.2 / 45.7.
-    static int cap = -1;
-    if (cap < 0) { const char* e = getenv("WB_VOCAB_CTAS"); cap = e ? atoi(e) : 0; }
+    static const int cap = [] { const char* e = getenv("WB_VOCAB_CTAS"); return e ? atoi(e) : 0; }();
     int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
     const int want = cap > 0 ? cap : (ctx->sm_count + 1) / 2;
     if (want < grid) grid = want;
     cudaLaunchConfig_t cfg{};
-    static int l2_last = -1;                   // WB_VOCAB_L2=none: plain loads (the evict-last hint keeps the matrix in L2 under the K/V streams)
-    if (l2_last < 0) { const char* e = getenv("WB_VOCAB_L2"); l2_last = !(e && e[0] == 'n'); }
+    // WB_VOCAB_L2=none: plain loads (default: evict-last hint, keeps the matrix in L2 under the K/V streams)
+    static const int l2_last = [] { const char* e = getenv("WB_VOCAB_L2"); return (e && e[0] == 'n') ? 0 : 1; }();
     const bool two = B > VT_N;
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(VT_THREADS); cfg.dynamicSmemBytes = two ? VtCfg<2>::SMEM : VtCfg<1>::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
