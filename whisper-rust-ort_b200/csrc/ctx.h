@@ -123,6 +123,7 @@ struct DecBufs {
     int* unfinished_host = nullptr;    // mapped: sequences still running, written at the end of a segment
     int* unfinished_dev = nullptr;
     bool pdl = false;                  // programmatic dependent launch for the decode chain
+    bool ffn_handoff = true;           // fc1 writes its output as bf16 for fc2 (bit-identical, half the staging bytes)
     int lean = 0;                      // 1: register-capped skinny GEMMs + 4-warp cross-attention (see decoder.cu)
     int self_attn_warps = 4;           // warps per (sequence, head) in the self-attention kernel (WB_SELF_ATTN_WARPS = 2 | 4 | 8)
     int* stage_host = nullptr;         // pinned staging of the per-decode control state (ids, bitmaps, lens): a pageable

@@ -361,7 +361,7 @@ template <> struct RowRaw<bf16> {
 
 template <typename KT, int NW>          // NW warps per CTA: 8, or 4 when H*B would not fit one wave of 8-warp CTAs
 __global__ void __launch_bounds__(NW * 32)
-cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out, int d, int Tk) {
+cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float* __restrict__ out, int d, int Tk, int out_bf16) {
     constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = NW * 32 / LPR, UN = 4;
     __shared__ float s_m[NW], s_l[NW];
     __shared__ float s_acc[NW][64];
@@ -463,7 +463,10 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
             lt = fmaf(s_l[w], wgt, lt);
         }
     }
-    if (tid < 64) out[(size_t)b * d + h * 64 + tid] = my / lt;
+    if (tid < 64) {                                     // out_bf16: the consuming GEMM rounds to bf16 anyway; it then stages half the bytes
+        if (out_bf16) reinterpret_cast<bf16*>(out)[(size_t)b * d + h * 64 + tid] = __float2bfloat16_rn(my / lt);
+        else out[(size_t)b * d + h * 64 + tid] = my / lt;
+    }
 }
 
 // ---- decoder self-attention for the new token (causal = all cached keys 0..s) ----
@@ -477,7 +480,7 @@ cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, float
 template <typename KT, int NW>
 __global__ void __launch_bounds__(NW * 32)
 self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, KT* __restrict__ cache,
-                 float* __restrict__ out, int d, int T_max) {
+                 float* __restrict__ out, int d, int T_max, int out_bf16) {
     constexpr int DPL = RowRaw<KT>::DPL, LPR = 64 / DPL, NG = NW * 32 / LPR, UN = 4, HPL = DPL / 2;
     __shared__ float s_m[NW], s_l[NW];
     __shared__ float s_acc[NW][64];
@@ -566,7 +569,8 @@ self_attn_kernel(const int* __restrict__ state, const float* __restrict__ qkv, K
             my = fmaf(s_acc[w][tid], wgt, my);
             lt = fmaf(s_l[w], wgt, lt);
         }
-        out[(size_t)b * d + h * 64 + tid] = my / lt;
+        if (out_bf16) reinterpret_cast<bf16*>(out)[(size_t)b * d + h * 64 + tid] = __float2bfloat16_rn(my / lt);
+        else out[(size_t)b * d + h * 64 + tid] = my / lt;
     }
 }
 
@@ -693,7 +697,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // one cross-attention launch over B sequences
 template <typename WT>
-void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, int H, int B, int d, int Tk, bool four_warps = false) {
+void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv, float* att, int H, int B, int d, int Tk, bool four_warps = false, int out_bf16 = 0) {
     // 8-warp CTAs hold 2 per SM (register file), 4-warp CTAs 4 per SM.  When the (b,h) pairs overflow one wave of
     // 8-warp CTAs but fit one wave of 4-warp CTAs, the smaller shape keeps every pair streaming at once instead of
     // leaving a few CTAs to run alone at the end (large-v3 widths at batch 16: 320 pairs on 148 SMs).
@@ -701,12 +705,13 @@ void launch_cross_attn(cudaStream_t st, bool pdl, const float* q, const WT* ckv,
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const int units = H * B;
     if (four_warps || (units > 2 * sms && units <= 4 * sms))
-        launch_k(cross_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, q, ckv, att, d, Tk);
+        launch_k(cross_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, q, ckv, att, d, Tk, out_bf16);
     else
-        launch_k(cross_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, q, ckv, att, d, Tk);
+        launch_k(cross_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, q, ckv, att, d, Tk, out_bf16);
 }
 
 constexpr int MM_THREADS = 256;
+constexpr int ACT_GELU = 1, ACT_X_BF16 = 16, ACT_Y_BF16 = 32;       // `act` argument of the decode GEMMs (bit 0: GELU)
 // One skinny GEMM executed by CTA `cta` of the `ncta` CTAs of the grid.
 // Sequences are processed in groups of GS = 8 * NT (NT n-tiles of 8): batches up to GS take one pass as before; a wider
 // batch walks its groups with the SAME register-resident weight fragments (one weight read per step for 64 or 128
@@ -721,6 +726,10 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
           const int* __restrict__ state, const unsigned* __restrict__ sup_base, const unsigned* __restrict__ sup_first,
           float* __restrict__ amax_val, int* __restrict__ amax_idx) {
     static_assert(RW * KS == 8, "8 warps");
+    // act: bit 0 = GELU; ACT_X_BF16 = X is already bf16 [B][K] (written by a predecessor with ACT_Y_BF16): the staging is a
+    // plain copy of half the bytes and bit-identical to converting the f32 values here; ACT_Y_BF16 = Y is written as bf16
+    const bool x_bf16 = (act & ACT_X_BF16) != 0, y_bf16 = (act & ACT_Y_BF16) != 0;
+    act &= 15;
     // decoder weights are re-read by every step of every batch in flight: keep them in L2 (evict-last) against the
     // streams that pass through it (cross-attention K/V is evict-first, encoder activations are untagged)
     const uint64_t wpol = l2_evict_last_policy();
@@ -805,6 +814,27 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                             *reinterpret_cast<uint2*>(xs + bb * xstride + c * 2) = pk;
                         }
                     }
+                }
+            } else if (x_bf16) {
+                // rows of 8-element (16-byte) pieces; two rows per warp in flight (<= 16 loads per lane at K = 2048)
+                const uint4* Xb = reinterpret_cast<const uint4*>(X);
+                const int k8 = K >> 3;
+                for (int bb0 = warp; bb0 < rows_st; bb0 += 16) {
+                    uint4 v[2][8];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int bb = bb0 + rr * 8, c = lane + i * 32;
+                            v[rr][i] = (bb < rows_st && b0 + bb < B && c < k8) ? __ldcg(Xb + (size_t)(b0 + bb) * k8 + c) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int bb = bb0 + rr * 8, c = lane + i * 32;
+                            if (bb < rows_st && c < k8) *reinterpret_cast<uint4*>(xs + bb * xstride + c * 16) = v[rr][i];
+                        }
                 }
             } else
             for (int r4 = 0; r4 * 32 < rows_st; ++r4)                // 32 staged rows (4 per warp) at a time
@@ -953,7 +983,8 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                     if (bias) v += bias[n];
                     if (act == 1) v = gelu_erf(v);
                     if (residual) v += __ldcg(residual + (size_t)b * N + n);
-                    Y[(size_t)b * N + n] = v;
+                    if (y_bf16) reinterpret_cast<bf16*>(Y)[(size_t)b * N + n] = __float2bfloat16_rn(v);
+                    else Y[(size_t)b * N + n] = v;
                 }
             }
         } else {
@@ -975,7 +1006,10 @@ mma_stage(unsigned char* mm_smem, int cta, int ncta,
                     if (act == 1) v = gelu_erf(v);
                     if (b < B && n < N) {
                         if (residual) v += __ldcg(residual + (size_t)b * N + n);
-                        if (Y) Y[(size_t)b * N + n] = v;
+                        if (Y) {
+                            if (y_bf16) reinterpret_cast<bf16*>(Y)[(size_t)b * N + n] = __float2bfloat16_rn(v);
+                            else Y[(size_t)b * N + n] = v;
+                        }
                     }
                     if (amax_val && ok[i >> 1]) {           // strict '>' in increasing n: lowest index wins ties, NaN never
                         const int slot = nt * 2 + (i & 1);
@@ -1168,9 +1202,11 @@ void skinny(wb_ctx* ctx, const float* X, int B, int K, const LinearW& L, const L
     const float* lw = ln ? ln->w : nullptr;
     const float* lb = ln ? ln->b : nullptr;
     const float* bias = (L.b && !W_override) ? L.b : nullptr;
-    if (sizeof(WT) == 2 &&
+    const bool handoff = (act & (ACT_X_BF16 | ACT_Y_BF16)) != 0;      // bf16 activation hand-off: mma.sync kernels only
+    if (sizeof(WT) == 2 && !handoff &&
         skinny_tc_launch(ctx, ctx->stream, ctx->dec.pdl, X, B, K, W, N, bias, lw, lb, act, residual, Y)) return;       // tcgen05 (vocab_tc.cu)
     if (skinny_mma(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y)) { CUDA_CHECK(cudaGetLastError()); return; }
+    WB_REQUIRE(!handoff, WB_EINVAL, "skinny gemm: bf16 hand-off requested for a shape without a tensor-core kernel (N=%d K=%d B=%d)", N, K, B);
     WB_REQUIRE(Y != nullptr, WB_EINVAL, "skinny gemm: no output buffer on the SIMT path (N=%d K=%d)", N, K);
     // rows per warp: enough CTAs to cover the chip for the per-layer GEMMs, register blocking for the vocab one
     if (N >= 8192) skinny_launch<WT, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y);
@@ -1215,20 +1251,26 @@ int enqueue_step(wb_ctx* ctx, cudaStream_t st, int B, int* state, bool with_logi
                 launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean == 1); ++n;
                 continue;
             }
+            // attention outputs go to their out-projections as bf16 under the same conditions as fc1 -> fc2 below
+            const bool att_bf16 = sizeof(WT) == 2 && D.ffn_handoff && skinny_mma_enabled() && (d == 512 || d == 128);
+            const bool xatt_bf16 = att_bf16 && !(sizeof(WT) == 2 && cross_attn_tc_ok(ctx));
             skinny<WT>(ctx, x, B, d, L.qkv, &L.ln1, 0, nullptr, D.qkv.p); ++n;                                             // K3c
-            if (D.self_attn_warps == 2) launch_k(self_attn_kernel<WT, 2>, dim3(H, B), dim3(64), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);   // K3d
-            else if (D.self_attn_warps == 4) launch_k(self_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);
-            else launch_k(self_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max);
+            if (D.self_attn_warps == 2) launch_k(self_attn_kernel<WT, 2>, dim3(H, B), dim3(64), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max, att_bf16 ? 1 : 0);   // K3d
+            else if (D.self_attn_warps == 4) launch_k(self_attn_kernel<WT, 4>, dim3(H, B), dim3(128), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max, att_bf16 ? 1 : 0);
+            else launch_k(self_attn_kernel<WT, 8>, dim3(H, B), dim3(256), 0, st, pdl, (const int*)state, (const float*)D.qkv.p, skv, D.att.p, d, D.T_max, att_bf16 ? 1 : 0);
             ++n;
-            skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, 0, x, x); ++n;                                                      // K3f
+            skinny<WT>(ctx, D.att.p, B, d, L.o, nullptr, att_bf16 ? ACT_X_BF16 : 0, x, x); ++n;                               // K3f
             skinny<WT>(ctx, x, B, d, L.cq, &L.ln2, 0, nullptr, D.q.p); ++n;
             if (skip == 1) {}
             else if (sizeof(WT) == 2 && cross_attn_tc_ok(ctx)) cross_attn_tc(ctx, st, pdl, l, D.q.p, D.att.p, B);           // K3e
-            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean == 1);
+            else launch_cross_attn<WT>(st, pdl, (const float*)D.q.p, ckv, D.att.p, H, B, d, Tk, D.lean == 1, xatt_bf16 ? 1 : 0);
             ++n;
-            skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, 0, x, x); ++n;
-            skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, 1, nullptr, D.ffn.p); ++n;                                               // K3g
-            skinny<WT>(ctx, D.ffn.p, B, c.ffn_dim, L.fc2, nullptr, 0, x, x); ++n;
+            skinny<WT>(ctx, D.att.p, B, d, L.co, nullptr, (xatt_bf16 && skip != 1) ? ACT_X_BF16 : 0, x, x); ++n;
+            // fc1 hands its GELU output to fc2 as bf16 where both run on the mma.sync kernels (whisper-base / toy widths):
+            // fc2 rounds its input to bf16 anyway, so the result is bit-identical and fc2 stages half the bytes
+            const bool ffn_bf16 = sizeof(WT) == 2 && D.ffn_handoff && skinny_mma_enabled() && (d == 512 || d == 128) && c.ffn_dim == 4 * d;
+            skinny<WT>(ctx, x, B, d, L.fc1, &L.ln3, ACT_GELU | (ffn_bf16 ? ACT_Y_BF16 : 0), nullptr, D.ffn.p); ++n;         // K3g
+            skinny<WT>(ctx, D.ffn.p, B, c.ffn_dim, L.fc2, nullptr, ffn_bf16 ? ACT_X_BF16 : 0, x, x); ++n;
         }
     }
     if (with_logits && sizeof(WT) == 2 && dec_cluster_vocab_ok(ctx, B) && D.fuse_argmax) {
@@ -1303,6 +1345,8 @@ void decoder_alloc(wb_ctx* ctx) {
         const int late = e ? atoi(e) : 1;
         CUDA_CHECK(cudaMemcpyToSymbol(g_pdl_late, &late, sizeof(int)));
     }
+    D.ffn_handoff = true;              // WB_FFN_BF16=0: fc1 -> fc2 activations in f32 (the first version)
+    if (const char* e = getenv("WB_FFN_BF16")) D.ffn_handoff = e[0] != '0';
     D.lean = 0;                        // WB_DEC_LEAN=1: register-capped GEMM kernels + 4-warp cross-attention CTAs (co-residency across batches in flight); 2: the GEMM kernels only
     if (const char* e = getenv("WB_DEC_LEAN")) D.lean = e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0;
     D.self_attn_warps = 4;            // measured: 4 warps is the best of 2 / 4 / 8 both for one batch alone and for 8 in flight
