@@ -75,6 +75,11 @@ int wb_get_cfg(const wb_ctx* ctx, wb_model_cfg* out);
 int wb_get_timing(const wb_ctx* ctx, wb_timing* out);
 /* Debug/test: keep copies of encoder intermediates for wb_get_encoder_debug (also WB_DEBUG=1). */
 int wb_set_debug(wb_ctx* ctx, int on);
+/* How many batches the caller keeps in flight on this GPU (0 = unknown, the default).  The decode GEMMs trade latency
+ * against SM-time: with ONE batch in flight (hint 1) they spread over twice the CTAs (one decode chain alone ~6 % faster),
+ * with several they keep the fewer, fatter CTAs that cost the other batches less (11 % more throughput at 8 in flight).
+ * wb_pool sets the hint of its slots to n_slots.  Results are identical either way. */
+int wb_set_load_hint(wb_ctx* ctx, int batches_in_flight);
 /* Debug/test: copy a weight tensor (HF state_dict name) back as f32. n = element count. */
 int wb_get_tensor(wb_ctx* ctx, const char* name, float* out, int64_t n);
 

@@ -55,6 +55,7 @@ def lib():
         "wb_get_cfg": [vp, C.POINTER(wb_model_cfg)],
         "wb_get_timing": [vp, C.POINTER(wb_timing)],
         "wb_set_debug": [vp, ci],
+        "wb_set_load_hint": [vp, ci],
         "wb_selftest_gemm": [vp, ci, ci, ci, ci, ci, ci, f32p, f32p],
         "wb_selftest_attn": [vp, ci, f32p, f32p],
         "wb_mark": [vp, ci],
@@ -211,6 +212,10 @@ class Whisper:
 
     def set_debug(self, on=True):
         _chk(self.L.wb_set_debug(self.h, int(on)))
+
+    def set_load_hint(self, batches_in_flight: int):
+        """How many batches the caller keeps in flight on this GPU (1 = latency-oriented decode kernels)."""
+        _chk(self.L.wb_set_load_hint(self.h, int(batches_in_flight)))
 
     def encoder_debug(self, what: str, B: int):
         c = self.cfg

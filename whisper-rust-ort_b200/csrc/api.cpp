@@ -424,6 +424,14 @@ int wb_set_debug(wb_ctx* ctx, int on) {
     WB_CATCH
 }
 
+int wb_set_load_hint(wb_ctx* ctx, int batches_in_flight) {
+    WB_TRY
+    require_ctx(ctx);
+    WB_REQUIRE(batches_in_flight >= 0, WB_EINVAL, "wb_set_load_hint: negative hint");
+    ctx->dec.load_hint = batches_in_flight;
+    WB_CATCH
+}
+
 int wb_get_tensor(wb_ctx* ctx, const char* name, float* out, int64_t n) {
     WB_TRY
     require_ctx(ctx);

@@ -125,6 +125,7 @@ struct DecBufs {
     bool pdl = false;                  // programmatic dependent launch for the decode chain
     bool ffn_handoff = true;           // fc1 writes its output as bf16 for fc2 (bit-identical, half the staging bytes)
     int lean = 0;                      // 1: register-capped skinny GEMMs + 4-warp cross-attention (see decoder.cu)
+    int load_hint = 0;                 // wb_set_load_hint: batches the caller keeps in flight (0 unknown); 1 selects the latency-oriented GEMM shapes
     int self_attn_warps = 4;           // warps per (sequence, head) in the self-attention kernel (WB_SELF_ATTN_WARPS = 2 | 4 | 8)
     int* stage_host = nullptr;         // pinned staging of the per-decode control state (ids, bitmaps, lens): a pageable
     size_t stage_ints = 0;             //   source would make every cudaMemcpyAsync wait for the stream to drain first

@@ -1132,6 +1132,14 @@ inline bool skinny_mma(wb_ctx* ctx, const float* X, int B, int K, const bf16* W,
         if (K == 128) { skinny_mma_launch<8, 1, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y, fa); return true; }
         return false;
     }
+    // Twice the CTAs with half the weight rows each: the latency-oriented shapes, chosen when the caller said that ONE batch
+    // is in flight (wb_set_load_hint; WB_SKINNY_THIN=0..3 overrides).  Decode only, ms per batch alone / with 8 in flight:
+    // 47.4 / 18.7 (default shapes), fc2 thin 47.1 / 19.0, + o/cq/co 45.8 / 19.7, + qkv/fc1 44.4 / 20.7.
+    static const int thin_env = [] { const char* e = getenv("WB_SKINNY_THIN"); return e ? atoi(e) : -1; }();
+    const int thin = thin_env >= 0 ? thin_env : (ctx->dec.load_hint == 1 ? 3 : 0);
+    if (thin && !wide && !lw && K == 2048) { skinny_mma_launch<1, 8, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+    if (thin >= 2 && !wide && K == 512 && N <= 1024) { skinny_mma_launch<1, 8, 2>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
+    if (thin >= 3 && !wide && K == 512 && N > 1024 && N < 8192) { skinny_mma_launch<2, 4, 4>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
     if (N > 1024) {                                // qkv / fc1: 64 rows per CTA, 2 k-slices
         if (K == 512 && wide) { skinny_mma_launch<4, 2, 8, 1, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
         if (K == 512) { skinny_mma_launch<4, 2, 8>(ctx, X, B, K, W, N, bias, lw, lb, act, residual, Y); return true; }
@@ -1161,6 +1169,8 @@ void skinny_mma_set_attrs() {       // once per process, outside any stream capt
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 16, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 2, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 8, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<1, 8, 2, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<4, 2, 8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 4, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_CHECK(cudaFuncSetAttribute(skinny_mma_kernel<2, 4, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1454,7 +1464,7 @@ void decoder_run(wb_ctx* ctx, const DecodeParams& p) {
     auto run_segment = [&](int n_steps, bool with_logits, int first_gi) {
         if (!use_graph) return enqueue_steps(n_steps, with_logits, first_gi);
         const int key[8] = {B, P, max_new, p.eot, forced_dev ? 1 : 0,
-                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0) + (cross_attn_tc_ok(ctx) ? 8 : 0) + (vocab_tc_ok(ctx, B) ? 16 : 0),
+                            c.precision * 64 + (D.pdl ? 4 : 0) + (dec_cluster_enabled(ctx) ? 2 : 0) + (D.fuse_argmax ? 1 : 0) + (cross_attn_tc_ok(ctx) ? 8 : 0) + (vocab_tc_ok(ctx, B) ? 16 : 0) + (D.load_hint == 1 ? 32 : 0),
                             n_steps, with_logits ? 1 : 0};
         DecGraph* g = nullptr;
         for (auto& e : D.graphs) {

@@ -455,6 +455,7 @@ void run_worker(const Job& J, int device, const std::vector<std::pair<size_t, si
     TRACE("worker on gpu %d: creating context", device);
     CK(wb_create(&ctx, device, &J.mc, J.wpath.empty() ? nullptr : J.wpath.c_str()));
     struct Guard { wb_ctx* c; ~Guard() { wb_destroy(c); } } guard{ctx};
+    CK(wb_set_load_hint(ctx, (int)args.in_flight));     // the reference's serial loop (1 in flight) gets the latency-oriented kernels
     TRACE("worker on gpu %d: context ready", device);
     PinnedPcm slots[2];
     auto prefetch = [&](int which) {

@@ -81,6 +81,7 @@ int wb_pool_create(wb_pool** out, int device, const wb_model_cfg* cfg, const cha
             delete p;
             return rc;                                                     // wb_last_error() holds wb_create's message
         }
+        wb_set_load_hint(c, n_slots);                                      // one slot: latency-oriented kernels; several: throughput-oriented
         p->slots.push_back(c);
     }
     p->max_pending = n_slots;
