@@ -711,13 +711,13 @@ int vocab_tc_launch(wb_ctx* ctx, cudaStream_t st, bool pdl, const int* state, co
     const wb_model_cfg& c = ctx->cfg;
     const VocabTc* v = static_cast<const VocabTc*>(ctx->dec.vocab_tc);
     const int n_tiles = (c.vocab + VT_BM - 1) / VT_BM;
-    // One CTA per TWO SMs by default (WB_VOCAB_CTAS overrides): the TMA ring streams a CTA's tiles at a rate that does not
+    // One CTA per TWO SMs unless the caller said that one batch is in flight (wb_set_load_hint; WB_VOCAB_CTAS overrides): the TMA ring streams a CTA's tiles at a rate that does not
     // need every SM, and with several batches in flight the SM-time a launch holds is what it costs the other batches.
     // Measured (decode only, B = 32; 8 in flight / alone, ms per batch): 148 CTAs 18.78 / 44.5, 74: 18.48 / 44.8,
     // 50: 18.3 / 45.3, 37: 18.2 / 45.7.
     static const int cap = [] { const char* e = getenv("WB_VOCAB_CTAS"); return e ? atoi(e) : 0; }();
     int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
-    const int want = cap > 0 ? cap : (ctx->sm_count + 1) / 2;
+    const int want = cap > 0 ? cap : ctx->dec.load_hint == 1 ? ctx->sm_count : (ctx->sm_count + 1) / 2;   // one batch in flight: every SM
     if (want < grid) grid = want;
     cudaLaunchConfig_t cfg{};
     // WB_VOCAB_L2=none: plain loads (default: evict-last hint, keeps the matrix in L2 under the K/V streams)
