@@ -23,7 +23,10 @@ def make(B, **env):
     old = {k: os.environ.get(k) for k in env}
     os.environ.update({k: str(v) for k, v in env.items()})
     try:
-        return wb200.Whisper(wb200.default_cfg("base", precision=wb200.WB_PREC_BF16, max_batch=B, max_chunks=B))
+        m = wb200.Whisper(wb200.default_cfg("base", precision=wb200.WB_PREC_BF16, max_batch=B, max_chunks=B))
+        if os.environ.get("WB_PROBE_HINT"):                  # wb_set_load_hint: 1 = latency-oriented kernels
+            m.set_load_hint(int(os.environ["WB_PROBE_HINT"]))
+        return m
     finally:
         for k, v in old.items():
             if v is None:
