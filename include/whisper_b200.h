@@ -191,10 +191,13 @@ int wb_selftest_fft400(const float* re, const float* im, float* out_re, float* o
 int wb_selftest_attn(wb_ctx* ctx, int B, float* max_diff_out, float* max_abs_out);
 
 /* ---- host-side pieces of the path (C++ in csrc/host/, exported for the CLI and tests) ---- */
-/* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8 / s16 / f32 / A-law / mu-law (what symphonia hands the
- * reference as U8, S16 or F32 buffers; s24 / s32 / f64 / ADPCM / FLAC fail with its "Unsupported decoded sample format"), channel
- * mean downmix, linear resample to 16 kHz.  *pcm_out is malloc'd; release with wb_host_free. */
+/* load_audio_16k_mono + resample_linear (main.rs:207-316): RIFF/WAVE u8 / s16 / f32 / A-law / mu-law and MPEG-1 / -2 / -2.5
+ * Layer III (what symphonia hands the reference as U8, S16 or F32 buffers; s24 / s32 / f64 / ADPCM / FLAC fail with its
+ * "Unsupported decoded sample format"), recognised by content like symphonia's probe; channel mean downmix, linear
+ * resample to 16 kHz.  *pcm_out is malloc'd; release with wb_host_free. */
 int wb_host_load_audio_16k_mono(const char* path, float** pcm_out, int64_t* n_out, double* dur_out);
+/* Test hook: an in-memory Layer III stream -> the mono mix the loader builds BEFORE resampling (malloc'd), channels, rate. */
+int wb_host_mp3_decode_mono(const uint8_t* bytes, int64_t n, float** out, int64_t* n_out, int* channels, uint32_t* sr);
 int64_t wb_host_resample_linear(const float* x, int64_t n, uint32_t sr_in, uint32_t sr_out,
                                 float* out, int64_t cap);
 void wb_host_free(void* p);

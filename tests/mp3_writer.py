@@ -90,7 +90,18 @@ def lsf_slen(sfc):
     return [sfc // 3, sfc % 3, 0, 0], 2
 
 
-def random_granule(rng, version, row, budget_bits, gr, prev, allow_scfsi, spec=None, force=None):
+def lsf_slen_intensity(sfc):
+    v = sfc >> 1
+    if v < 180:
+        return [v // 36, (v % 36) // 6, (v % 36) % 6, 0], 3
+    if v < 244:
+        v -= 180
+        return [(v % 64) >> 4, (v % 16) >> 2, v % 4, 0], 4
+    v -= 244
+    return [v // 3, v % 3, 0, 0], 5
+
+
+def random_granule(rng, version, row, budget_bits, gr, prev, allow_scfsi, spec=None, force=None, is_right=False):
     """Draws one granule/channel: returns (side-info dict, main-data BitWriter)."""
     T = tables()
     for attempt in range(50):
@@ -132,11 +143,14 @@ def random_granule(rng, version, row, budget_bits, gr, prev, allow_scfsi, spec=N
                         w.put(int(rng.integers(0, 1 << s)), s)
         else:
             g["sfc"] = int(rng.integers(0, 512))
-            slen, r = lsf_slen(g["sfc"])
+            slen, r = lsf_slen_intensity(g["sfc"]) if is_right else lsf_slen(g["sfc"])
             col = (2 if g["mixed"] else 1) if shortb else 0
             for k in range(4):
                 for _ in range(T["nsf"][r][col][k]):
-                    w.put(int(rng.integers(0, 1 << slen[k])), slen[k])
+                    # right channel of an intensity-stereo pair: positions; the all-ones value is "illegal", which decoders treat differently
+                    # (and libavcodec knows only positions 0..15 of the up-to-5-bit LSF field)
+                    top = min(16, max(1, (1 << slen[k]) - 1)) if is_right else 1 << slen[k]
+                    w.put(int(rng.integers(0, top)), slen[k])
         # ---- part 3: Huffman-coded spectrum
         scale = 0.25 * (0.5 ** attempt)
         bv = int(rng.integers(0, max(1, int(288 * scale)) + 1))
@@ -156,6 +170,10 @@ def random_granule(rng, version, row, budget_bits, gr, prev, allow_scfsi, spec=N
             r2 = int(edge[min(g["region0_count"] + g["region1_count"] + 2, 22)])
             nreg = 3
         ids = sorted(T["sel"].keys())
+        if is_right:
+            # the intensity bound is "right channel all zero": keep to the books without escape values, whose lines libavcodec
+            # dequantises in float (its integer path for escaped values rounds very small magnitudes to an exact 0)
+            ids = [t for t in ids if t < 16]
         g["table_select"] = [int(rng.choice([0] + ids)) if rng.random() < 0.9 else 0 for _ in range(nreg)]
         if spec is not None:
             bv, g["table_select"] = spec["big_values"], spec["table_select"]
@@ -252,13 +270,15 @@ def side_info(version, channels, main_data_begin, grs):
     return out
 
 
-def make_stream(seed, version=0, sr_idx=0, br_idx=9, channels=2, n_frames=6, ms=False, crc=False, reservoir=True, specs=None, force=None):
+def make_stream(seed, version=0, sr_idx=0, br_idx=9, channels=2, n_frames=6, ms=False, crc=False, reservoir=True, specs=None, force=None, intensity=False):
     """-> (list of frame bytes, sample rate).  `specs`: optional {(frame, gr, ch): spec} with explicit spectra."""
     rng = np.random.default_rng(seed)
     row = version * 3 + sr_idx
     n_gr = 2 if version == 0 else 1
     mode = 3 if channels == 1 else (1 if ms else int(rng.choice([0, 2])))
-    mode_ext = 2 if (ms and channels == 2) else 0
+    mode_ext = (2 if (ms and channels == 2) else 0) | (1 if (intensity and channels == 2) else 0)
+    if mode_ext:
+        mode = 1
     side = (17 if channels == 1 else 32) if version == 0 else (9 if channels == 1 else 17)
     head = 4 + (2 if crc else 0)
     max_back = 511 if version == 0 else 255
@@ -294,9 +314,9 @@ def make_stream(seed, version=0, sr_idx=0, br_idx=9, channels=2, n_frames=6, ms=
                     if bt == 2 and last_bt[c] == 2:             # a run of short blocks keeps its layout: the long-windowed low
                         mixed = last_mixed[c]                   # subbands of a mixed block are no legal neighbour of short windows
                     f_c = dict(ws=int(bt != 0), block_type=bt, mixed=mixed)
-                    if mode_ext == 2 and c == 1:                # MS stereo pairs lines of the two channels: same window layout in both
+                    if mode_ext and c == 1:                     # joint stereo pairs lines of the two channels: same window layout in both
                         f_c = {k: grs[gr][0][k] for k in ("ws", "block_type", "mixed")}
-                g, w = random_granule(rng, version, row, max(share, 80), gr, grs[0][c] if gr else None, allow_scfsi=True, spec=spec, force=f_c)
+                g, w = random_granule(rng, version, row, max(share, 80), gr, grs[0][c] if gr else None, allow_scfsi=True, spec=spec, force=f_c, is_right=bool(mode_ext & 1) and c == 1)
                 last_bt[c], last_mixed[c] = g["block_type"], g["mixed"]
                 grs[gr][c] = g
                 body.bits += w.bits

@@ -144,3 +144,35 @@ def test_cli_scheduler_worker_failure_fails_the_run(wb, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 1 and "Error:" in r.stderr
     assert not (out / "a.csv").exists()
+
+
+def test_cli_reads_mp3_next_to_wav(wb, tmp_path):
+    """The reference's extension filter takes .mp3 too (main.rs:1116) and symphonia decodes it (main.rs:266-275): an MPEG
+    Layer III file goes through the same pipeline as a WAV file; its row is what the library gives for the PCM the loader
+    (csrc/host/mp3.cpp, held to libavcodec in tests/test_mp3_cpu.py) produced."""
+    import ctypes as C
+    import mp3_writer as mw
+    audio, onnx, out = tmp_path / "audio", tmp_path / "onnx", tmp_path / "out"
+    audio.mkdir(); onnx.mkdir()
+    frames, sr = mw.make_stream(seed=11, version=1, sr_idx=2, br_idx=8, channels=2, n_frames=60, ms=True)      # 16 kHz, 2.16 s
+    (audio / "a.mp3").write_bytes(b"".join(frames))
+    wb.synth.write_wav(str(audio / "b.wav"), wb.synth.clip(4, 1, 3.0), fmt="s16")
+    r = subprocess.run([EXE, "--audio-dir", str(audio), "--onnx-dir", str(onnx), "--max-new-tokens", "5", "--precision", "fp32",
+                        "--out-csv", str(out / "p.csv"), "--out-json", str(out / "p.json"), "--out-summary-json", str(out / "s.json")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rows = json.loads((out / "p.json").read_text())
+    assert [x["file"] for x in rows] == ["a.mp3", "b.wav"]
+    L = wb.lib()
+    f32p = C.POINTER(C.c_float)
+    L.wb_host_load_audio_16k_mono.argtypes = [C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.wb_host_free.argtypes = [C.c_void_p]
+    buf, n, dur = f32p(), C.c_int64(), C.c_double()
+    assert L.wb_host_load_audio_16k_mono(str(audio / "a.mp3").encode(), C.byref(buf), C.byref(n), C.byref(dur)) == 0
+    pcm = np.ctypeslib.as_array(buf, (n.value,)).copy()
+    L.wb_host_free(buf)
+    assert n.value == 60 * 576 and rows[0]["duration_s"] == round(dur.value, 3)
+    m = wb.Whisper(wb.default_cfg("base", max_batch=4, max_chunks=8))
+    toks, _ = m.transcribe_batch([pcm], [50258, 50259, 50359, 50363], 5, 50257)
+    assert rows[0]["text"] == hr.stitch_texts([hr.decode_tokens_fallback(t[4:]) for t in toks])
+    m.close()

@@ -1,8 +1,9 @@
 // audio.cpp — host-side audio ingest (replaces load_audio_16k_mono + resample_linear,
 // /root/reference/src/main.rs:207-316, which sit on the symphonia crate).  RIFF/WAVE in the sample
 // formats the reference accepts (U8 / S16 / F32; its match bails on S24 / S32 / F64, and so on every FLAC
-// file, which symphonia decodes to S32).  MP3 is the one container the reference reads and this does
-// not (no decoder offline; SURVEY.md §8f3 ranks that "next"): reported as unsupported.
+// file, which symphonia decodes to S32), and MPEG Layer III streams (mp3.cpp; symphonia hands the reference F32
+// planes for them, main.rs:266-275).  Like symphonia's probe, the container is recognised by content, not by
+// the file extension.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +38,11 @@ int64_t wb_host_resample_linear(const float* x, int64_t n, uint32_t sr_in, uint3
 void wb_host_free(void* p) { std::free(p); }
 
 }  // extern "C"
+
+namespace wbmp3 {                                  // mp3.cpp
+bool probe(const uint8_t* p, size_t n, size_t* first);
+void decode_to_mono(const uint8_t* p, size_t n, size_t first, std::vector<float>& mono, uint32_t& sr);
+}
 
 namespace {
 
@@ -87,8 +93,11 @@ void load_wav(const char* path, std::vector<float>& mono, uint32_t& sr) {
     // FLAC: symphonia's FLAC decoder hands back S32 buffers, which the reference's match rejects (main.rs:265-303,
     // `_ => bail!`), so a faithful drop-in fails on .flac too -- with the reference's own message.
     if (std::memcmp(buf.data(), "fLaC", 4) == 0) WB_THROW(WB_EINVAL, "Unsupported decoded sample format");
-    if (std::memcmp(buf.data(), "RIFF", 4) != 0)
-        WB_THROW(WB_EINVAL, "unsupported audio container (only RIFF/WAVE is decodable offline): %s", path);
+    if (std::memcmp(buf.data(), "RIFF", 4) != 0) {
+        size_t first = 0;
+        if (wbmp3::probe(buf.data(), buf.size(), &first)) { wbmp3::decode_to_mono(buf.data(), buf.size(), first, mono, sr); return; }
+        WB_THROW(WB_EINVAL, "unsupported audio container (RIFF/WAVE and MPEG Layer III are the decodable ones): %s", path);
+    }
     if (std::memcmp(buf.data() + 8, "WAVE", 4) != 0) WB_THROW(WB_EINVAL, "wav: riff form is not wave");
     const uint64_t riff_len = rd32(buf.data() + 4);
     uint64_t consumed = 0;                       // ChunksReader::consumed (counts from after the form id, like the crate)

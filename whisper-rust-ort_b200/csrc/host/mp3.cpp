@@ -11,7 +11,6 @@
 //  * every frame yields 1152 (MPEG-1) or 576 (LSF) samples per channel; the channel count is the first frame's;
 //  * a frame cut off by the end of the file is an IoError -> `break` (main.rs:258-262): dropped;
 //  * Layer I / II (cargo feature "mp3" builds Layer III only) and free-format streams are errors.
-// Not implemented (loud error, never silent): intensity stereo (no mainstream encoder emits it).
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -76,6 +75,7 @@ struct Granule {
     int block_type, table_select[3], subblock_gain[3], region0_count, region1_count;
     bool preflag, scalefac_scale, count1_table;
     int sf_l[23], sf_s[13][3];
+    bool is_bad_l[23], is_bad_s[13][3];     // right channel in intensity stereo: the scalefactor is an ILLEGAL intensity position
 };
 
 struct Trie { std::vector<int16_t> next; };      // node i: next[2i + bit] >= 0 -> child node, < 0 -> ~symbol
@@ -202,6 +202,8 @@ struct Decoder {
                 for (int s = kEdge[k]; s < kEdge[k + 1]; ++s)
                     q.sf_l[s] = (gr0 && scfsi[k]) ? gr0->sf_l[s] : (int)b.get(k < 2 ? s1 : s2);
         }
+        for (int s = 0; s < 23; ++s) q.is_bad_l[s] = q.sf_l[s] >= 7;                   // 2.4.3.4: is_pos = 7 means "not intensity coded"
+        for (int s = 0; s < 13; ++s) for (int w = 0; w < 3; ++w) q.is_bad_s[s][w] = q.sf_s[s][w] >= 7;
     }
 
     // 13818-3 2.4.3.2 scalefactors (LSF): four partitions, widths from scalefac_compress
@@ -219,13 +221,17 @@ struct Decoder {
         }
         const int col = (q.window_switching && q.block_type == 2) ? (q.mixed ? 2 : 1) : 0;
         int flat[48] = {0}, n = 0;
+        bool bad[48] = {false};                                      // 13818-3 2.4.3.2: the all-ones value of a field is the illegal position
         for (int k = 0; k < 4; ++k)
-            for (int i = 0; i < kLsfPartitions[row][col][k]; ++i) flat[n++] = (int)b.get(slen[k]);
-        if (col == 0) { for (int s = 0; s < 21; ++s) q.sf_l[s] = flat[s]; }
+            for (int i = 0; i < kLsfPartitions[row][col][k]; ++i, ++n) {
+                flat[n] = (int)b.get(slen[k]);
+                bad[n] = slen[k] > 0 && flat[n] == (1 << slen[k]) - 1;
+            }
+        if (col == 0) { for (int s = 0; s < 21; ++s) { q.sf_l[s] = flat[s]; q.is_bad_l[s] = bad[s]; } }
         else {
             int i = 0, sfb0 = 0;
-            if (q.mixed) { for (int s = 0; s < 6; ++s) q.sf_l[s] = flat[i++]; sfb0 = 3; }
-            for (int s = sfb0; s < 12; ++s) for (int w = 0; w < 3; ++w) q.sf_s[s][w] = flat[i++];
+            if (q.mixed) { for (int s = 0; s < 6; ++s, ++i) { q.sf_l[s] = flat[i]; q.is_bad_l[s] = bad[i]; } sfb0 = 3; }
+            for (int s = sfb0; s < 12; ++s) for (int w = 0; w < 3; ++w, ++i) { q.sf_s[s][w] = flat[i]; q.is_bad_s[s][w] = bad[i]; }
         }
     }
 
@@ -273,7 +279,7 @@ struct Decoder {
         b.pos = end;
     }
 
-    // 2.4.3.4 requantisation (+ the short-window reorder into frequency-interleaved order)
+    // 2.4.3.4 requantisation, in bitstream order (short windows still band by band)
     void requantize(const Header& h, const Granule& q, const int is[576], float xr[576]) {
         static const int kPretab[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
         const double mult = q.scalefac_scale ? 1.0 : 0.5;
@@ -296,9 +302,79 @@ struct Decoder {
             const int w = kBandShort[h.band_row][s];
             for (int win = 0; win < 3; ++win) {
                 const double e = (q.global_gain - 210 - 8 * q.subblock_gain[win]) / 4.0 - mult * (s < 12 ? q.sf_s[s][win] : 0);
-                for (int k = 0; k < w; ++k, ++i) xr[3 * (start + k) + win] = deq(is[i], e);
+                for (int k = 0; k < w; ++k, ++i) xr[i] = deq(is[i], e);
             }
             start += w;
+        }
+    }
+
+    // short windows: band-by-band order of the bitstream -> frequency-interleaved order (line 3 f + window)
+    void reorder(const Header& h, const Granule& q, float xr[576]) {
+        if (!(q.window_switching && q.block_type == 2)) return;
+        float tmp[576];
+        std::memcpy(tmp, xr, sizeof tmp);
+        const int s0 = q.mixed ? 3 : 0;
+        int start = 0;
+        for (int s = 0; s < s0; ++s) start += kBandShort[h.band_row][s];
+        int i = 3 * start;
+        for (int s = s0; s < 13; ++s) {
+            const int w = kBandShort[h.band_row][s];
+            for (int win = 0; win < 3; ++win)
+                for (int k = 0; k < w; ++k, ++i) xr[3 * (start + k) + win] = tmp[i];
+            start += w;
+        }
+    }
+
+    // 2.4.3.4 stereo processing on the two channels of a granule, in bitstream order.  MS: (m + s, m - s) / sqrt 2.  Intensity:
+    // scanning down from the top, bands (per window for short blocks) in which the right channel is still all zero take
+    // the left channel's lines split by the ratio the right channel's scalefactor encodes (MPEG-1: tan(is_pos pi / 12);
+    // LSF: powers of 2^-1/4 or 2^-1/2, 13818-3 2.4.3.2); the band above the last scalefactor band reuses the last position;
+    // an illegal position, and everything from the right channel's highest non-zero band down, is plain or MS stereo.
+    void stereo(const Header& h, const Granule& gr, float* l, float* r) {
+        const bool ms = (h.mode_ext & 2) != 0;
+        auto mid_side = [&](int at, int n) {
+            for (int j = at; j < at + n; ++j) {
+                const float m = l[j], s = r[j];
+                l[j] = (m + s) * 0.70710678118654752f;
+                r[j] = (m - s) * 0.70710678118654752f;
+            }
+        };
+        if (!(h.mode_ext & 1)) { if (ms) mid_side(0, 576); return; }
+        auto intensity = [&](int at, int n, int pos) {
+            float kl, kr;
+            if (h.version == 0) {
+                const double t = std::tan(pos * kPi / 12.0);
+                kl = pos == 6 ? 1.0f : (float)(t / (1.0 + t));
+                kr = pos == 6 ? 0.0f : (float)(1.0 / (1.0 + t));
+            } else {
+                const double f = std::exp2(-(double)((gr.scalefac_compress & 1) + 1) * ((pos + 1) >> 1) / 4.0);
+                kl = (pos & 1) ? (float)f : 1.0f;
+                kr = (pos & 1) ? 1.0f : (float)f;
+            }
+            for (int j = at; j < at + n; ++j) { const float x = l[j]; l[j] = x * kl; r[j] = x * kr; }
+        };
+        auto silent = [&](int at, int n) { for (int j = at; j < at + n; ++j) if (r[j] != 0.0f) return false; return true; };
+        const bool shortb = gr.window_switching && gr.block_type == 2;
+        const int long_end = !shortb ? 22 : gr.mixed ? (h.version == 0 ? 8 : 6) : 0;
+        const int short_start = !shortb ? 13 : gr.mixed ? 3 : 0;
+        int at = 576;
+        bool found_w[3] = {false, false, false};
+        for (int s = 12; s >= short_start; --s) {
+            const int n = kBandShort[h.band_row][s], sf = s == 12 ? 11 : s;
+            for (int w = 2; w >= 0; --w) {
+                at -= n;
+                if (!found_w[w] && !silent(at, n)) found_w[w] = true;
+                if (!found_w[w] && !gr.is_bad_s[sf][w]) intensity(at, n, gr.sf_s[sf][w]);
+                else if (ms) mid_side(at, n);
+            }
+        }
+        bool found = found_w[0] || found_w[1] || found_w[2];
+        for (int s = long_end - 1; s >= 0; --s) {
+            const int n = kBandLong[h.band_row][s], sf = s == 21 ? 20 : s;
+            at -= n;
+            if (!found && !silent(at, n)) found = true;
+            if (!found && !gr.is_bad_l[sf]) intensity(at, n, gr.sf_l[sf]);
+            else if (ms) mid_side(at, n);
         }
     }
 
@@ -383,7 +459,6 @@ struct Decoder {
             return;
         }
         const bool joint = h.mode == 1;
-        WB_REQUIRE(!(joint && (h.mode_ext & 1)), WB_EINVAL, "mpa: intensity stereo is not supported");
         Bits b{data.data(), data.size() * 8, 0};
         for (int gr = 0; gr < h.granules; ++gr) {
             static thread_local float xr[2][576];
@@ -392,18 +467,14 @@ struct Decoder {
                 Granule& q = g[gr][c];
                 const size_t end = b.pos + (size_t)q.part2_3_length;
                 if (h.version == 0) read_scalefactors_v1(b, q, gr == 1 ? &g[0][c] : nullptr, scfsi[c]);
-                else read_scalefactors_lsf(b, q, false);
+                else read_scalefactors_lsf(b, q, joint && (h.mode_ext & 1) && c == 1);
                 WB_REQUIRE(b.pos <= end, WB_EINVAL, "mpa: part2_3_length shorter than the scalefactors");
                 read_spectrum(h, b, q, end, is);
                 std::memset(xr[c], 0, sizeof xr[c]);
                 requantize(h, q, is, xr[c]);
             }
-            if (joint && (h.mode_ext & 2))                           // 2.4.3.4 MS stereo
-                for (int i = 0; i < 576; ++i) {
-                    const float m = xr[0][i], s = xr[1][i];
-                    xr[0][i] = (m + s) * 0.70710678118654752f;
-                    xr[1][i] = (m - s) * 0.70710678118654752f;
-                }
+            if (joint) stereo(h, g[gr][1], xr[0], xr[1]);
+            for (int c = 0; c < h.channels; ++c) reorder(h, g[gr][c], xr[c]);
             for (int c = 0; c < h.channels; ++c) {
                 float sbs[18][32];
                 hybrid(g[gr][c], xr[c], ch[c], sbs);
