@@ -20,6 +20,8 @@
 #include "../common.h"
 #include "mp3_tables.h"
 
+#pragma GCC optimize("O3")        // lets the y[i] += x[k] * table[k][i] loops vectorise (no reassociation: -ffp-contract=off, no fast-math)
+
 namespace wbmp3 {
 namespace {
 
@@ -84,7 +86,9 @@ struct Tables {
     Trie book[15];
     int book_of[32], linbits[32];
     Trie quad_a;
-    float win[4][36], cs[8], ca[8], synth_cos[64][32], imdct36[36][18], imdct12[12][6];
+    // cosine tables are stored input-major (table[k][i]) so that the sums below run as vectorisable y[i] += x[k] * table[k][i]
+    // updates that keep the textbook summation order
+    float win[4][36], cs[8], ca[8], synth_cos[32][64], synth_win[512], imdct36[18][36], imdct12[6][12];
     Tables() {
         for (int b = 0; b < 15; ++b) {
             const int n = kBookDim[b] * kBookDim[b];
@@ -111,14 +115,15 @@ struct Tables {
             win[1][i] = (float)(i < 18 ? s36 : i < 24 ? 1.0 : i < 30 ? std::sin(kPi / 12.0 * (i - 18 + 0.5)) : 0.0);
             win[3][i] = (float)(i < 6 ? 0.0 : i < 12 ? std::sin(kPi / 12.0 * (i - 6 + 0.5)) : i < 18 ? 1.0 : s36);
             win[2][i] = (float)(i < 12 ? std::sin(kPi / 12.0 * (i + 0.5)) : 0.0);
-            for (int k = 0; k < 18; ++k) imdct36[i][k] = (float)std::cos(kPi / 72.0 * (2 * i + 1 + 18) * (2 * k + 1));
+            for (int k = 0; k < 18; ++k) imdct36[k][i] = (float)std::cos(kPi / 72.0 * (2 * i + 1 + 18) * (2 * k + 1));
         }
         for (int i = 0; i < 12; ++i)
-            for (int k = 0; k < 6; ++k) imdct12[i][k] = (float)std::cos(kPi / 24.0 * (2 * i + 1 + 6) * (2 * k + 1));
+            for (int k = 0; k < 6; ++k) imdct12[k][i] = (float)std::cos(kPi / 24.0 * (2 * i + 1 + 6) * (2 * k + 1));
         static const double kC[8] = {-0.6, -0.535, -0.33, -0.185, -0.095, -0.041, -0.0142, -0.0037};
         for (int i = 0; i < 8; ++i) { cs[i] = (float)(1.0 / std::sqrt(1.0 + kC[i] * kC[i])); ca[i] = (float)(kC[i] / std::sqrt(1.0 + kC[i] * kC[i])); }
         for (int i = 0; i < 64; ++i)
-            for (int k = 0; k < 32; ++k) synth_cos[i][k] = (float)std::cos((16 + i) * (2 * k + 1) * kPi / 64.0);
+            for (int k = 0; k < 32; ++k) synth_cos[k][i] = (float)std::cos((16 + i) * (2 * k + 1) * kPi / 64.0);
+        for (int i = 0; i < 512; ++i) synth_win[i] = (float)kSynthWindowQ16[i] * (1.0f / 65536.0f);
     }
     static void insert(Trie& t, uint32_t code, int len, int sym) {
         int node = 0;
@@ -392,21 +397,22 @@ struct Decoder {
         for (int sb = 0; sb < 32; ++sb) {
             float out[36];
             const float* X = xr + 18 * sb;
-            if (shortb && !(q.mixed && sb < 2)) {
+            bool any = false;
+            for (int k = 0; k < 18; ++k) any |= X[k] != 0.0f;
+            if (!any) {                                                // an empty subband (most of the upper ones at speech bit rates)
                 std::memset(out, 0, sizeof out);
-                for (int win = 0; win < 3; ++win)
-                    for (int i = 0; i < 12; ++i) {
-                        float acc = 0.0f;
-                        for (int k = 0; k < 6; ++k) acc += X[3 * k + win] * T.imdct12[i][k];
-                        out[6 + 6 * win + i] += acc * T.win[2][i];
-                    }
+            } else if (shortb && !(q.mixed && sb < 2)) {
+                std::memset(out, 0, sizeof out);
+                for (int win = 0; win < 3; ++win) {
+                    float y[12] = {0};
+                    for (int k = 0; k < 6; ++k) for (int i = 0; i < 12; ++i) y[i] += X[3 * k + win] * T.imdct12[k][i];
+                    for (int i = 0; i < 12; ++i) out[6 + 6 * win + i] += y[i] * T.win[2][i];
+                }
             } else {
                 const float* w = T.win[(q.window_switching && !(q.mixed && sb < 2)) ? q.block_type : 0];
-                for (int i = 0; i < 36; ++i) {
-                    float acc = 0.0f;
-                    for (int k = 0; k < 18; ++k) acc += X[k] * T.imdct36[i][k];
-                    out[i] = acc * w[i];
-                }
+                float y[36] = {0};
+                for (int k = 0; k < 18; ++k) for (int i = 0; i < 36; ++i) y[i] += X[k] * T.imdct36[k][i];
+                for (int i = 0; i < 36; ++i) out[i] = y[i] * w[i];
             }
             for (int i = 0; i < 18; ++i) {
                 float v = out[i] + st.overlap[sb][i];
@@ -420,20 +426,16 @@ struct Decoder {
     // 2.4.3.2 synthesis subband filter: 32 subband samples -> 32 PCM samples
     void synth(ChannelState& st, const float s[32], float* pcm) {
         const Tables& T = tables();
-        st.v_off = (st.v_off - 64) & 1023;
-        float* v = st.v;
-        for (int i = 0; i < 64; ++i) {
-            float acc = 0.0f;
-            for (int k = 0; k < 32; ++k) acc += T.synth_cos[i][k] * s[k];
-            v[(st.v_off + i) & 1023] = acc;
-        }
-        for (int j = 0; j < 32; ++j) {
-            float acc = 0.0f;
-            for (int i = 0; i < 8; ++i) {
-                acc += v[(st.v_off + 128 * i + j) & 1023] * ((float)kSynthWindowQ16[64 * i + j] * (1.0f / 65536.0f));
-                acc += v[(st.v_off + 128 * i + 96 + j) & 1023] * ((float)kSynthWindowQ16[64 * i + 32 + j] * (1.0f / 65536.0f));
-            }
-            pcm[j] = acc;
+        st.v_off = (st.v_off - 64) & 1023;                           // a multiple of 64: the 64- and 32-sample runs below never wrap
+        float* v = st.v + st.v_off;
+        for (int i = 0; i < 64; ++i) v[i] = 0.0f;
+        for (int k = 0; k < 32; ++k) for (int i = 0; i < 64; ++i) v[i] += T.synth_cos[k][i] * s[k];
+        for (int j = 0; j < 32; ++j) pcm[j] = 0.0f;
+        for (int i = 0; i < 8; ++i) {
+            const float* a = st.v + ((st.v_off + 128 * i) & 1023);
+            const float* b = st.v + ((st.v_off + 128 * i + 96) & 1023);
+            const float* wa = T.synth_win + 64 * i;
+            for (int j = 0; j < 32; ++j) { pcm[j] += a[j] * wa[j]; pcm[j] += b[j] * wa[32 + j]; }
         }
     }
 
