@@ -524,12 +524,17 @@ void decode_to_mono(const uint8_t* p, size_t n, size_t first, std::vector<float>
     sr = (uint32_t)h0.sr;
     const int channels = h0.channels;
     size_t pos = first;
-    {   // Xing / Info / VBRI frame: read by the demuxer for its metadata, never decoded
+    {   // Xing / Info / VBRI frame: read by the demuxer for its metadata, never decoded.  The tag sits where the main data
+        // of an audio frame would start, behind an all-zero side information block (VBRI: at a fixed offset).
         const size_t off = 4 + h0.side_size;
-        if (pos + h0.frame_size <= n &&
-            ((off + 4 <= h0.frame_size && (std::memcmp(p + pos + off, "Xing", 4) == 0 || std::memcmp(p + pos + off, "Info", 4) == 0)) ||
-             (36 + 4 <= h0.frame_size && std::memcmp(p + pos + 36, "VBRI", 4) == 0)))
-            pos += h0.frame_size;
+        bool tag = false;
+        if (pos + h0.frame_size <= n && off + 4 <= h0.frame_size &&
+            (std::memcmp(p + pos + off, "Xing", 4) == 0 || std::memcmp(p + pos + off, "Info", 4) == 0)) {
+            tag = true;
+            for (size_t i = 4; i < off; ++i) tag = tag && p[pos + i] == 0;
+        }
+        if (pos + h0.frame_size <= n && 36 + 4 <= h0.frame_size && std::memcmp(p + pos + 36, "VBRI", 4) == 0) tag = true;
+        if (tag) pos += h0.frame_size;
     }
     Decoder dec;
     std::vector<float> out[2];
