@@ -69,6 +69,18 @@ def test_tables_are_what_the_standard_guarantees():
 
 
 RATES = [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2)]
+@needs_libav
+def test_committed_tables_are_what_the_generator_writes(tmp_path):
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_mp3_tables", os.path.join(root, "tools", "gen_mp3_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gen.main(str(tmp_path / "t.h"))                         # runs the generator's own checks (Kraft sums, symbol sets, band sums)
+    assert (tmp_path / "t.h").read_text() == open(gen.OUT).read()
+
+
 CASES = [(v, s, ch, ms, False, res) for (v, s), ch, ms, res in itertools.product(RATES, [1, 2], [False, True], [True, False]) if not (ms and ch == 1)]
 CASES += [(v, s, 2, ms, True, True) for (v, s), ms in itertools.product(RATES, [False, True])]          # intensity stereo, alone and with MS
 
