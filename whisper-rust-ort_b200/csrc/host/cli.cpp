@@ -390,6 +390,7 @@ struct Job {            // shared, read-only
     const GenCfg& gen;
     wb_model_cfg mc;
     std::string wpath;
+    size_t decode_threads = 1;      // host threads a group loader may use to decode its files (from --intra-op, capped)
 };
 struct Pcm {
     float* p = nullptr; int64_t n = 0; double dur = 0;
@@ -428,14 +429,33 @@ LoadedGroup load_group(const Job& J, int device, const std::vector<std::pair<siz
     const size_t n = L.g1 - L.g0;
     std::vector<Pcm> au(n);
     L.offs.assign(n + 1, 0); L.dur.resize(n); L.load_s.resize(n);
+    // files of a group are independent: decode them on up to decode_threads host threads (a group of one file, the
+    // reference's serial loop, stays on this thread); the first failure in file order is the one reported
+    std::vector<std::exception_ptr> err(n);
+    std::atomic<size_t> next_file{0};
+    auto decode_files = [&]() {
+        for (size_t i; (i = next_file.fetch_add(1)) < n;) {
+            try {
+                auto tl0 = Clock::now();
+                Pcm& p = au[i];
+                CK(wb_host_load_audio_16k_mono(join(J.args.audio_dir, J.files[L.g0 + i]).c_str(), &p.p, &p.n, &p.dur));
+                WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
+                L.dur[i] = p.dur;
+                L.load_s[i] = since(tl0);
+            } catch (...) {
+                err[i] = std::current_exception();
+            }
+        }
+    };
+    {
+        std::vector<std::thread> helpers;
+        for (size_t t = 1; t < std::min(J.decode_threads, n); ++t) helpers.emplace_back(decode_files);
+        decode_files();
+        for (std::thread& t : helpers) t.join();
+    }
     for (size_t i = 0; i < n; ++i) {
-        auto tl0 = Clock::now();
-        Pcm& p = au[i];
-        CK(wb_host_load_audio_16k_mono(join(J.args.audio_dir, J.files[L.g0 + i]).c_str(), &p.p, &p.n, &p.dur));
-        WB_REQUIRE(p.n > 0, WB_EINVAL, "Empty audio");
-        L.offs[i + 1] = L.offs[i] + p.n;
-        L.dur[i] = p.dur;
-        L.load_s[i] = since(tl0);
+        if (err[i]) std::rethrow_exception(err[i]);
+        L.offs[i + 1] = L.offs[i] + au[i].n;
     }
     auto tc0 = Clock::now();
     slot.reserve(device, (size_t)L.offs.back());
@@ -618,7 +638,8 @@ int run(const Args& args) {
     std::vector<std::pair<size_t, size_t>> groups;
     for (size_t g0 = 0; g0 < files.size(); g0 += args.file_batch) groups.push_back({g0, std::min(files.size(), g0 + args.file_batch)});
     const size_t world = std::min(args.gpus, groups.size());
-    const Job job{args, files, tk.t, gen, mc, wpath};
+    // --intra-op is the reference's "CPU threads per unit of work" knob; here the CPU work of a unit is audio decode
+    const Job job{args, files, tk.t, gen, mc, wpath, std::max<size_t>(1, std::min<size_t>(cfg.intra_op, 8))};
     TRACE("%zu files in %zu groups, %zu worker process(es) x %zu in flight", files.size(), groups.size(), world, args.in_flight);
     std::vector<FileResult> results(files.size());
     if (world <= 1) {
