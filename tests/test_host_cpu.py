@@ -260,3 +260,14 @@ def test_cli_without_a_gpu_fails_loudly_in_both_scheduler_modes(wb, tmp_path):
         assert r.returncode == 1 and msg in r.stderr, r.stderr
         assert not (out_dir / "a.csv").exists()
         assert not [p for p in out_dir.iterdir() if p.name.endswith(".rows")]
+
+
+def test_known_answer_digest_is_the_reference_transcripts():
+    # tests/test_gpu_known_answer.py compares the drop-in's transcript of audio/audio.wav with the Rust binary's by digest
+    # (the reference's file is not copied into this repo): the digest it holds must be that file's
+    import hashlib
+    import test_gpu_known_answer as ka
+    if not os.path.exists(ka.REF_TRANSCRIPT):
+        pytest.skip("reference checkout not present")
+    t = open(ka.REF_TRANSCRIPT, encoding="utf-8").read().strip()
+    assert (hashlib.sha256(t.encode()).hexdigest(), len(t), len(t.split())) == (ka.WANT_SHA256, ka.WANT_CHARS, ka.WANT_WORDS)
