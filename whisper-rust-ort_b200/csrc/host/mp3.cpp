@@ -301,15 +301,12 @@ struct Decoder {
             for (int k = 0; k < kBandLong[h.band_row][s]; ++k, ++i) xr[i] = deq(is[i], e);
         }
         if (!shortb) return;
-        int s0 = q.mixed ? 3 : 0, start = 0;
-        for (int s = 0; s < s0; ++s) start += kBandShort[h.band_row][s];
-        for (int s = s0; s < 13; ++s) {
+        for (int s = q.mixed ? 3 : 0; s < 13; ++s) {
             const int w = kBandShort[h.band_row][s];
             for (int win = 0; win < 3; ++win) {
                 const double e = (q.global_gain - 210 - 8 * q.subblock_gain[win]) / 4.0 - mult * (s < 12 ? q.sf_s[s][win] : 0);
                 for (int k = 0; k < w; ++k, ++i) xr[i] = deq(is[i], e);
             }
-            start += w;
         }
     }
 
