@@ -62,3 +62,25 @@ def test_weights_from_onnx_export_and_blob(wb, tmp_path):
         toks = m.greedy_decode(1, [1, 2, 3, 4], 4, 1030)
         assert toks == ref.greedy(want, [1, 2, 3, 4], 4, 1030)
         m.close()
+
+
+def test_weights_from_a_real_torch_onnx_export(wb, tmp_path):
+    """The same path on a REAL torch.onnx export of HF's WhisperForConditionalGeneration (tests/torch_export.py: the exporter
+    optimum calls; anonymous MatMul weights, folded encoder position table): the context created from the export directory
+    encodes and greedy-decodes like the oracle run on the HF state_dict."""
+    pytest.importorskip("transformers")
+    import torch_export
+    try:
+        sd = torch_export.export(str(tmp_path / "onnx"), randomize=True, seed=5)
+    except (ImportError, AttributeError) as e:
+        pytest.skip(f"torch.onnx TorchScript exporter not usable here: {e}")
+    mc = wb.weights.WHISPER_TOY
+    W = {name: sd[name].reshape(shape) for name, shape, *_ in wb.weights.tensor_specs(mc)}
+    ref = wr.WhisperRef(mc, W)
+    mel = np.random.default_rng(2).normal(0, 0.5, (2, 80, 3000)).astype(np.float32)
+    want = ref.encode(mel)
+    m = wb.Whisper(wb.default_cfg("toy", max_batch=2, max_chunks=2), weights_path=str(tmp_path / "onnx"))
+    assert np.array_equal(m.tensor("model.encoder.embed_positions.weight", (1500, 128)), W["model.encoder.embed_positions.weight"])
+    assert np.abs(m.encode(mel) - want).max() <= 1e-4
+    assert m.greedy_decode(2, [1, 2, 3, 4], 6, 1030) == ref.greedy(want, [1, 2, 3, 4], 6, 1030)
+    m.close()

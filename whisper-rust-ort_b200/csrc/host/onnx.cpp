@@ -14,8 +14,12 @@
 // (encoder layer: q, k, v, out, fc1, fc2; decoder layer: self q, k, v, out, cross q, k, v, out,
 // fc1, fc2; then the tied proj_out).  Shapes are checked for every assignment.
 //
-// No .onnx file exists offline, so this reader is exercised on files synthesised by
-// tests/onnx_writer.py with exactly that structure; it has not met a real optimum export yet.
+// Two more things the real exporter does (found by exporting HF's WhisperForConditionalGeneration with torch.onnx in
+// tests/test_onnx_torch_export_cpu.py): identical initializers are de-duplicated into Identity aliases, and the
+// encoder's position table is folded into an anonymous `onnx::Add_<n>` initializer.  Both are handled below.
+//
+// No optimum export of the real checkpoint exists offline: the reader is exercised on files synthesised
+// by tests/onnx_writer.py and on torch.onnx exports of a randomly initialised HF model of the toy shape.
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -136,6 +140,21 @@ void load(const std::string& path, Model& m) {
         } else r.skip(wt);
     }
     WB_REQUIRE(have_graph, WB_EIO, "%s is not an ONNX ModelProto (no graph)", path.c_str());
+    // torch.onnx de-duplicates identical initializers (all-zero biases, all-one LayerNorm weights of an untrained
+    // model; it can happen to trained tensors too): one copy stays an initializer, every other name becomes the output
+    // of an Identity node fed by it.  Resolve those aliases (chains included) so that lookups by name see them.
+    for (bool grew = true; grew;) {
+        grew = false;
+        for (const Node& nd : m.nodes) {
+            if (nd.op != "Identity" || nd.in.size() != 1 || nd.out.size() != 1 || m.init.count(nd.out[0])) continue;
+            auto it = m.init.find(nd.in[0]);
+            if (it == m.init.end()) continue;
+            Tensor alias = it->second;
+            alias.name = nd.out[0];
+            m.init[nd.out[0]] = std::move(alias);
+            grew = true;
+        }
+    }
 }
 
 static float half_to_float(uint16_t h) {
@@ -314,7 +333,25 @@ void onnx_load_dir(const std::string& dir, const wb_model_cfg& c, std::map<std::
         take_named(enc, pre, "conv1.bias", hp + "conv1.bias", {d});
         take_named(enc, pre, "conv2.weight", hp + "conv2.weight", {d, d, 3});
         take_named(enc, pre, "conv2.bias", hp + "conv2.bias", {d});
-        take_named(enc, pre, "embed_positions.weight", hp + "embed_positions.weight", {c.n_audio_ctx, d});
+        if (find_named(enc, "embed_positions.weight", pre)) {
+            take_named(enc, pre, "embed_positions.weight", hp + "embed_positions.weight", {c.n_audio_ctx, d});
+        } else {
+            // the encoder adds the whole position table to the conv output, so torch.onnx folds `embed_positions.weight`
+            // into an anonymous `onnx::Add_<n>` initializer: take THE [n_audio_ctx, d] initializer that feeds an Add
+            const Tensor* pos = nullptr;
+            for (const auto& n : enc.nodes) {
+                if (n.op != "Add") continue;
+                for (const auto& i : n.in) {
+                    auto it = enc.init.find(i);
+                    if (it == enc.init.end() || it->second.dims != std::vector<int64_t>{c.n_audio_ctx, d}) continue;
+                    WB_REQUIRE(pos == nullptr || pos == &it->second, WB_EINVAL, "ONNX: two candidates for the encoder position table (%s, %s)",
+                               pos->name.c_str(), it->second.name.c_str());
+                    pos = &it->second;
+                }
+            }
+            WB_REQUIRE(pos != nullptr, WB_EINVAL, "ONNX export misses initializer embed_positions.weight");
+            host[hp + "embed_positions.weight"] = to_f32(*pos);
+        }
         std::vector<Lin> lins;
         for (int i = 0; i < c.enc_layers; ++i) {
             const std::string L = "layers." + std::to_string(i) + ".";
