@@ -185,3 +185,24 @@ def test_damaged_streams_fail_or_decode_but_never_crash(L):
             outcomes.add("error")
             assert str(e)
     assert outcomes == {"decoded", "error"}
+
+
+def test_loader_is_reentrant(wb, L, tmp_path):
+    """The CLI's group loader decodes the files of a group on several host threads: concurrent calls (WAV and MP3 mixed, the
+    decoder's tables built on first use) return exactly what the serial calls return."""
+    from concurrent.futures import ThreadPoolExecutor
+    paths = []
+    for i in range(6):
+        frames, _ = mw.make_stream(seed=20 + i, version=i % 3, sr_idx=i % 3, br_idx=9 if i % 3 == 0 else 8, channels=1 + i % 2, n_frames=40, ms=bool(i % 2))
+        p = tmp_path / f"m{i}.mp3"
+        p.write_bytes(b"".join(frames))
+        paths.append(p)
+    for i in range(4):
+        p = tmp_path / f"w{i}.wav"
+        wb.synth.write_wav(str(p), wb.synth.clip(i, 2, 1.5), sr=[16000, 22050, 44100, 8000][i], fmt=["s16", "f32", "u8", "s16"][i])
+        paths.append(p)
+    serial = [load(L, p) for p in paths]
+    with ThreadPoolExecutor(8) as ex:
+        for _ in range(3):
+            for (a, da), (b, db) in zip(ex.map(lambda q: load(L, q), paths * 4), serial * 4):
+                assert da == db and np.array_equal(a, b)
