@@ -21,6 +21,12 @@
 #include "mp3_tables.h"
 
 #pragma GCC optimize("O3")        // lets the y[i] += x[k] * table[k][i] loops vectorise (no reassociation: -ffp-contract=off, no fast-math)
+// the two filterbank routines are also built for AVX2 and picked at load time (same operations in the same order, 8 lanes wide)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define WB_MP3_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define WB_MP3_CLONES
+#endif
 
 namespace wbmp3 {
 namespace {
@@ -381,7 +387,7 @@ struct Decoder {
     }
 
     // 2.4.3.4 alias reduction, IMDCT with windowing and overlap-add, frequency inversion
-    void hybrid(const Granule& q, float xr[576], ChannelState& st, float sb_out[18][32]) {
+    WB_MP3_CLONES void hybrid(const Granule& q, float xr[576], ChannelState& st, float sb_out[18][32]) {
         const Tables& T = tables();
         const bool shortb = q.window_switching && q.block_type == 2;
         const int alias_sb = shortb ? (q.mixed ? 2 : 0) : 32;
@@ -421,19 +427,24 @@ struct Decoder {
     }
 
     // 2.4.3.2 synthesis subband filter: 32 subband samples -> 32 PCM samples
-    void synth(ChannelState& st, const float s[32], float* pcm) {
+    WB_MP3_CLONES void synth(ChannelState& st, const float s[32], float* pcm) {
         const Tables& T = tables();
         st.v_off = (st.v_off - 64) & 1023;                           // a multiple of 64: the 64- and 32-sample runs below never wrap
-        float* v = st.v + st.v_off;
-        for (int i = 0; i < 64; ++i) v[i] = 0.0f;
-        for (int k = 0; k < 32; ++k) for (int i = 0; i < 64; ++i) v[i] += T.synth_cos[k][i] * s[k];
-        for (int j = 0; j < 32; ++j) pcm[j] = 0.0f;
+        float acc[64] = {0};                                         // local accumulators: no aliasing with the tables, stay in registers
+        for (int k = 0; k < 32; ++k) {
+            const float sk = s[k];
+            const float* c = T.synth_cos[k];
+            for (int i = 0; i < 64; ++i) acc[i] += c[i] * sk;
+        }
+        std::memcpy(st.v + st.v_off, acc, sizeof acc);
+        float out[32] = {0};
         for (int i = 0; i < 8; ++i) {
             const float* a = st.v + ((st.v_off + 128 * i) & 1023);
             const float* b = st.v + ((st.v_off + 128 * i + 96) & 1023);
             const float* wa = T.synth_win + 64 * i;
-            for (int j = 0; j < 32; ++j) { pcm[j] += a[j] * wa[j]; pcm[j] += b[j] * wa[32 + j]; }
+            for (int j = 0; j < 32; ++j) { out[j] += a[j] * wa[j]; out[j] += b[j] * wa[32 + j]; }
         }
+        std::memcpy(pcm, out, sizeof out);
     }
 
     // one frame -> granules * 576 samples per channel, appended to out[c]
