@@ -4,6 +4,12 @@ Python restatement of the host-side (non-tensor) functions on the reference's ho
 following /root/reference/src/main.rs line by line; used by tests/ to check the C++ host in
 whisper-rust-ort_b200/csrc/host/.  Pinned by the reference's own committed outputs where they
 exist (results.old/.../inference_summary.json, inference_per_file.csv: schema, rounding, key order).
+
+Audio decode: the RIFF/WAVE reader is restated here (read_wav_symphonia).  MPEG Layer III has NO restatement in
+oracle/: its decoder lives in a dependency (symphonia-bundle-mp3 0.5.x) absent from /root/reference, and MP3
+decoding is only defined up to floating-point rounding, so a second implementation by the same hand would pin
+nothing.  The checker for csrc/host/mp3.cpp is an independent conforming decoder instead (tests/libav_ref.py:
+libavcodec's mp3float), fed by tests/mp3_writer.py; see DESIGN.md section 3.
 """
 from __future__ import annotations
 
