@@ -1,0 +1,41 @@
+"""CPU: oracle/whisper_ref.py against the exported ONNX GRAPH itself.  tests/torch_export.py writes a real torch.onnx export of
+HF's Whisper (the exporter optimum calls for the reference's whisper-base-with-past); tests/onnx_eval.py evaluates those
+graphs node by node in numpy — the arithmetic `ort::Session::run` performs at main.rs:703 (encoder) and :770 (decoder) —
+and the oracle, given the same weights, must reproduce the graph's outputs: encoder hidden states and next-token logits
+within 1e-4 absolute (the fp32 bar of north_star), same arg-max.  This ties the oracle to what ONNX Runtime executes, not only
+to HF's eager forward (tests/golden/)."""
+import numpy as np
+import pytest
+
+pytest.importorskip("transformers")
+import onnx_eval  # noqa: E402
+import torch_export  # noqa: E402
+import whisper_ref as wr  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def exported(wb, tmp_path_factory):
+    d = tmp_path_factory.mktemp("graph")
+    try:
+        sd = torch_export.export(str(d), randomize=True, seed=9)
+    except (ImportError, AttributeError) as e:
+        pytest.skip(f"torch.onnx TorchScript exporter not usable here: {e}")
+    mc = wb.weights.WHISPER_TOY
+    W = {name: sd[name].reshape(shape) for name, shape, *_ in wb.weights.tensor_specs(mc)}
+    return d, wr.WhisperRef(mc, W)
+
+
+def test_encoder_and_decoder_graphs(exported):
+    d, oracle = exported
+    rng = np.random.default_rng(4)
+    for trial, ids in enumerate([[1, 5, 7, 9], [1, 1030, 2, 400], [3, 3, 3, 3]]):
+        mel = rng.normal(0, 0.6, (1, 80, 3000)).astype(np.float32)
+        hidden = onnx_eval.run(str(d / "encoder_model.onnx"), {"input_features": mel})["last_hidden_state"]
+        want = oracle.encode(mel)
+        assert hidden.shape == want.shape == (1, 1500, 128)
+        assert np.abs(hidden - want).max() <= 1e-4
+        logits = onnx_eval.run(str(d / "decoder_model.onnx"), {"input_ids": np.array([ids], np.int64), "encoder_hidden_states": hidden,
+                                                                 "position_ids": np.arange(4, dtype=np.int64)[None]})["logits"]
+        toks, lg = oracle.greedy(want, ids, 1, 1030, [], [], return_logits=True)
+        assert np.abs(logits[0, -1] - lg[0][0]).max() <= 1e-4
+        assert int(logits[0, -1].argmax()) == toks[0][-1]
