@@ -36,6 +36,7 @@ def test_encoder_and_decoder_graphs(exported):
         assert np.abs(hidden - want).max() <= 1e-4
         logits = onnx_eval.run(str(d / "decoder_model.onnx"), {"input_ids": np.array([ids], np.int64), "encoder_hidden_states": hidden,
                                                                  "position_ids": np.arange(4, dtype=np.int64)[None]})["logits"]
-        toks, lg = oracle.greedy(want, ids, 1, 1030, [], [], return_logits=True)
-        assert np.abs(logits[0, -1] - lg[0][0]).max() <= 1e-4
-        assert int(logits[0, -1].argmax()) == toks[0][-1]
+        for k in range(1, 5):                                # causal mask: position k-1 of the graph sees the first k tokens only
+            toks, lg = oracle.greedy(want, ids[:k], 1, 1030, [], [], return_logits=True)
+            assert np.abs(logits[0, k - 1] - lg[0][0]).max() <= 1e-4
+            assert int(logits[0, k - 1].argmax()) == toks[0][-1]
