@@ -101,7 +101,7 @@ def test_same_pcm_as_libavcodec(L, version, sr_idx, channels, ms, intensity, res
 
 @needs_libav
 @pytest.mark.parametrize("version,sr_idx", [(0, 0), (0, 1), (1, 2), (2, 2)])
-def test_file_through_the_loader(L, tmp_path, version, sr_idx):
+def test_file_through_the_loader(wb, L, tmp_path, version, sr_idx):
     """ID3v2 in front, an Info frame first, an ID3v1 tag and half a frame behind: the loader returns the channel mean of the
     audio frames only, resampled like main.rs:207-226."""
     channels = 2
@@ -122,6 +122,8 @@ def test_file_through_the_loader(L, tmp_path, version, sr_idx):
     q = tmp_path / "misnamed.wav"
     q.write_bytes(blob)
     assert np.array_equal(load(L, q)[0], got)
+    pcm, seconds = wb.load_audio(p)                                          # the Python mirror of load_audio_16k_mono
+    assert np.array_equal(pcm, got) and seconds == dur
 
 
 @pytest.mark.parametrize("line", [7, 25, 40, 300])

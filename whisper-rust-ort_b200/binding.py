@@ -119,6 +119,21 @@ def default_cfg(name: str = "base", precision: int = WB_PREC_FP32, max_batch: in
     return cfg
 
 
+def load_audio(path: str):
+    """load_audio_16k_mono (main.rs:228-316) through the C ABI: RIFF/WAVE or MPEG Layer III file -> (mono f32 PCM at
+    16 kHz, duration in seconds).  Host-only: works without a GPU."""
+    L = lib()
+    f32p = C.POINTER(C.c_float)
+    L.wb_host_load_audio_16k_mono.argtypes = [C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.wb_host_free.argtypes = [C.c_void_p]
+    buf, n, dur = f32p(), C.c_int64(), C.c_double()
+    _chk(L.wb_host_load_audio_16k_mono(os.fspath(path).encode(), C.byref(buf), C.byref(n), C.byref(dur)))
+    try:
+        return np.ctypeslib.as_array(buf, (max(n.value, 1),))[:n.value].copy(), dur.value
+    finally:
+        L.wb_host_free(buf)
+
+
 def model_cfg_of(cfg: wb_model_cfg) -> ModelCfg:
     return ModelCfg(cfg.n_mels, cfg.d_model, cfg.n_heads, cfg.ffn_dim, cfg.enc_layers, cfg.dec_layers, cfg.vocab,
                     cfg.n_audio_ctx, cfg.n_text_ctx)
