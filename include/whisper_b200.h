@@ -245,6 +245,9 @@ int wb_onnx_read_tensor(const char* onnx_dir, const wb_model_cfg* cfg, const cha
 
 /* The drop-in CLI (main.rs:23-86 flag surface, :1065-1271 driver) as a callable. */
 int wb_cli_main(int argc, const char* const* argv);
+/* Architecture fields of `cfg` from the HF config.json optimum writes into the export directory (the reference reads shapes
+ * from the ONNX graphs themselves; the CLI uses this when --arch is not given). Other fields of `cfg` are left alone. */
+int wb_cfg_from_hf_config(const char* config_json_path, wb_model_cfg* cfg);
 
 #ifdef __cplusplus
 }

@@ -271,3 +271,29 @@ def test_known_answer_digest_is_the_reference_transcripts():
         pytest.skip("reference checkout not present")
     t = open(ka.REF_TRANSCRIPT, encoding="utf-8").read().strip()
     assert (hashlib.sha256(t.encode()).hexdigest(), len(t), len(t.split())) == (ka.WANT_SHA256, ka.WANT_CHARS, ka.WANT_WORDS)
+
+
+def test_architecture_from_hf_config_json(wb, tmp_path):
+    # the export directory's config.json sizes the model when --arch is not given (the reference takes shapes from the graphs)
+    L = wb.lib()
+    L.wb_cfg_from_hf_config.argtypes = [C.c_char_p, C.c_void_p]
+    transformers = pytest.importorskip("transformers")
+    for name, kw in [("toy", dict(vocab_size=1031, num_mel_bins=80, d_model=128, encoder_layers=2, decoder_layers=2, encoder_attention_heads=2,
+                                  decoder_attention_heads=2, encoder_ffn_dim=256, decoder_ffn_dim=256, max_source_positions=1500,
+                                  max_target_positions=448)),
+                     ("large-v3", dict(vocab_size=51866, num_mel_bins=128, d_model=1280, encoder_layers=32, decoder_layers=32,
+                                       encoder_attention_heads=20, decoder_attention_heads=20, encoder_ffn_dim=5120, decoder_ffn_dim=5120))]:
+        d = tmp_path / name
+        transformers.WhisperConfig(**kw).save_pretrained(str(d))            # writes config.json the way optimum leaves it
+        cfg = wb.default_cfg("base", precision=wb.WB_PREC_BF16, max_batch=7)
+        assert L.wb_cfg_from_hf_config(str(d / "config.json").encode(), C.byref(cfg)) == 0, L.wb_last_error()
+        assert wb.binding.model_cfg_of(cfg) == wb.binding.model_cfg_of(wb.default_cfg(name))
+        assert (cfg.precision, cfg.max_batch) == (wb.WB_PREC_BF16, 7)        # everything else is left alone
+    bad = tmp_path / "bad.json"
+    bad.write_text(json.dumps({"d_model": 512, "num_mel_bins": 80}))
+    cfg = wb.default_cfg("base")
+    assert L.wb_cfg_from_hf_config(str(bad).encode(), C.byref(cfg)) != 0 and b"encoder_attention_heads" in L.wb_last_error()
+    assert wb.binding.model_cfg_of(cfg) == wb.weights.WHISPER_BASE            # untouched on failure
+    ref_cfg = "/root/reference/config.json"
+    if os.path.exists(ref_cfg) and "d_model" in open(ref_cfg).read():
+        assert L.wb_cfg_from_hf_config(ref_cfg.encode(), C.byref(cfg)) == 0

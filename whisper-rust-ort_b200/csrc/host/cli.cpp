@@ -66,6 +66,7 @@ struct Args {
     // extensions (not in the reference)
     int device = 0;
     std::string precision = "bf16", weights, arch = "base";
+    bool arch_given = false;
     uint64_t seed = 0;
     int batch = 32;
     size_t file_batch = 1;      // files transcribed together (1 = the reference's serial per-file loop)
@@ -161,7 +162,7 @@ Args parse_args(int argc, const char* const* argv) {
         else if (flag == "--device") a.device = (int)to_usize(need(i, flag, iv, has_inline), flag);
         else if (flag == "--precision") a.precision = need(i, flag, iv, has_inline);
         else if (flag == "--weights") a.weights = need(i, flag, iv, has_inline);
-        else if (flag == "--arch") a.arch = need(i, flag, iv, has_inline);
+        else if (flag == "--arch") { a.arch = need(i, flag, iv, has_inline); a.arch_given = true; }
         else if (flag == "--seed") a.seed = to_usize(need(i, flag, iv, has_inline), flag);
         else if (flag == "--batch") a.batch = (int)to_usize(need(i, flag, iv, has_inline), flag);
         else if (flag == "--file-batch") a.file_batch = std::max<size_t>(1, to_usize(need(i, flag, iv, has_inline), flag));
@@ -313,6 +314,41 @@ GenCfg load_generation_cfg(const std::string& path) {                           
 }
 
 struct Timing { double preprocess_s = 0, model_only_s = 0, decode_s = 0, end_to_end_s = 0; };
+
+}  // namespace
+
+// The architecture of an export directory from the HF `config.json` optimum writes next to the .onnx files.  The reference
+// needs no such thing (the ONNX graphs carry their shapes, so `--onnx-dir` may hold any Whisper size); here the shapes size
+// the device buffers.  Returns WB_OK and fills the nine architecture fields, or an error when a field is missing.
+extern "C" int wb_cfg_from_hf_config(const char* config_json_path, wb_model_cfg* cfg) {
+    try {
+        WB_REQUIRE(config_json_path && cfg, WB_EINVAL, "null argument");
+        WB_REQUIRE(is_file(config_json_path), WB_EIO, "no such file: %s", config_json_path);
+        wbjson::Value v = wbjson::parse(read_file(config_json_path));
+        auto field = [&](const char* key) -> int32_t {
+            const wbjson::Value& x = v[key];
+            WB_REQUIRE(!x.is_null() && x.num() >= 1 && x.num() == (double)(int32_t)x.num(), WB_EINVAL, "%s: no usable \"%s\"", config_json_path, key);
+            return (int32_t)x.num();
+        };
+        wb_model_cfg c = *cfg;
+        c.n_mels = field("num_mel_bins"); c.d_model = field("d_model"); c.n_heads = field("encoder_attention_heads");
+        c.ffn_dim = field("encoder_ffn_dim"); c.enc_layers = field("encoder_layers"); c.dec_layers = field("decoder_layers");
+        c.vocab = field("vocab_size"); c.n_audio_ctx = field("max_source_positions"); c.n_text_ctx = field("max_target_positions");
+        WB_REQUIRE(field("decoder_attention_heads") == c.n_heads && field("decoder_ffn_dim") == c.ffn_dim, WB_EINVAL,
+                   "%s: encoder and decoder widths differ (not a Whisper layout)", config_json_path);
+        WB_REQUIRE(c.d_model % c.n_heads == 0, WB_EINVAL, "%s: d_model %d is not a multiple of %d heads", config_json_path, c.d_model, c.n_heads);
+        *cfg = c;
+        return WB_OK;
+    } catch (const WbError& e) {
+        wb_set_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        wb_set_error(e.what());
+        return WB_EINVAL;
+    }
+}
+
+namespace {
 
 #define CK(call)                                                  \
     do {                                                          \
@@ -613,6 +649,11 @@ int run(const Args& args) {
                         "using seeded random-init %s weights\n", args.onnx_dir.c_str(), args.arch.c_str());
     wb_model_cfg mc;
     CK(wb_default_cfg(&mc, args.arch.c_str()));
+    // like the reference, take the model size from the export directory: its config.json wins unless --arch was given
+    if (!args.arch_given && is_file(join(args.onnx_dir, "config.json")) &&
+        wb_cfg_from_hf_config(join(args.onnx_dir, "config.json").c_str(), &mc) != WB_OK)
+        fprintf(stderr, "note: %s is not a Whisper config (%s): keeping --arch %s\n", join(args.onnx_dir, "config.json").c_str(),
+                wb_last_error(), args.arch.c_str());
     WB_REQUIRE(args.precision == "bf16" || args.precision == "fp32", WB_EINVAL, "--precision must be bf16 or fp32");
     mc.precision = args.precision == "bf16" ? WB_PREC_BF16 : WB_PREC_FP32;
     mc.max_batch = std::max(1, args.batch);
