@@ -208,3 +208,17 @@ def test_loader_is_reentrant(wb, L, tmp_path):
         for _ in range(3):
             for (a, da), (b, db) in zip(ex.map(lambda q: load(L, q), paths * 4), serial * 4):
                 assert da == db and np.array_equal(a, b)
+
+
+def test_random_bytes_are_not_mistaken_for_mpeg_audio(L, tmp_path):
+    """The probe wants two consecutive frame headers of one stream (like symphonia's strict first-frame read): noise, text and
+    a lone header do not pass; the loader then reports the container as unsupported."""
+    rng = np.random.default_rng(5)
+    frames, _ = mw.make_stream(seed=2, channels=1, n_frames=2)
+    blobs = [rng.integers(0, 256, 4096, dtype=np.uint8).tobytes() for _ in range(100)]
+    blobs += [b"just some text, not audio at all\n" * 100, frames[0][:4] + bytes(2000), b"\xff" * 3000]
+    for i, blob in enumerate(blobs):
+        p = tmp_path / f"n{i}.mp3"
+        p.write_bytes(blob)
+        with pytest.raises(RuntimeError, match="unsupported audio container"):
+            load(L, p)
