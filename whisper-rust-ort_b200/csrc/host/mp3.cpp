@@ -11,6 +11,8 @@
 //  * every frame yields 1152 (MPEG-1) or 576 (LSF) samples per channel; the channel count is the first frame's;
 //  * a frame cut off by the end of the file is an IoError -> `break` (main.rs:258-262): dropped;
 //  * Layer I / II (cargo feature "mp3" builds Layer III only) and free-format streams are errors.
+// Known limit: mixed blocks at 8 kHz (MPEG-2.5), where the long-window part spans four subbands instead of two, are
+// windowed as if it spanned two (libavcodec refuses that combination as well; no encoder is known to produce it).
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
