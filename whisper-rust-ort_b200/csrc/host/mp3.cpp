@@ -296,24 +296,29 @@ struct Decoder {
     void requantize(const Header& h, const Granule& q, const int is[576], float xr[576]) {
         static const int kPretab[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
         const double mult = q.scalefac_scale ? 1.0 : 0.5;
-        auto deq = [](int v, double e) -> float {
+        static const std::vector<double> pow43 = [] {                // |is| <= 15 + 2^13 - 1
+            std::vector<double> t(8207);
+            for (int v = 0; v < 8207; ++v) t[(size_t)v] = std::pow((double)v, 4.0 / 3.0);
+            return t;
+        }();
+        auto deq = [](int v, double gain) -> float {
             if (v == 0) return 0.0f;
-            const double m = std::pow((double)(v < 0 ? -v : v), 4.0 / 3.0) * std::exp2(e);
+            const double m = pow43[(size_t)(v < 0 ? -v : v)] * gain;
             return (float)(v < 0 ? -m : m);
         };
         const bool shortb = q.window_switching && q.block_type == 2;
         int i = 0;
         const int long_bands = !shortb ? 22 : q.mixed ? (h.version == 0 ? 8 : 6) : 0;
         for (int s = 0; s < long_bands; ++s) {
-            const double e = (q.global_gain - 210) / 4.0 - mult * ((s < 21 ? q.sf_l[s] : 0) + (q.preflag ? kPretab[s] : 0));
-            for (int k = 0; k < kBandLong[h.band_row][s]; ++k, ++i) xr[i] = deq(is[i], e);
+            const double g = std::exp2((q.global_gain - 210) / 4.0 - mult * ((s < 21 ? q.sf_l[s] : 0) + (q.preflag ? kPretab[s] : 0)));
+            for (int k = 0; k < kBandLong[h.band_row][s]; ++k, ++i) xr[i] = deq(is[i], g);
         }
         if (!shortb) return;
         for (int s = q.mixed ? 3 : 0; s < 13; ++s) {
             const int w = kBandShort[h.band_row][s];
             for (int win = 0; win < 3; ++win) {
-                const double e = (q.global_gain - 210 - 8 * q.subblock_gain[win]) / 4.0 - mult * (s < 12 ? q.sf_s[s][win] : 0);
-                for (int k = 0; k < w; ++k, ++i) xr[i] = deq(is[i], e);
+                const double g = std::exp2((q.global_gain - 210 - 8 * q.subblock_gain[win]) / 4.0 - mult * (s < 12 ? q.sf_s[s][win] : 0));
+                for (int k = 0; k < w; ++k, ++i) xr[i] = deq(is[i], g);
             }
         }
     }
