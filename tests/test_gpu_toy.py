@@ -83,4 +83,15 @@ def test_weights_from_a_real_torch_onnx_export(wb, tmp_path):
     assert np.array_equal(m.tensor("model.encoder.embed_positions.weight", (1500, 128)), W["model.encoder.embed_positions.weight"])
     assert np.abs(m.encode(mel) - want).max() <= 1e-4
     assert m.greedy_decode(2, [1, 2, 3, 4], 6, 1030) == ref.greedy(want, [1, 2, 3, 4], 6, 1030)
+    # ... and, without the oracle in between, like the exported GRAPHS evaluated node by node (tests/onnx_eval.py: what
+    # ort::Session::run computes at main.rs:703 / :770): encoder hidden states and the first new token's logits within 1e-4
+    import onnx_eval
+    hidden = onnx_eval.run(str(tmp_path / "onnx" / "encoder_model.onnx"), {"input_features": mel[:1]})["last_hidden_state"]
+    got = m.encode(mel)
+    assert np.abs(got[:1] - hidden).max() <= 1e-4
+    ids = [1, 5, 7, 9]
+    graph_logits = onnx_eval.run(str(tmp_path / "onnx" / "decoder_model.onnx"), {"input_ids": np.array([ids], np.int64), "encoder_hidden_states": hidden,
+                                                                                  "position_ids": np.arange(4, dtype=np.int64)[None]})["logits"]
+    toks, lg = m.greedy_decode(2, ids, 1, 1030, want_logits=True)
+    assert np.abs(np.asarray(lg)[0, 0] - graph_logits[0, -1]).max() <= 1e-4 and toks[0][-1] == int(graph_logits[0, -1].argmax())
     m.close()
