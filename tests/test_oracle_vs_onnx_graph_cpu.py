@@ -40,3 +40,23 @@ def test_encoder_and_decoder_graphs(exported):
             toks, lg = oracle.greedy(want, ids[:k], 1, 1030, [], [], return_logits=True)
             assert np.abs(logits[0, k - 1] - lg[0][0]).max() <= 1e-4
             assert int(logits[0, k - 1].argmax()) == toks[0][-1]
+
+
+def test_whisper_base_shape(wb, tmp_path):
+    """The same at the benchmarked architecture (d = 512, 8 heads, 6 + 6 layers, vocabulary 51865): one clip through the exported
+    encoder graph, one prompt through the exported decoder graph."""
+    try:
+        sd = torch_export.export(str(tmp_path), randomize=True, seed=3, shape="base")
+    except (ImportError, AttributeError) as e:
+        pytest.skip(f"torch.onnx TorchScript exporter not usable here: {e}")
+    mc = wb.weights.WHISPER_BASE
+    oracle = wr.WhisperRef(mc, {name: sd[name].reshape(shape) for name, shape, *_ in wb.weights.tensor_specs(mc)})
+    mel = np.random.default_rng(8).normal(0, 0.6, (1, 80, 3000)).astype(np.float32)
+    hidden = onnx_eval.run(str(tmp_path / "encoder_model.onnx"), {"input_features": mel})["last_hidden_state"]
+    want = oracle.encode(mel)
+    assert hidden.shape == want.shape == (1, 1500, 512) and np.abs(hidden - want).max() <= 1e-4
+    ids = [50258, 50259, 50359, 50363]
+    logits = onnx_eval.run(str(tmp_path / "decoder_model.onnx"), {"input_ids": np.array([ids], np.int64), "encoder_hidden_states": hidden,
+                                                                    "position_ids": np.arange(4, dtype=np.int64)[None]})["logits"]
+    toks, lg = oracle.greedy(want, ids, 1, 50257, [], [], return_logits=True)
+    assert np.abs(logits[0, -1] - lg[0][0]).max() <= 1e-4 and int(logits[0, -1].argmax()) == toks[0][-1]

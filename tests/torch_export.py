@@ -9,17 +9,24 @@ import os
 import warnings
 
 
-def export(out_dir: str, randomize: bool, seed: int = 0):
+SHAPES = {   # wb200.weights.WHISPER_TOY / WHISPER_BASE as HF config fields
+    "toy": dict(vocab_size=1031, d_model=128, layers=2, heads=2, ffn=256),
+    "base": dict(vocab_size=51865, d_model=512, layers=6, heads=8, ffn=2048),
+}
+
+
+def export(out_dir: str, randomize: bool, seed: int = 0, shape: str = "toy"):
     """-> HF state_dict as {name: float32 ndarray} (the names wb200.weights.tensor_specs uses)."""
     import torch
     from torch.onnx._internal.torchscript_exporter import onnx_proto_utils
     from transformers import WhisperConfig, WhisperForConditionalGeneration
 
     onnx_proto_utils._add_onnxscript_fn = lambda proto, custom_opsets: proto
-    cfg = WhisperConfig(vocab_size=1031, num_mel_bins=80, d_model=128, encoder_layers=2, decoder_layers=2, encoder_attention_heads=2,
-                        decoder_attention_heads=2, encoder_ffn_dim=256, decoder_ffn_dim=256, max_source_positions=1500,
-                        max_target_positions=448, pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=1,
-                        attn_implementation="eager")
+    sh = SHAPES[shape]
+    cfg = WhisperConfig(vocab_size=sh["vocab_size"], num_mel_bins=80, d_model=sh["d_model"], encoder_layers=sh["layers"],
+                        decoder_layers=sh["layers"], encoder_attention_heads=sh["heads"], decoder_attention_heads=sh["heads"],
+                        encoder_ffn_dim=sh["ffn"], decoder_ffn_dim=sh["ffn"], max_source_positions=1500, max_target_positions=448,
+                        pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=1, attn_implementation="eager")
     torch.manual_seed(seed)
     m = WhisperForConditionalGeneration(cfg).eval()
     if randomize:                       # HF initialises biases to 0 and LayerNorm weights to 1: make every tensor distinct
@@ -49,7 +56,7 @@ def export(out_dir: str, randomize: bool, seed: int = 0):
         warnings.simplefilter("ignore")
         torch.onnx.export(m.get_encoder(), (torch.randn(1, 80, 3000),), os.path.join(out_dir, "encoder_model.onnx"), dynamo=False,
                           opset_version=14, input_names=["input_features"], output_names=["last_hidden_state"])
-        torch.onnx.export(Decoder(m), (torch.tensor([[1, 5, 7, 9]]), torch.randn(1, 1500, 128), torch.tensor([[0, 1, 2, 3]])),
+        torch.onnx.export(Decoder(m), (torch.tensor([[1, 5, 7, 9]]), torch.randn(1, 1500, sh["d_model"]), torch.tensor([[0, 1, 2, 3]])),
                           os.path.join(out_dir, "decoder_model.onnx"), dynamo=False, opset_version=14,
                           input_names=["input_ids", "encoder_hidden_states", "position_ids"], output_names=["logits"])
     return {k: v.detach().numpy().astype("float32") for k, v in m.state_dict().items()}
