@@ -50,6 +50,17 @@ def test_whisper_base_shape(wb, tmp_path):
     except (ImportError, AttributeError) as e:
         pytest.skip(f"torch.onnx TorchScript exporter not usable here: {e}")
     mc = wb.weights.WHISPER_BASE
+    # the product's ONNX reader on the same files (a few representative tensors; every tensor is checked at the toy shape)
+    import ctypes as C
+    L = wb.lib()
+    L.wb_onnx_read_tensor.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_int64]
+    cfg = wb.default_cfg("base")
+    shapes = {name: shape for name, shape, *_ in wb.weights.tensor_specs(mc)}
+    for name in ["model.encoder.embed_positions.weight", "model.encoder.layers.3.fc1.weight", "model.decoder.embed_tokens.weight",
+                 "model.decoder.layers.5.encoder_attn.k_proj.weight", "model.decoder.layers.0.self_attn.out_proj.bias"]:
+        out = np.empty(shapes[name], np.float32)
+        assert L.wb_onnx_read_tensor(str(tmp_path).encode(), C.byref(cfg), name.encode(), out.ctypes.data_as(C.POINTER(C.c_float)), out.size) == 0, name
+        assert np.array_equal(out, sd[name].reshape(shapes[name])), name
     oracle = wr.WhisperRef(mc, {name: sd[name].reshape(shape) for name, shape, *_ in wb.weights.tensor_specs(mc)})
     mel = np.random.default_rng(8).normal(0, 0.6, (1, 80, 3000)).astype(np.float32)
     hidden = onnx_eval.run(str(tmp_path / "encoder_model.onnx"), {"input_features": mel})["last_hidden_state"]
